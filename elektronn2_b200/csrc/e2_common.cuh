@@ -1,0 +1,71 @@
+// Shared internals of libe2b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "e2b200.h"
+
+struct e2_handle {
+  int device;
+  int sm_count;
+  int64_t launches;
+  char err[512];
+  void* tmap_cache;  // tcgen05 path: host-side tensor-map cache (opaque)
+};
+
+static inline int e2_fail(e2_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define E2_REQUIRE(h, cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return e2_fail((h), E2_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define E2_CUDA_CHECK(h, what)                                                                       \
+  do {                                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                            \
+    if (e__ != cudaSuccess) return e2_fail((h), E2_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline bool e2_tensor_ok(const e2_tensor* t) {
+  return t && t->n > 0 && t->z > 0 && t->x > 0 && t->y > 0 && t->c > 0 && t->c_pitch >= t->c;
+}
+static inline int64_t e2_positions(const e2_tensor* t) { return (int64_t)t->n * t->z * t->x * t->y; }
+
+static inline int e2_grid_1d(int64_t work, int threads, int sm_count, int max_waves = 32) {
+  int64_t g = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+__device__ __forceinline__ float e2_apply_act(float v, int act) {
+  switch (act) {
+    case E2_ACT_RELU: return v > 0.f ? v : 0.f;
+    case E2_ACT_TANH: return tanhf(v);
+    case E2_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case E2_ACT_ABS: return fabsf(v);
+    default: return v;
+  }
+}
+
+// round-to-nearest fp32 -> tf32 (kept in an fp32 container)
+__device__ __forceinline__ float e2_round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// internal launchers shared between translation units
+int e2_conv_tc_supported(const e2_handle* h, int c_in, int c_out, int c_in_pitch, int c_out_pitch);

@@ -1,0 +1,46 @@
+// Problem descriptions shared by the CUDA-core and tcgen05 conv kernels (internal).
+#pragma once
+#include "e2_common.cuh"
+
+// C[m, n] = sum_{tap,k} A[pos(m)*s + tap + org][k] * B[n*b_row + tap*b_tap + k]
+struct GatherGemm {
+  const float* A;
+  int a_pitch, K;
+  int An, Az, Ax, Ay;
+  const float* B;
+  int64_t b_row, b_tap;
+  float* C;
+  int c_pitch, N;
+  int On, Oz, Ox, Oy;  // output position grid (GEMM M)
+  int tz, tx, ty;      // taps
+  int oz, ox, oy;      // origin
+  int sz, sx, sy;      // position stride
+  const float* bias;
+  int act, accumulate, round_tf32;
+  int shuffle, pz, px, py, Fo;  // pixel-shuffle epilogue (upconv fwd)
+};
+
+// W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]
+struct ReduceGemm {
+  const float* P;
+  int p_pitch, R;
+  int Mn, Mz, Mx, My;
+  const float* Q;
+  int q_pitch, S;
+  int Qn, Qz, Qx, Qy;
+  int tz, tx, ty, oz, ox, oy, sz, sx, sy;
+  float* W;
+  int out_mode;  // 0: dw[r][s][flip(tap)] (conv)   1: dw[s][r][tap] (upconv)
+};
+
+int e2_launch_gather_gemm_ffma(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+int e2_launch_reduce_gemm_ffma(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+int e2_launch_conv_c1_fwd(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+int e2_launch_conv_c1_wgrad(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pitch, float* db, cudaStream_t s);
+
+// tcgen05 path (e2_conv_tc.cu)
+bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g);
+int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
+int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);

@@ -1,0 +1,546 @@
+// Bandwidth-bound kernels: 3-D max-pool (+argmax, optional fused +bias->act), its
+// backward, max-fragment-pooling fwd/bwd, fragments->dense fwd/bwd, crop+concat fwd/bwd.
+// All tensors are channels-last; one thread owns V consecutive channels of one output
+// position, so a warp reads/writes 32*V contiguous floats (V=4: 512 B) per window tap.
+#include <initializer_list>
+#include "e2_common.cuh"
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <int V>
+struct IVec;
+template <>
+struct IVec<1> {
+  int v[1];
+  __device__ __forceinline__ void load(const int* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void store(int* p) const { p[0] = v[0]; }
+};
+template <>
+struct IVec<4> {
+  int v[4];
+  __device__ __forceinline__ void load(const int* p) {
+    int4 t = __ldg(reinterpret_cast<const int4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(int* p) const { *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]); }
+};
+
+static inline bool vec4_ok(std::initializer_list<const void*> ptrs, std::initializer_list<int> counts) {
+  for (const void* p : ptrs)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  for (int c : counts)
+    if (c & 3) return false;
+  return true;
+}
+
+struct PoolP {
+  int n, Z, X, Y, C, xp;  // input dims, input pitch
+  int Zo, Xo, Yo, yp;     // output dims, output pitch
+  int pz, px, py;
+  int act, has_bias, tie, accumulate;
+};
+
+// ------------------------------------------------------------------ max-pool forward
+template <int V>
+__global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, const float* __restrict__ x, const float* __restrict__ bias,
+                                                     float* __restrict__ y, int* __restrict__ amax) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Zo * p.Xo * p.Yo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yo = (int)(pos % p.Yo);
+    int64_t t = pos / p.Yo;
+    int xo = (int)(t % p.Xo);
+    t /= p.Xo;
+    int zo = (int)(t % p.Zo);
+    int n = (int)(t / p.Zo);
+    float best[V];
+    int bi[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) best[j] = -INFINITY, bi[j] = 0;
+    bool first = true;
+    for (int dz = 0; dz < p.pz; ++dz)
+      for (int dx = 0; dx < p.px; ++dx)
+        for (int dy = 0; dy < p.py; ++dy) {
+          int zz = zo * p.pz + dz, xx = xo * p.px + dx, yy = yo * p.py + dy;
+          int lin = (zz * p.X + xx) * p.Y + yy;
+          Vec<V> v;
+          v.load(x + ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            // strict '>' keeps the FIRST maximum in (z,x,y) scan order
+            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin;
+          }
+          first = false;
+        }
+    Vec<V> o;
+    IVec<V> oi;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float r = best[j];
+      if (p.has_bias) r += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
+      o.v[j] = e2_apply_act(r, p.act);
+      oi.v[j] = bi[j];
+    }
+    int64_t oofs = pos * p.yp + c;
+    o.store(y + oofs);
+    if (amax) oi.store(amax + oofs);
+  }
+}
+
+// ----------------------------------------------------------------- max-pool backward
+// Windows do not overlap and tile the input, so each dx element is written exactly once.
+template <int V>
+__global__ void __launch_bounds__(256) k_maxpool_bwd(PoolP p, const float* __restrict__ dy, const int* __restrict__ amax,
+                                                     const float* __restrict__ x, float* __restrict__ dx) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Zo * p.Xo * p.Yo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yo = (int)(pos % p.Yo);
+    int64_t t = pos / p.Yo;
+    int xo = (int)(t % p.Xo);
+    t /= p.Xo;
+    int zo = (int)(t % p.Zo);
+    int n = (int)(t / p.Zo);
+    Vec<V> g;
+    g.load(dy + pos * p.yp + c);
+    IVec<V> am;
+    float mx[V];
+    if (p.tie == E2_TIE_FIRST) {
+      am.load(amax + pos * p.yp + c);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) mx[j] = -INFINITY;
+      for (int dz = 0; dz < p.pz; ++dz)
+        for (int dxx = 0; dxx < p.px; ++dxx)
+          for (int dyy = 0; dyy < p.py; ++dyy) {
+            int lin = ((zo * p.pz + dz) * p.X + xo * p.px + dxx) * p.Y + yo * p.py + dyy;
+            Vec<V> v;
+            v.load(x + ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c);
+#pragma unroll
+            for (int j = 0; j < V; ++j) mx[j] = fmaxf(mx[j], v.v[j]);
+          }
+    }
+    for (int dz = 0; dz < p.pz; ++dz)
+      for (int dxx = 0; dxx < p.px; ++dxx)
+        for (int dyy = 0; dyy < p.py; ++dyy) {
+          int lin = ((zo * p.pz + dz) * p.X + xo * p.px + dxx) * p.Y + yo * p.py + dyy;
+          int64_t ofs = ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c;
+          Vec<V> o;
+          if (p.tie == E2_TIE_FIRST) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] = (am.v[j] == lin) ? g.v[j] : 0.f;
+          } else {
+            Vec<V> v;
+            v.load(x + ofs);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] = (v.v[j] == mx[j]) ? g.v[j] : 0.f;
+          }
+          if (p.accumulate) {
+            Vec<V> old;
+            old.load(dx + ofs);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o.v[j] += old.v[j];
+          }
+          o.store(dx + ofs);
+        }
+  }
+}
+
+static int fill_pool(e2_handle* h, const e2_pool_desc* d, PoolP* p) {
+  E2_REQUIRE(h, d && e2_tensor_ok(&d->x) && e2_tensor_ok(&d->y), "maxpool3d: bad descriptor");
+  E2_REQUIRE(h, d->pz >= 1 && d->px >= 1 && d->py >= 1, "maxpool3d: pool factors must be >= 1");
+  // Pool._calc_shape (neural.py:1543-1546) / Conv._calc_shape (:746-750): axes must divide
+  E2_REQUIRE(h, d->x.z % d->pz == 0 && d->x.x % d->px == 0 && d->x.y % d->py == 0,
+             "maxpool3d: cannot downsample (%d,%d,%d) by (%d,%d,%d)", d->x.z, d->x.x, d->x.y, d->pz, d->px, d->py);
+  E2_REQUIRE(h, d->y.z == d->x.z / d->pz && d->y.x == d->x.x / d->px && d->y.y == d->x.y / d->py && d->y.n == d->x.n &&
+                    d->y.c == d->x.c,
+             "maxpool3d: output extents do not match input/pool");
+  E2_REQUIRE(h, (int64_t)d->x.z * d->x.x * d->x.y < (1ll << 31), "maxpool3d: volume too large for int32 argmax");
+  p->n = d->x.n, p->Z = d->x.z, p->X = d->x.x, p->Y = d->x.y, p->C = d->x.c, p->xp = d->x.c_pitch;
+  p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
+  p->pz = d->pz, p->px = d->px, p->py = d->py;
+  p->act = d->act, p->has_bias = d->has_bias, p->tie = d->tie_mode, p->accumulate = d->accumulate;
+  return E2_OK;
+}
+
+extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,
+                                int32_t* argmax, void* stream) {
+  PoolP p;
+  int rc = fill_pool(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, x && y && (!d->has_bias || bias), "maxpool3d_fwd: null pointer");
+  int64_t work = e2_positions(&d->y) * d->y.c;
+  if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp})) {
+    k_maxpool_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+  } else {
+    k_maxpool_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+  }
+  h->launches++;
+  E2_CUDA_CHECK(h, "maxpool3d_fwd");
+  return E2_OK;
+}
+
+extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax,
+                                const float* x, float* dx, void* stream) {
+  PoolP p;
+  int rc = fill_pool(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, dy && dx, "maxpool3d_bwd: null pointer");
+  E2_REQUIRE(h, d->tie_mode == E2_TIE_FIRST ? argmax != nullptr : x != nullptr,
+             "maxpool3d_bwd: tie_mode FIRST needs argmax, tie_mode ALL needs x");
+  int64_t work = e2_positions(&d->y) * d->y.c;
+  if (vec4_ok({dy, dx, argmax, x}, {p.C, p.xp, p.yp})) {
+    k_maxpool_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx);
+  } else {
+    k_maxpool_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx);
+  }
+  h->launches++;
+  E2_CUDA_CHECK(h, "maxpool3d_bwd");
+  return E2_OK;
+}
+
+// --------------------------------------------------------------- MFP forward / backward
+// One pass produces all prod(p) fragments (the reference issues prod(p) pool ops + a
+// concat copy, computations.py:665-674).  Fragment index = off_idx * n_in + n_old with
+// off_idx = (iz*px + ix)*py + iy  (itertools.product order, last axis fastest).
+template <int V>
+__global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, const float* __restrict__ x, const float* __restrict__ bias,
+                                                 float* __restrict__ y, int* __restrict__ amax) {
+  const int cv = p.C / V;
+  const int nfr = p.n * p.pz * p.px * p.py;
+  const int64_t total = (int64_t)nfr * p.Zo * p.Xo * p.Yo * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yo = (int)(pos % p.Yo);
+    int64_t t = pos / p.Yo;
+    int xo = (int)(t % p.Xo);
+    t /= p.Xo;
+    int zo = (int)(t % p.Zo);
+    int fr = (int)(t / p.Zo);
+    int n = fr % p.n, off = fr / p.n;
+    int iy = off % p.py, ix = (off / p.py) % p.px, iz = off / (p.py * p.px);
+    float best[V];
+    int bi[V];
+    bool first = true;
+#pragma unroll
+    for (int j = 0; j < V; ++j) best[j] = -INFINITY, bi[j] = 0;
+    for (int dz = 0; dz < p.pz; ++dz)
+      for (int dx = 0; dx < p.px; ++dx)
+        for (int dy = 0; dy < p.py; ++dy) {
+          int lin = ((iz + zo * p.pz + dz) * p.X + ix + xo * p.px + dx) * p.Y + iy + yo * p.py + dy;
+          Vec<V> v;
+          v.load(x + ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin;
+          first = false;
+        }
+    Vec<V> o;
+    IVec<V> oi;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float r = best[j];
+      if (p.has_bias) r += __ldg(bias + c + j);
+      o.v[j] = e2_apply_act(r, p.act);
+      oi.v[j] = bi[j];
+    }
+    o.store(y + pos * p.yp + c);
+    if (amax) oi.store(amax + pos * p.yp + c);
+  }
+}
+
+// Gather form (no atomics, deterministic): each input element checks the prod(p) windows
+// (one per fragment offset) that contain it.
+template <int V>
+__global__ void __launch_bounds__(256) k_mfp_bwd(PoolP p, const float* __restrict__ dy, const int* __restrict__ amax,
+                                                 float* __restrict__ dx) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yy = (int)(pos % p.Y);
+    int64_t t = pos / p.Y;
+    int xx = (int)(t % p.X);
+    t /= p.X;
+    int zz = (int)(t % p.Z);
+    int n = (int)(t / p.Z);
+    int lin = (zz * p.X + xx) * p.Y + yy;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int iz = 0; iz < p.pz; ++iz) {
+      int rz = zz - iz;
+      if (rz < 0) continue;
+      int zo = rz / p.pz;
+      if (zo >= p.Zo) continue;
+      for (int ix = 0; ix < p.px; ++ix) {
+        int rx = xx - ix;
+        if (rx < 0) continue;
+        int xo = rx / p.px;
+        if (xo >= p.Xo) continue;
+        for (int iy = 0; iy < p.py; ++iy) {
+          int ry = yy - iy;
+          if (ry < 0) continue;
+          int yo = ry / p.py;
+          if (yo >= p.Yo) continue;
+          int fr = ((iz * p.px + ix) * p.py + iy) * p.n + n;
+          int64_t o = ((((int64_t)fr * p.Zo + zo) * p.Xo + xo) * p.Yo + yo) * p.yp + c;
+          IVec<V> am;
+          am.load(amax + o);
+          Vec<V> g;
+          g.load(dy + o);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (am.v[j] == lin) acc[j] += g.v[j];
+        }
+      }
+    }
+    Vec<V> o;
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = acc[j];
+    o.store(dx + pos * p.xp + c);
+  }
+}
+
+static int fill_mfp(e2_handle* h, const e2_mfp_desc* d, PoolP* p) {
+  E2_REQUIRE(h, d && e2_tensor_ok(&d->x) && e2_tensor_ok(&d->y), "mfp: bad descriptor");
+  E2_REQUIRE(h, d->pz >= 1 && d->px >= 1 && d->py >= 1, "mfp: pool factors must be >= 1");
+  // Conv._calc_shape MFP rule (neural.py:739-744): (S - p + 1) % p == 0
+  E2_REQUIRE(h, (d->x.z - d->pz + 1) % d->pz == 0 && (d->x.x - d->px + 1) % d->px == 0 && (d->x.y - d->py + 1) % d->py == 0,
+             "mfp: cannot pool (%d,%d,%d) by (%d,%d,%d) using MFP", d->x.z, d->x.x, d->x.y, d->pz, d->px, d->py);
+  E2_REQUIRE(h, d->y.n == d->x.n * d->pz * d->px * d->py && d->y.z == (d->x.z - d->pz + 1) / d->pz &&
+                    d->y.x == (d->x.x - d->px + 1) / d->px && d->y.y == (d->x.y - d->py + 1) / d->py && d->y.c == d->x.c,
+             "mfp: output extents do not match input/pool");
+  E2_REQUIRE(h, (int64_t)d->x.z * d->x.x * d->x.y < (1ll << 31), "mfp: volume too large for int32 argmax");
+  p->n = d->x.n, p->Z = d->x.z, p->X = d->x.x, p->Y = d->x.y, p->C = d->x.c, p->xp = d->x.c_pitch;
+  p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
+  p->pz = d->pz, p->px = d->px, p->py = d->py;
+  p->act = d->act, p->has_bias = d->has_bias, p->tie = 0, p->accumulate = 0;
+  return E2_OK;
+}
+
+extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, const float* bias, float* y,
+                          int32_t* argmax, void* stream) {
+  PoolP p;
+  int rc = fill_mfp(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, x && y && (!d->has_bias || bias), "mfp_fwd: null pointer");
+  int64_t work = e2_positions(&d->y) * d->y.c;
+  if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp}))
+    k_mfp_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+  else
+    k_mfp_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+  h->launches++;
+  E2_CUDA_CHECK(h, "mfp_fwd");
+  return E2_OK;
+}
+
+extern "C" int e2_mfp_bwd(e2_handle* h, const e2_mfp_desc* d, const float* dy, const int32_t* argmax, float* dx,
+                          void* stream) {
+  PoolP p;
+  int rc = fill_mfp(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, dy && argmax && dx, "mfp_bwd: null pointer");
+  int64_t work = e2_positions(&d->x) * d->x.c;
+  if (vec4_ok({dy, dx, argmax}, {p.C, p.xp, p.yp}))
+    k_mfp_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx);
+  else
+    k_mfp_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx);
+  h->launches++;
+  E2_CUDA_CHECK(h, "mfp_bwd");
+  return E2_OK;
+}
+
+// ------------------------------------------------------------- fragments <-> dense
+struct F2DP {
+  int nfr, Z, X, Y, C, fp, dp;
+  int sz, sx, sy;
+};
+
+template <int V, bool FWD>
+__global__ void __launch_bounds__(256) k_f2d(F2DP p, const float* __restrict__ src, const int* __restrict__ offs,
+                                             float* __restrict__ dst) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.nfr * p.Z * p.X * p.Y * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yy = (int)(pos % p.Y);
+    int64_t t = pos / p.Y;
+    int xx = (int)(t % p.X);
+    t /= p.X;
+    int zz = (int)(t % p.Z);
+    int fr = (int)(t / p.Z);
+    int oz = __ldg(offs + fr * 3), ox = __ldg(offs + fr * 3 + 1), oy = __ldg(offs + fr * 3 + 2);
+    int64_t dpos = ((int64_t)(zz * p.sz + oz) * (p.X * p.sx) + (xx * p.sx + ox)) * (p.Y * p.sy) + (yy * p.sy + oy);
+    Vec<V> v;
+    if (FWD) {
+      v.load(src + pos * p.fp + c);
+      v.store(dst + dpos * p.dp + c);
+    } else {
+      v.load(src + dpos * p.dp + c);
+      v.store(dst + pos * p.fp + c);
+    }
+  }
+}
+
+static int f2d_launch(e2_handle* h, const e2_f2d_desc* d, const float* src, const int32_t* offs, float* dst, bool fwd,
+                      void* stream) {
+  E2_REQUIRE(h, d && e2_tensor_ok(&d->frag) && e2_tensor_ok(&d->dense) && src && dst && offs, "frag2dense: bad arguments");
+  // FragmentsToDense._make_output (neural.py:873-875)
+  E2_REQUIRE(h, d->frag.n == d->sz * d->sx * d->sy, "frag2dense: need %d fragments on the batch axis, got %d",
+             d->sz * d->sx * d->sy, d->frag.n);
+  E2_REQUIRE(h, d->dense.n == 1 && d->dense.z == d->frag.z * d->sz && d->dense.x == d->frag.x * d->sx &&
+                    d->dense.y == d->frag.y * d->sy && d->dense.c == d->frag.c,
+             "frag2dense: dense extents do not match fragments*strides");
+  F2DP p = {d->frag.n, d->frag.z, d->frag.x, d->frag.y, d->frag.c, d->frag.c_pitch, d->dense.c_pitch, d->sz, d->sx, d->sy};
+  int64_t work = e2_positions(&d->frag) * d->frag.c;
+  bool v4 = vec4_ok({src, dst}, {p.C, p.fp, p.dp});
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fwd) {
+    if (v4) k_f2d<4, true><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
+    else k_f2d<1, true><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
+  } else {
+    if (v4) k_f2d<4, false><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
+    else k_f2d<1, false><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
+  }
+  h->launches++;
+  E2_CUDA_CHECK(h, "frag2dense");
+  return E2_OK;
+}
+
+extern "C" int e2_frag2dense_fwd(e2_handle* h, const e2_f2d_desc* d, const float* frag, const int32_t* offsets,
+                                 float* dense, void* stream) {
+  return f2d_launch(h, d, frag, offsets, dense, true, stream);
+}
+extern "C" int e2_frag2dense_bwd(e2_handle* h, const e2_f2d_desc* d, const float* ddense, const int32_t* offsets,
+                                 float* dfrag, void* stream) {
+  return f2d_launch(h, d, ddense, offsets, dfrag, false, stream);
+}
+
+// -------------------------------------------------------------------- crop + concat
+struct CropP {
+  int n, Z, X, Y, C, sp;   // src
+  int Zd, Xd, Yd, dp, c0;  // dst
+  int oz, ox, oy, accumulate;
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) k_crop_fwd(CropP p, const float* __restrict__ src, float* __restrict__ dst) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Zd * p.Xd * p.Yd * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yy = (int)(pos % p.Yd);
+    int64_t t = pos / p.Yd;
+    int xx = (int)(t % p.Xd);
+    t /= p.Xd;
+    int zz = (int)(t % p.Zd);
+    int n = (int)(t / p.Zd);
+    int64_t spos = (((int64_t)n * p.Z + zz + p.oz) * p.X + xx + p.ox) * p.Y + yy + p.oy;
+    Vec<V> v;
+    v.load(src + spos * p.sp + c);
+    v.store(dst + pos * p.dp + p.c0 + c);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restrict__ ddst, float* __restrict__ dsrc) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    int64_t pos = i / cv;
+    int yy = (int)(pos % p.Y);
+    int64_t t = pos / p.Y;
+    int xx = (int)(t % p.X);
+    t /= p.X;
+    int zz = (int)(t % p.Z);
+    int n = (int)(t / p.Z);
+    int zd = zz - p.oz, xd = xx - p.ox, yd = yy - p.oy;
+    bool inside = zd >= 0 && zd < p.Zd && xd >= 0 && xd < p.Xd && yd >= 0 && yd < p.Yd;
+    Vec<V> v;
+    if (inside) {
+      int64_t dpos = (((int64_t)n * p.Zd + zd) * p.Xd + xd) * p.Yd + yd;
+      v.load(ddst + dpos * p.dp + p.c0 + c);
+      if (p.accumulate) {
+        Vec<V> old;
+        old.load(dsrc + pos * p.sp + c);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v.v[j] += old.v[j];
+      }
+      v.store(dsrc + pos * p.sp + c);
+    } else if (!p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v.v[j] = 0.f;
+      v.store(dsrc + pos * p.sp + c);
+    }
+  }
+}
+
+static int fill_crop(e2_handle* h, const e2_crop_desc* d, CropP* p) {
+  E2_REQUIRE(h, d && e2_tensor_ok(&d->src) && e2_tensor_ok(&d->dst), "crop_concat: bad descriptor");
+  E2_REQUIRE(h, d->oz >= 0 && d->ox >= 0 && d->oy >= 0, "crop_concat: negative crop");
+  E2_REQUIRE(h, d->dst.z == d->src.z - 2 * d->oz && d->dst.x == d->src.x - 2 * d->ox && d->dst.y == d->src.y - 2 * d->oy &&
+                    d->dst.n == d->src.n,
+             "crop_concat: destination extents do not match source minus 2*crop");
+  E2_REQUIRE(h, d->dst_c0 >= 0 && d->dst_c0 + d->src.c <= d->dst.c, "crop_concat: channel slice [%d,%d) outside %d",
+             d->dst_c0, d->dst_c0 + d->src.c, d->dst.c);
+  *p = CropP{d->src.n, d->src.z, d->src.x, d->src.y, d->src.c, d->src.c_pitch, d->dst.z, d->dst.x, d->dst.y,
+             d->dst.c_pitch, d->dst_c0, d->oz, d->ox, d->oy, d->accumulate};
+  return E2_OK;
+}
+
+extern "C" int e2_crop_concat_fwd(e2_handle* h, const e2_crop_desc* d, const float* src, float* dst, void* stream) {
+  CropP p;
+  int rc = fill_crop(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, src && dst, "crop_concat_fwd: null pointer");
+  int64_t work = e2_positions(&d->dst) * d->src.c;
+  if (vec4_ok({src, dst}, {p.C, p.sp, p.dp, p.c0}))
+    k_crop_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, src, dst);
+  else
+    k_crop_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, src, dst);
+  h->launches++;
+  E2_CUDA_CHECK(h, "crop_concat_fwd");
+  return E2_OK;
+}
+
+extern "C" int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc, void* stream) {
+  CropP p;
+  int rc = fill_crop(h, d, &p);
+  if (rc) return rc;
+  E2_REQUIRE(h, ddst && dsrc, "crop_concat_bwd: null pointer");
+  int64_t work = e2_positions(&d->src) * d->src.c;
+  if (vec4_ok({ddst, dsrc}, {p.C, p.sp, p.dp, p.c0}))
+    k_crop_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc);
+  else
+    k_crop_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc);
+  h->launches++;
+  E2_CUDA_CHECK(h, "crop_concat_bwd");
+  return E2_OK;
+}

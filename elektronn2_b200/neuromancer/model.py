@@ -1,0 +1,294 @@
+"""Model: the caller of the hot path (reference: neuromancer/model.py).
+
+Mirrors ``Model.designate_nodes`` (model.py:95-227), ``trainingstep`` (:548-600),
+``loss / gradients / predict / predict_ext / predict_dense`` (:237-255),
+``get/set_param_values``, ``test_run_prediction`` and the MFP re-build done by
+``modelload`` / ``rebuild_model`` (:623-729, 848-867).  Instead of compiling Theano
+functions, each entry point owns a static launch plan (``executor.Plan``).
+"""
+from collections import OrderedDict
+import logging
+import pickle
+import time
+
+import numpy as np
+
+from .node_basic import Node, Input, model_manager
+from .neural import Conv, FragmentsToDense
+from .loss import Softmax
+from . import optimiser
+from .shapecalc import unet_fov_backfill, closest_valid_patch_size
+
+logger = logging.getLogger('elektronn2log')
+
+
+class Model(object):
+    def __init__(self, name=""):
+        self.name = name
+        self.nodes = OrderedDict()
+        self.node_descriptors = OrderedDict()
+        self.input_node = self.target_node = self.loss_node = None
+        self.prediction_node = self.error_node = None
+        self.prediction_ext, self.debug_outputs = [], []
+        self._desig_descr = {}
+        self.trainable_params, self.nontrainable_params = [], OrderedDict()
+        self.optimisers = {}
+        self.batch_size = None
+        self.ndim = None
+        self.iterations = 0
+        self.elapsed_time = 0.0
+        self._last_exec_times, self._last_losses = [], []
+        self._store = None
+        self._train_plans, self._ext_plans = {}, {}
+        self.data_parallel = None  # set by parallel.DataParallel
+
+    # -- registration ------------------------------------------------------------
+    def register_node(self, node, name, cls, args, kwargs):
+        self.nodes[name] = node
+        self.node_descriptors[name] = (cls, args, kwargs)
+
+    def __getitem__(self, slice):
+        if isinstance(slice, str):
+            return self.nodes[slice]
+        return list(self.nodes.values())[slice]
+
+    def __repr__(self):
+        return "\n".join(repr(n) for n in self.nodes.values())
+
+    # -- designation (model.py:95-227) ---------------------------------------------
+    def designate_nodes(self, input_node='input', target_node=None, loss_node=None, prediction_node=None,
+                        prediction_ext=None, error_node=None, debug_outputs=None):
+        def resolve(v):
+            if v is None:
+                return None
+            if isinstance(v, (list, tuple)):
+                return [resolve(x) for x in v]
+            return self.nodes[v if isinstance(v, str) else v.name]
+
+        self.input_node = resolve(input_node)
+        self.target_node = resolve(target_node)
+        self.loss_node = resolve(loss_node)
+        self.prediction_node = resolve(prediction_node)
+        self.error_node = resolve(error_node)
+        self.prediction_ext = resolve(prediction_ext) or []
+        self.debug_outputs = resolve(debug_outputs) or []
+        self._desig_descr = dict(input_node=input_node, target_node=target_node, loss_node=loss_node,
+                                 prediction_node=prediction_node, prediction_ext=prediction_ext,
+                                 error_node=error_node, debug_outputs=debug_outputs)
+        if self.prediction_node is not None:
+            psh = self.prediction_node.shape
+            self.batch_size = psh['b']
+            self.ndim = psh.ndim
+            if np.any(np.less(psh.fov, 0)):  # UpConvs contained: back-fill the fov (model.py:141-152)
+                diff = unet_fov_backfill(self.input_node.shape.spatial_shape, psh.spatial_shape, psh.strides)
+                self.prediction_node.shape._fov = diff
+                if self.target_node is not None:
+                    self.target_node.shape._fov = diff
+            elif not psh.fov_all_centered:
+                logger.warning("Not all field of views are centered (odd) this might cause problems for many setups")
+        if self.loss_node is not None:
+            self.trainable_params = list(self.loss_node.all_trainable_params.values())
+            self.nontrainable_params = self.loss_node.all_nontrainable_params
+            self.optimisers = dict(SGD=optimiser.SGD(self), Adam=optimiser.Adam(self))
+
+    # -- parameters ------------------------------------------------------------------
+    def _all_named_params(self):
+        out = OrderedDict()
+        for n in self.nodes.values():
+            for k, p in n.params.items():
+                if p.apply_train:
+                    out["%s_%s" % (n.name, k)] = p
+        return out
+
+    def _ensure_param_store(self, device):
+        if self._store is None:
+            from .executor import ParamStore
+            self._store = ParamStore(self._all_named_params().items(), device)
+        return self._store
+
+    def get_param_values(self, skip_const=True, as_list=False):
+        if as_list:
+            return [n.get_param_values(skip_const) for n in self.nodes.values()]
+        return OrderedDict((name, n.get_param_values(skip_const)) for name, n in self.nodes.items())
+
+    def set_param_values(self, value_dict, skip_const=True):
+        for k, v in value_dict.items():
+            self.nodes[k].set_param_values(v, skip_const)
+
+    # -- execution -------------------------------------------------------------------
+    def _train_plan(self, batch):
+        from .executor import Plan
+        if batch not in self._train_plans:
+            outs = [self.loss_node] + [n for n in self.prediction_ext if n is not self.loss_node]
+            self._train_plans[batch] = Plan(self, outs, batch, train=True)
+        return self._train_plans[batch]
+
+    def _feed_dict(self, plan, args):
+        srcs = [n for n in [self.input_node, self.target_node] if n is not None and n in plan.inputs]
+        extra = [n for n in plan.inputs if n not in srcs]
+        srcs += extra
+        if len(args) != len(srcs):
+            raise ValueError("expected %d input arrays %s, got %d" % (len(srcs), [n.name for n in srcs], len(args)))
+        return dict(zip(srcs, args))
+
+    def trainingstep(self, *args, **kwargs):
+        """One optimiser iteration: ``trainingstep(data, target, optimiser='Adam')``
+        -> (loss, time, extra) (model.py:548-600).  The returned loss is the one
+        computed in the same pass as the gradients (before the update)."""
+        opt_name = kwargs.get('optimiser', 'SGD')
+        if opt_name not in self.optimisers:
+            logger.warning("No optimiser '%s'. Falling back to SGD" % (opt_name,))
+            opt_name = 'SGD'
+        opt = self.optimisers[opt_name]
+        t0 = time.time()
+        plan = self._train_plan(np.shape(args[0])[0])
+        plan.feed(self._feed_dict(plan, args))
+        plan.execute()
+        if self.data_parallel is not None:
+            self.data_parallel.allreduce_gradients(plan.store)
+        opt.step(plan.store)
+        loss = np.float32(plan.loss_op.read()[0])  # the only device->host sync of the step
+        if kwargs.get('update_loss', False):
+            loss = self.loss(*args)
+        t = time.time() - t0
+        opt.last_exec_time = t
+        self.elapsed_time += t
+        self._last_exec_times.append(t + 1e-10)
+        self._last_losses.append(loss)
+        self.iterations += 1
+        return loss, t, None
+
+    def loss(self, *args, **kwargs):
+        return self.loss_node(*args)
+
+    def gradients(self, *args, **kwargs):
+        """d loss / d trainable_params, in ``self.trainable_params`` order (model.py:182-185)."""
+        plan = self._train_plan(np.shape(args[0])[0])
+        plan.feed(self._feed_dict(plan, args))
+        plan.execute()
+        return [p._grad.detach().cpu().numpy().copy() for p in self.trainable_params]
+
+    def predict(self, *args, **kwargs):
+        return self.prediction_node(*args)
+
+    def predict_ext(self, *args, **kwargs):
+        from .executor import Plan
+        b = np.shape(args[0])[0]
+        if b not in self._ext_plans:
+            self._ext_plans[b] = Plan(self, self.prediction_ext, b)
+        plan = self._ext_plans[b]
+        return plan.run(self._feed_dict(plan, args))
+
+    def predict_dense(self, raw_img, as_uint8=False, pad_raw=False):
+        return self.prediction_node.predict_dense(raw_img, as_uint8=as_uint8, pad_raw=pad_raw)
+
+    def test_run_prediction(self):
+        return self.prediction_node.test_run()
+
+    # -- persistence (weights only; the .mdl descriptor format is SURVEY 8f-3) ---------
+    def save(self, file_name):
+        with open(file_name, 'wb') as f:
+            pickle.dump(dict(name=self.name, params=self.get_param_values()), f, protocol=2)
+
+    def load_params(self, file_name):
+        with open(file_name, 'rb') as f:
+            d = pickle.load(f)
+        self.set_param_values(d['params'])
+
+
+def kernel_lists_from_node_descr(model):
+    """(filter_shapes, pool_shapes, mfp) of the Conv nodes in graph order (model.py:871-895)."""
+    f, p, m = [], [], []
+    for n in model.nodes.values():
+        if type(n) is Conv:
+            f.append(list(n.filter_shape)), p.append(list(n.pool_shape)), m.append(bool(n.mfp))
+    return f, p, m
+
+
+def rebuild_model(model, override_mfp_to_active=False, imposed_patch_size=None, imposed_batch_size=None, name=None):
+    """Re-create ``model`` with the same parameters but MFP switched on and / or another
+    patch size: what ``modelload(..., override_mfp_to_active=True, imposed_patch_size=...)``
+    does to a saved model (model.py:623-729): every node whose class is exactly ``Conv``
+    gets ``mfp=True`` (graphmanager.py:183-185), a ``FragmentsToDense`` is injected in
+    front of the prediction (Softmax) node (model.py:668-689), and the patch size is
+    snapped to an MFP-valid one."""
+    filters, pools, mfps = kernel_lists_from_node_descr(model)
+    old_patch = model.input_node.shape.spatial_shape
+    if override_mfp_to_active:
+        mfps = [True] * len(mfps)
+        if imposed_patch_size is None:
+            imposed_patch_size = old_patch
+    patch = None
+    if imposed_patch_size is not None:
+        if len(imposed_patch_size) != len(old_patch):
+            raise ValueError("Dimensionality of patch size and imposed patchsize do not match.")
+        patch = closest_valid_patch_size(filters, pools, imposed_patch_size, mfps)
+        if list(patch) != list(imposed_patch_size):
+            logger.info("patch_size %s changed to %s (size not possible)" % (list(imposed_patch_size), list(patch)))
+    new = model_manager.newmodel(name or ("%s_rebuilt_%d" % (model.name, len(model_manager.models))))
+    mapping = {}
+
+    def remap(v):
+        if isinstance(v, Node):
+            return mapping[id(v)]
+        if isinstance(v, (list, tuple)):
+            return type(v)(remap(x) for x in v)
+        return v
+
+    pred_name = model.prediction_node.name if model.prediction_node is not None else None
+    for nm_, (cls, args, kwargs) in model.node_descriptors.items():
+        old = model.nodes[nm_]
+        try:
+            args = [remap(a) for a in args]
+            kwargs = {k: remap(v) for k, v in kwargs.items()}
+        except KeyError:
+            continue  # depends on a node that did not survive the re-build
+        kwargs['print_repr'] = False
+        if cls is Input and old is model.input_node:
+            sh = list(old.shape.shape)
+            if patch is not None:
+                for ax, s in zip(old.shape.spatial_axes, patch):
+                    sh[ax] = int(s)
+            if imposed_batch_size is not None:
+                sh[old.shape.tag2index('b')] = imposed_batch_size
+            elif override_mfp_to_active:
+                sh[old.shape.tag2index('b')] = 1  # MFP needs raw batch 1 (neural.py:667-668)
+            args = [sh] + list(args[1:])
+        if cls is Conv and override_mfp_to_active:
+            kwargs['mfp'] = True
+            if len(args) > 6:
+                args = list(args)
+                args[6] = True
+        for pk in ('w', 'b'):
+            if pk in old.params and issubclass(cls, Conv):
+                kwargs[pk] = old.params[pk].get_value()
+        if issubclass(cls, Conv) and 'identity_init' in cls.__init__.__code__.co_varnames:
+            kwargs['identity_init'] = False
+        if override_mfp_to_active and nm_ == pred_name and cls is Softmax:
+            args[0] = FragmentsToDense(args[0], print_repr=False)
+        try:
+            node = cls(*args, **kwargs)
+        except ValueError:
+            if old in (model.target_node, model.loss_node, model.error_node) or not _needed_for_prediction(model, old):
+                continue  # training-only nodes need not survive an inference re-build
+            raise
+        mapping[id(old)] = node
+    d = {}
+    for k, v in model._desig_descr.items():
+        if v is None:
+            d[k] = None
+        elif isinstance(v, (list, tuple)):
+            vs = [mapping.get(id(model.nodes[x if isinstance(x, str) else x.name])) for x in v]
+            d[k] = [x for x in vs if x is not None] or None
+        else:
+            d[k] = mapping.get(id(model.nodes[v if isinstance(v, str) else v.name]))
+    if d.get('loss_node') is None:
+        d['loss_node'] = d['target_node'] = d['error_node'] = None
+        d['prediction_ext'] = None
+    new.designate_nodes(**d)
+    model_manager.togglemodel()
+    return new
+
+
+def _needed_for_prediction(model, node):
+    return model.prediction_node is not None and any(n is node for n in model.prediction_node.ancestors())

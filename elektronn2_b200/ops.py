@@ -1,0 +1,215 @@
+"""Op objects: one per hot-path primitive, each binding caller-owned device buffers to a
+C-ABI descriptor once and then launching with no further host work.
+
+These are the Python face of include/e2b200.h.  ``elektronn2_b200.computations`` wraps
+them with the reference's function signatures; the graph executor
+(``neuromancer/executor.py``) strings them into static plans.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, COMPUTE, TIE
+from .devtensor import DevTensor
+
+
+def _dev_f32(n, device):
+    return torch.zeros(int(n), dtype=torch.float32, device=device)
+
+
+class ConvOp(object):
+    """computations.conv 3-D valid branch + bias/activation epilogue
+    (reference: computations.py:364-428, neural.py:711-712)."""
+
+    def __init__(self, h, x, y, w, b, k, act='relu', compute='tf32'):
+        self.h, self.x, self.y, self.w, self.b = h, x, y, w, b
+        self.k = tuple(int(v) for v in k)
+        self.d = _lib.ConvDesc(x.desc, y.desc, self.k[0], self.k[1], self.k[2], ACT[act], 1 if b is not None else 0,
+                               COMPUTE[compute], 0)
+        f, g = C.c_size_t(), C.c_size_t()
+        _lib.lib.e2_conv3d_packed_floats(C.byref(self.d), C.byref(f), C.byref(g))
+        self.wf = _dev_f32(f.value, x.buf.device)
+        self.wd = _dev_f32(g.value, x.buf.device)
+
+    def _desc(self, x=None, y=None, accumulate=0, act=None, has_bias=None):
+        d = _lib.ConvDesc()
+        C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
+        if x is not None:
+            d.x = x.desc
+        if y is not None:
+            d.y = y.desc
+        d.accumulate = int(accumulate)
+        if act is not None:
+            d.act = ACT[act]
+        if has_bias is not None:
+            d.has_bias = int(has_bias)
+        return d
+
+    def pack(self, need_dgrad=True):
+        self.h.call('e2_conv3d_pack_weights', C.byref(self.d), _lib.ptr(self.w), _lib.ptr(self.wf),
+                    _lib.ptr(self.wd) if need_dgrad else None, self.h.stream())
+
+    def fwd(self, act=None, has_bias=None, y=None):
+        d = self.d if (act is None and has_bias is None and y is None) else self._desc(act=act, has_bias=has_bias, y=y)
+        yy = y or self.y
+        self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
+                    _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), None, 0, self.h.stream())
+
+    def dgrad(self, dy, dx, accumulate=False):
+        d = self._desc(x=dx, y=dy, accumulate=accumulate)
+        self.h.call('e2_conv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(), None, 0, self.h.stream())
+
+    def wgrad(self, dy, dw, db=None):
+        d = self._desc(y=dy)
+        self.h.call('e2_conv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), None, 0,
+                    self.h.stream())
+
+
+class UpConvOp(object):
+    """UpConv (neural.py:989-1072; computations.py:216-255, 749-756)."""
+
+    def __init__(self, h, x, y, w, b, pool, act='relu', compute='tf32'):
+        self.h, self.x, self.y, self.w, self.b = h, x, y, w, b
+        self.pool = tuple(int(v) for v in pool)
+        self.d = _lib.UpConvDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
+                                 1 if b is not None else 0, COMPUTE[compute], 0)
+        f, g = C.c_size_t(), C.c_size_t()
+        _lib.lib.e2_upconv3d_packed_floats(C.byref(self.d), C.byref(f), C.byref(g))
+        self.wf = _dev_f32(f.value, x.buf.device)
+        self.wd = _dev_f32(g.value, x.buf.device)
+
+    def _desc(self, x=None, y=None, accumulate=0):
+        d = _lib.UpConvDesc()
+        C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
+        if x is not None:
+            d.x = x.desc
+        if y is not None:
+            d.y = y.desc
+        d.accumulate = int(accumulate)
+        return d
+
+    def pack(self, need_dgrad=True):
+        self.h.call('e2_upconv3d_pack_weights', C.byref(self.d), _lib.ptr(self.w), _lib.ptr(self.wf),
+                    _lib.ptr(self.wd) if need_dgrad else None, self.h.stream())
+
+    def fwd(self):
+        self.h.call('e2_upconv3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.wf),
+                    _lib.ptr(self.b) if self.d.has_bias else None, self.y.ptr(), None, 0, self.h.stream())
+
+    def dgrad(self, dy, dx, accumulate=False):
+        d = self._desc(x=dx, y=dy, accumulate=accumulate)
+        self.h.call('e2_upconv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(), None, 0, self.h.stream())
+
+    def wgrad(self, dy, dw, db=None):
+        d = self._desc(y=dy)
+        self.h.call('e2_upconv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), None, 0,
+                    self.h.stream())
+
+
+class PoolOp(object):
+    """computations.pooling 3-D max (computations.py:538-649) with optional fused
+    +bias -> act (Conv nodes that carry a pool, neural.py:678, 711-712)."""
+
+    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, tie_mode='first'):
+        self.h, self.x, self.y, self.bias = h, x, y, bias
+        self.pool = tuple(int(v) for v in pool)
+        self.d = _lib.PoolDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
+                               1 if bias is not None else 0, TIE[tie_mode], 0)
+        self.argmax = y.like(dtype=torch.int32) if keep_argmax else None
+
+    def fwd(self):
+        self.h.call('e2_maxpool3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.bias), self.y.ptr(),
+                    self.argmax.ptr() if self.argmax is not None else None, self.h.stream())
+
+    def bwd(self, dy, dx, accumulate=False):
+        d = _lib.PoolDesc()
+        C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
+        d.x, d.y, d.accumulate = dx.desc, dy.desc, int(accumulate)
+        self.h.call('e2_maxpool3d_bwd', C.byref(d), dy.ptr(), self.argmax.ptr() if self.argmax is not None else None,
+                    self.x.ptr(), dx.ptr(), self.h.stream())
+
+
+class MfpOp(object):
+    """computations.fragmentpool (computations.py:652-678)."""
+
+    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True):
+        self.h, self.x, self.y, self.bias = h, x, y, bias
+        self.pool = tuple(int(v) for v in pool)
+        self.d = _lib.MfpDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
+                              1 if bias is not None else 0)
+        self.argmax = y.like(dtype=torch.int32) if keep_argmax else None
+
+    def fwd(self):
+        self.h.call('e2_mfp_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.bias), self.y.ptr(),
+                    self.argmax.ptr() if self.argmax is not None else None, self.h.stream())
+
+    def bwd(self, dy, dx):
+        self.h.call('e2_mfp_bwd', C.byref(self.d), dy.ptr(), self.argmax.ptr(), dx.ptr(), self.h.stream())
+
+
+class Frag2DenseOp(object):
+    """computations.fragments2dense (computations.py:681-701)."""
+
+    def __init__(self, h, frag, dense, offsets, strides):
+        self.h, self.frag, self.dense = h, frag, dense
+        st = tuple(int(v) for v in strides)
+        self.d = _lib.F2DDesc(frag.desc, dense.desc, st[0], st[1], st[2])
+        self.offsets = torch.tensor([[int(v) for v in o] for o in offsets], dtype=torch.int32,
+                                    device=frag.buf.device).contiguous()
+
+    def fwd(self):
+        self.h.call('e2_frag2dense_fwd', C.byref(self.d), self.frag.ptr(), _lib.ptr(self.offsets), self.dense.ptr(),
+                    self.h.stream())
+
+    def bwd(self, ddense, dfrag):
+        self.h.call('e2_frag2dense_bwd', C.byref(self.d), ddense.ptr(), _lib.ptr(self.offsets), dfrag.ptr(),
+                    self.h.stream())
+
+
+class CropConcatOp(object):
+    """Crop (neural.py:1152-1168) writing straight into a channel slice of a Concat
+    buffer (node_basic.py:1403-1451)."""
+
+    def __init__(self, h, src, dst, crop, dst_c0=0):
+        self.h, self.src, self.dst = h, src, dst
+        c = tuple(int(v) for v in crop)
+        self.d = _lib.CropDesc(src.desc, dst.desc, c[0], c[1], c[2], int(dst_c0), 0)
+
+    def fwd(self):
+        self.h.call('e2_crop_concat_fwd', C.byref(self.d), self.src.ptr(), self.dst.ptr(), self.h.stream())
+
+    def bwd(self, ddst, dsrc, accumulate=False):
+        d = _lib.CropDesc()
+        C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
+        d.accumulate = int(accumulate)
+        self.h.call('e2_crop_concat_bwd', C.byref(d), ddst.ptr(), dsrc.ptr(), self.h.stream())
+
+
+class LossOp(object):
+    """Softmax -> MultinoulliNLL(sparse) -> AggregateLoss mean, and Errors
+    (computations.py:170-177; loss.py:261-347, 1346-1363, 730-814)."""
+
+    EPS = 1e-5
+
+    def __init__(self, h, logits, target, probs):
+        self.h, self.logits, self.target, self.probs = h, logits, target, probs
+        self.scalars = _dev_f32(4, logits.buf.device)
+
+    def fwd(self):
+        self.h.call('e2_softmax_nll_fwd', C.byref(self.logits.desc), self.logits.ptr(), self.target.ptr(),
+                    self.probs.ptr(), _lib.ptr(self.scalars), self.h.stream())
+
+    def bwd(self, dlogits, grad_scale=1.0):
+        self.h.call('e2_softmax_nll_bwd', C.byref(self.logits.desc), self.probs.ptr(), self.target.ptr(),
+                    _lib.ptr(self.scalars), C.c_float(grad_scale), dlogits.ptr(), self.h.stream())
+
+    def read(self):
+        """(loss, error_rate) -- one D2H copy of 4 floats."""
+        s = self.scalars.cpu().numpy()
+        n_pos = self.logits.desc.positions
+        return float(s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
+
+
+def act_bwd(h, t, act, y, dy, dpre):
+    h.call('e2_act_bwd', C.byref(t.desc), _lib.i32(ACT[act]), y.ptr(), dy.ptr(), dpre.ptr(), h.stream())

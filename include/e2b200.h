@@ -1,0 +1,232 @@
+/*
+ * e2b200.h -- C ABI of libe2b200.so, the B200 (sm_100a) implementation of
+ * ELEKTRONN2's volumetric-CNN hot path.
+ *
+ * The reference has no FFI for this path: it calls Theano, which calls
+ * cuDNN/BLAS.  Each entry point below therefore names the
+ * reference call site it replaces (paths relative to /root/reference/elektronn2);
+ * INTEGRATION.md shows the theano.Op / ctypes stub a maintainer would add at
+ * those sites.
+ *
+ * Conventions
+ *  - plain C, no torch types; every pointer is a DEVICE pointer owned by the
+ *    caller (the library never allocates, frees or retains them);
+ *  - every call is asynchronous on the given cudaStream_t (passed as void*);
+ *  - return value: E2_OK or a negative e2_status; e2_last_error(h) holds the text;
+ *  - activations are channels-last "NDHWC": element (n,z,x,y,c) lives at
+ *    ((((n*Z + z)*X + x)*Y + y) * c_pitch + c), c_pitch >= c.  The reference's
+ *    (b,f,z,x,y) arrays enter/leave through e2_layout_convert;
+ *  - conv weights are exchanged in the reference's own layout
+ *    (f_out, f_in, kz, kx, ky) float32 (neural.py:618-620) and re-packed on the
+ *    device by e2_conv3d_pack_weights;
+ *  - a handle is bound to one device; calls on different handles are independent;
+ *    there is no global mutable state.
+ */
+#ifndef E2B200_H
+#define E2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2B200_VERSION 100
+
+typedef struct e2_handle e2_handle;
+
+typedef enum {
+  E2_OK = 0,
+  E2_ERR_INVALID = -1,     /* bad descriptor / null pointer / shape mismatch (ValueError in the reference) */
+  E2_ERR_UNSUPPORTED = -2, /* valid request this build cannot serve (NotImplementedError) */
+  E2_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed */
+  E2_ERR_WORKSPACE = -4    /* workspace too small, see e2_*_workspace_size */
+} e2_status;
+
+/* apply_activation, computations.py:57-134 (the parameter-free subset) */
+typedef enum { E2_ACT_LIN = 0, E2_ACT_RELU = 1, E2_ACT_TANH = 2, E2_ACT_SIGMOID = 3, E2_ACT_ABS = 4 } e2_act;
+
+/* arithmetic used inside the conv GEMMs (accumulation is always fp32) */
+typedef enum {
+  E2_COMPUTE_F32 = 0,  /* CUDA-core FFMA, exact fp32 products                          */
+  E2_COMPUTE_TF32 = 1, /* tcgen05.mma kind::tf32, operands rounded to tf32 (rel 2^-11) */
+  E2_COMPUTE_BF16 = 2  /* reserved */
+} e2_compute;
+
+typedef enum { E2_TIE_FIRST = 0, E2_TIE_ALL = 1 } e2_tie_mode;
+
+typedef struct {
+  int32_t n, z, x, y, c; /* logical extents */
+  int32_t c_pitch;       /* floats between consecutive positions, >= c */
+} e2_tensor;
+
+/* ---------------------------------------------------------------- handle */
+int e2_version(void);
+int e2_create(e2_handle** out, int device);
+int e2_destroy(e2_handle* h);
+const char* e2_last_error(const e2_handle* h);
+/* number of kernel launches issued through this handle since creation */
+int64_t e2_launch_count(const e2_handle* h);
+
+/* --------------------------------------------------------- layout / boundary
+ * Node.__call__ (node_basic.py:464-494) hands numpy (b,f,z,x,y) arrays to Theano;
+ * here they are converted once at the edge.  ncdhw is dense C-contiguous. */
+int e2_ncdhw_to_ndhwc(e2_handle* h, const e2_tensor* t, const float* ncdhw, float* ndhwc, void* stream);
+int e2_ndhwc_to_ncdhw(e2_handle* h, const e2_tensor* t, const float* ndhwc, float* ncdhw, void* stream);
+/* predict_dense input scaling, node_basic.py:904-910: uint8 -> float32 / 255 (count elements) */
+int e2_u8_to_f32(e2_handle* h, const uint8_t* src, float* dst, int64_t count, float scale, void* stream);
+/* predict_dense as_uint8 output, node_basic.py:990-996: trunc(p*255) */
+int e2_f32_to_u8(e2_handle* h, const float* src, uint8_t* dst, int64_t count, float scale, void* stream);
+
+/* ------------------------------------------------------------------ conv3d
+ * computations.conv 3-D 'valid' branch, computations.py:364-428 (true convolution,
+ * kernel flipped; stride 1), the 1x1x1 tensordot shortcut :330-335/:377-384, and the
+ * bias+activation epilogue of Conv._make_output, neural.py:711-712.
+ * Backward: what T.grad (model.py:182) derives for them. */
+typedef struct {
+  e2_tensor x;        /* input  (n, Z, X, Y, c_in)                               */
+  e2_tensor y;        /* output (n, Z-kz+1, X-kx+1, Y-ky+1, c_out)               */
+  int32_t kz, kx, ky;
+  int32_t act;        /* e2_act applied after +bias (fwd only)                   */
+  int32_t has_bias;
+  int32_t compute;    /* e2_compute                                              */
+  int32_t accumulate; /* dgrad only: dx += result instead of dx = result          */
+} e2_conv_desc;
+
+/* floats needed for the packed forward / dgrad weight images */
+int e2_conv3d_packed_floats(const e2_conv_desc* d, size_t* fwd_floats, size_t* dgrad_floats);
+/* w (f_out,f_in,kz,kx,ky) -> wf[o][tap][c] (flipped taps, fwd) and wd[c][tap][o] (dgrad);
+ * either output may be NULL.  With compute==TF32 values are rounded to tf32 (rna). */
+int e2_conv3d_pack_weights(e2_handle* h, const e2_conv_desc* d, const float* w, float* wf, float* wd, void* stream);
+int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes);
+/* y = act(conv(x, w) + bias) */
+int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x, const float* wf, const float* bias,
+                  float* y, void* ws, size_t ws_bytes, void* stream);
+/* dx (=|+=) full-correlation(dy, w) */
+int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float* dy, const float* wd, float* dx,
+                    void* ws, size_t ws_bytes, void* stream);
+/* dw (reference layout, overwritten) and optional db = sum dy */
+int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ----------------------------------------------------------------- upconv3d
+ * UpConv._make_output, neural.py:989-1072: CPU path unpooling+conv
+ * (computations.py:749-756, neural.py:1013-1020), GPU path computations.upconv
+ * (computations.py:216-255).  kernel == pool == stride (neural.py:968), so
+ *   y[n, z*pz+i, x*px+j, y*py+k, o] = act(sum_c x[n,z,x,y,c] * w[o,c,i,j,k] + b[o]). */
+typedef struct {
+  e2_tensor x; /* (n, Z, X, Y, c_in)            */
+  e2_tensor y; /* (n, Z*pz, X*px, Y*py, c_out)  */
+  int32_t pz, px, py;
+  int32_t act, has_bias, compute, accumulate;
+} e2_upconv_desc;
+
+int e2_upconv3d_packed_floats(const e2_upconv_desc* d, size_t* fwd_floats, size_t* dgrad_floats);
+int e2_upconv3d_pack_weights(e2_handle* h, const e2_upconv_desc* d, const float* w, float* wf, float* wd, void* stream);
+int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* wf, const float* bias,
+                    float* y, void* ws, size_t ws_bytes, void* stream);
+int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const float* dy, const float* wd, float* dx,
+                      void* ws, size_t ws_bytes, void* stream);
+int e2_upconv3d_wgrad(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* dy, float* dw, float* db,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* -------------------------------------------------- activation backward / bias
+ * dpre = dy * act'(y) evaluated from the stored post-activation y; may run in place
+ * (dpre == dy). */
+int e2_act_bwd(e2_handle* h, const e2_tensor* t, int32_t act, const float* y, const float* dy, float* dpre, void* stream);
+
+/* ----------------------------------------------------------------- pooling
+ * computations.pooling 3-D 'max', stride == pool, ignore_border
+ * (computations.py:538-649; dnn_pool :600 / pool_2d + z-maximum :617-631).
+ * Optional fused "+bias -> act" for Conv nodes that carry a pool: the reference
+ * pools BEFORE bias and activation (neural.py:678, 711-712).
+ * argmax (may be NULL): int32 z*X*Y + x*Y + y of the FIRST maximum in (z,x,y)
+ * row-major scan order of the window. */
+typedef struct {
+  e2_tensor x; /* (n, Z, X, Y, c)                */
+  e2_tensor y; /* (n, Z/pz, X/px, Y/py, c)       */
+  int32_t pz, px, py;
+  int32_t act, has_bias; /* fused epilogue, fwd only                 */
+  int32_t tie_mode;      /* e2_tie_mode, bwd only                    */
+  int32_t accumulate;    /* bwd only: dx += instead of dx =          */
+} e2_pool_desc;
+
+int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,
+                     int32_t* argmax, void* stream);
+/* E2_TIE_FIRST routes dy through argmax (x may be NULL); E2_TIE_ALL (Theano-CPU
+ * semantics) needs x and the pooled pre-bias maximum is recomputed from it. */
+int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax, const float* x,
+                     float* dx, void* stream);
+
+/* ------------------------------------------------------ max-fragment-pooling
+ * computations.fragmentpool, computations.py:652-678.  Output batch = prod(p) * n,
+ * new-offset-major / old-fragment-minor, offsets in itertools.product order (last
+ * spatial axis fastest).  y spatial = (S - p + 1) / p per axis. */
+typedef struct {
+  e2_tensor x; /* (n, Z, X, Y, c)                                    */
+  e2_tensor y; /* (n*pz*px*py, (Z-pz+1)/pz, (X-px+1)/px, (Y-py+1)/py, c) */
+  int32_t pz, px, py;
+  int32_t act, has_bias;
+} e2_mfp_desc;
+
+int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, const float* bias, float* y, int32_t* argmax,
+               void* stream);
+int e2_mfp_bwd(e2_handle* h, const e2_mfp_desc* d, const float* dy, const int32_t* argmax, float* dx, void* stream);
+
+/* ------------------------------------------------------- fragments -> dense
+ * computations.fragments2dense, computations.py:681-701:
+ *   dense[0, off_k[0]::s0, off_k[1]::s1, off_k[2]::s2, :] = frag[k].
+ * offsets: DEVICE int32 [n_frag][3]. */
+typedef struct {
+  e2_tensor frag;  /* (n_frag, Z, X, Y, c), n_frag == sz*sx*sy */
+  e2_tensor dense; /* (1, Z*sz, X*sx, Y*sy, c)                 */
+  int32_t sz, sx, sy;
+} e2_f2d_desc;
+
+int e2_frag2dense_fwd(e2_handle* h, const e2_f2d_desc* d, const float* frag, const int32_t* offsets, float* dense,
+                      void* stream);
+int e2_frag2dense_bwd(e2_handle* h, const e2_f2d_desc* d, const float* ddense, const int32_t* offsets, float* dfrag,
+                      void* stream);
+
+/* ----------------------------------------------------------- crop + concat
+ * Crop (neural.py:1152-1168) fused with the channel placement of Concat(axis='f')
+ * (node_basic.py:1403-1451) as AutoMerge builds them (neural.py:1393-1399):
+ *   dst[n, z, x, y, dst_c0 + c] = src[n, z+oz, x+ox, y+oy, c]. */
+typedef struct {
+  e2_tensor src; /* (n, Z, X, Y, c)                        */
+  e2_tensor dst; /* (n, Z-2oz, X-2ox, Y-2oy, c_total)      */
+  int32_t oz, ox, oy;
+  int32_t dst_c0;
+  int32_t accumulate; /* bwd only */
+} e2_crop_desc;
+
+int e2_crop_concat_fwd(e2_handle* h, const e2_crop_desc* d, const float* src, float* dst, void* stream);
+/* dsrc[.. cropped region ..] (=|+=) ddst[..., dst_c0 + c]; with accumulate==0 the border of dsrc is zeroed */
+int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc, void* stream);
+
+/* ------------------------------------------------ loss head (next-row 8f-2)
+ * Softmax (computations.py:170-177) -> MultinoulliNLL sparse target
+ * (loss.py:261-347, EPS=1e-5) -> AggregateLoss mean (loss.py:1346-1363) and
+ * Classification/_Errors (loss.py:736-737, 805-807) in one pass.
+ * out_scalars (device float[4]): loss_sum (sum of -log(p_t+EPS) over labelled voxels), n_labelled, n_errors, unused.
+ * The caller finishes: loss = loss_sum / (n_labelled + EPS). */
+int e2_softmax_nll_fwd(e2_handle* h, const e2_tensor* logits, const float* x, const float* target, float* probs,
+                       float* out_scalars, void* stream);
+/* dlogits given scalars from the forward pass; grad_scale multiplies the result (1/N for data parallel means) */
+int e2_softmax_nll_bwd(e2_handle* h, const e2_tensor* logits, const float* probs, const float* target,
+                       const float* scalars, float grad_scale, float* dlogits, void* stream);
+
+/* ---------------------------------------------------- optimiser (next-row 8f-2)
+ * Adam exactly as optimiser.py:301-324: eps=1e-5 inside the sqrt, factor =
+ * sqrt(1-beta2^t)/(1-mom^t), L2 term wd*p when apply_wd.  t is the 1-based step. */
+int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, float lr, float mom,
+                 float beta2, float wd, int32_t apply_wd, int32_t t, void* stream);
+/* SGD with momentum, optimiser.py:146-160 */
+int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom, float wd,
+                int32_t apply_wd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2B200_H */

@@ -1,0 +1,195 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the
+header declares, and the neuromancer mirror builds the reference's graphs with the
+same shapes / strides / fovs / parameter counts as the oracle and the goldens."""
+import ctypes
+import io
+import contextlib
+import json
+import os
+import re
+import runpy
+
+import numpy as np
+import pytest
+
+from oracle import nets as onets
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF_EXAMPLES = '/root/reference/examples'
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'e2b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(e2_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from elektronn2_b200 import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(_lib.lib, s), "libe2b200.so does not export %s" % s
+    # and the ctypes signature table covers the whole header
+    assert sorted(_lib.SIGNATURES.keys()) == syms
+    assert _lib.lib.e2_version() == 100
+
+
+def test_descriptor_structs_match_header_sizes():
+    from elektronn2_b200 import _lib
+    assert ctypes.sizeof(_lib.Tensor) == 24
+    assert ctypes.sizeof(_lib.ConvDesc) == 48 + 7 * 4
+    assert ctypes.sizeof(_lib.PoolDesc) == 48 + 7 * 4
+    assert ctypes.sizeof(_lib.MfpDesc) == 48 + 5 * 4
+    assert ctypes.sizeof(_lib.F2DDesc) == 48 + 3 * 4
+    assert ctypes.sizeof(_lib.CropDesc) == 48 + 5 * 4
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from elektronn2_b200 import _lib
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.Handle(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'elektronn2_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, f)).read()
+                assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def _build(name):
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200 import examples
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return getattr(examples, name)()
+
+
+@pytest.mark.parametrize('name', ['neuro3d_lite', 'neuro3d', 'unet3d_litelite', 'unet3d'])
+def test_graph_matches_oracle(name):
+    m = _build(name)
+    o = onets.BUILDERS[name]()
+    pred = m.prediction_node
+    osh = o.nodes[-1].sh
+    assert [1 if s is None else s for s in pred.shape.shape] == osh.shape
+    assert [int(s) for s in pred.shape.strides] == osh.strides
+    assert m.loss_node.all_params_count == sum(v.size for n in o.nodes for v in n.params.values())
+    # same seed, same draw order -> identical initial weights (reference init rule)
+    mine = [p.get_value() for p in m.trainable_params]
+    theirs = [n.params[k] for n, k in o.param_list()]
+    assert len(mine) == len(theirs)
+    for a, b in zip(mine, theirs):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    if name.startswith('neuro3d'):
+        assert [int(v) for v in pred.shape.fov] == osh.fov
+    else:
+        # U-Net fov back-fill (model.py:141-152)
+        from oracle.shapes import unet_fov_backfill
+        assert [int(v) for v in pred.shape.fov] == unet_fov_backfill(m.input_node.shape.spatial_shape, osh)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize('name', ['neuro3d_lite', 'neuro3d', 'unet3d_litelite', 'unet3d_lite', 'unet3d'])
+def test_unedited_reference_model_files_build(name):
+    """Drop-in check: the reference's own example files execute unedited against the
+    mirror (``from elektronn2 import neuromancer as nm``)."""
+    import elektronn2_b200
+    elektronn2_b200.install_as_elektronn2()
+    np.random.seed(2)
+    ns = runpy.run_path(os.path.join(REF_EXAMPLES, name + '.py'), run_name='not_main')
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ns['create_model']()
+    known = dict(neuro3d_lite=885132, neuro3d=2756042, unet3d_litelite=352207, unet3d=19069058)
+    if name in known:
+        assert m.loss_node.all_params_count == known[name]
+    assert m.prediction_node.shape['f'] == 2
+    if name in dict(neuro3d_lite=1, neuro3d=1):
+        # Conv cost == MACs (neural.py:767-778); SURVEY 8d: 5.469 / 20.016 GMAC
+        macs = sum(n.computational_cost for n in m.nodes.values() if type(n).__name__ == 'Conv')
+        assert round(macs / 1e9, 3) == dict(neuro3d_lite=5.469, neuro3d=20.016)[name]
+
+
+def test_taggedshape_matches_reference_golden():
+    from elektronn2_b200.neuromancer import TaggedShape
+    g = json.load(open(os.path.join(HERE, 'golden', 'ref_python.json')))['taggedshape']
+    sh = TaggedShape([None, 1, 23, 185, 185], 'b,f,z,x,y')
+    s2 = sh.updateshape('f', 20).updateshape(3, 90).updatefov(1, 7).updatestrides(np.array([1, 2, 2]))
+    s3 = s2.updateshape('b', 4, mode='mult').updateshape('z', 2, mode='mult')
+    assert sh.spatial_axes == g['spatial_axes'] and sh.ndim == g['ndim'] and sh.spatial_shape == g['spatial_shape']
+    assert s2.shape == g['s2_shape'] and [int(v) for v in s2.fov] == g['s2_fov'] and s2.offsets == g['s2_offsets']
+    assert [int(v) for v in s2.strides] == g['s2_strides'] and repr(s2) == g['s2_repr']
+    assert s3.shape == g['s3_shape'] and int(s2.stripnone_prod) == g['stripnone_prod']
+    assert s2.spatial_size == g['spatial_size'] and sh.tag2index('f') == g['f_index']
+    assert np.asarray(sh.mfp_offsets).tolist() == g['mfp_offsets']
+
+
+def test_initweights_matches_reference_golden():
+    from elektronn2_b200.neuromancer import initweights
+    iw = json.load(open(os.path.join(HERE, 'golden', 'ref_python.json')))['initweights_seed2']
+    np.random.seed(2)
+    w = initweights((20, 1, 1, 4, 4), scale='glorot', mode='normal', pool=(1, 2, 2), spatial_axes=[2, 3, 4])
+    assert w.dtype == np.float32 and np.allclose(w.ravel()[:8], iw['conv_w']['head'], rtol=1e-6)
+    assert np.isclose(float(w.std()), iw['conv_w']['std'], rtol=1e-6)
+    assert np.allclose(initweights((20,), scale=1.0 / 16, mode='const')[:3], iw['relu_b'])
+    assert np.allclose(initweights((2,), scale=1e-6, mode='fix-uni'), iw['lin_b'])
+    w = initweights((45, 42, 1, 4, 4), scale='glorot', mode='normal', pool=(1, 4, 4), spatial_axes=[2, 3, 4])
+    assert np.allclose(w.ravel()[:4], iw['upconv_w']['head'], rtol=1e-6)
+
+
+def test_error_behaviour_mirrors_reference():
+    from elektronn2_b200 import neuromancer as nm
+    inp = nm.Input((None, 1, 11, 155, 155), 'b,f,z,x,y', name='raw', print_repr=False)
+    with pytest.raises(ValueError, match="Cannot pool spatial axis"):      # neural.py:746-750
+        nm.Conv(inp, 4, (1, 3, 3), (1, 2, 2), print_repr=False)
+    with pytest.raises(ValueError, match="dimensionality"):                # neural.py:594-601
+        nm.Conv(inp, 4, (3, 3), print_repr=False)
+    c = nm.Conv(inp, 4, (1, 4, 4), (1, 2, 2), print_repr=False)
+    with pytest.raises(ValueError, match="linear activation"):             # loss.py:56-59
+        nm.Softmax(c, print_repr=False)
+    with pytest.raises(ValueError, match="Need .* fragments"):             # neural.py:873-875
+        nm.FragmentsToDense(c, print_repr=False)
+    with pytest.raises(ValueError, match="upconv_n_f"):                    # neural.py:1357-1360
+        c2 = nm.Conv(c, 4, (1, 3, 3), (1, 2, 2), print_repr=False)
+        nm.UpConvMerge(c, c2)
+    assert [n for n in nm.model_manager.current.nodes] == ['raw', 'conv', 'conv1']
+
+
+def test_mfp_rebuild_shapes():
+    """modelload(override_mfp_to_active=True): patch snaps to (22,184,184), fragments
+    (32,2,4,20,20) -> dense (1,2,8,80,80) (docs/examples.rst:201-209)."""
+    from elektronn2_b200 import neuromancer as nm
+    m = _build('neuro3d')
+    m2 = nm.rebuild_model(m, override_mfp_to_active=True, imposed_patch_size=(23, 185, 185))
+    assert m2.input_node.shape.spatial_shape == [22, 184, 184]
+    f2d = [n for n in m2.nodes.values() if isinstance(n, nm.FragmentsToDense)][0]
+    assert f2d.parent.shape.shape == [32, 2, 4, 20, 20]
+    assert m2.prediction_node.shape.shape == [1, 2, 8, 80, 80]
+    assert [int(s) for s in m2.prediction_node.shape.strides] == [1, 1, 1]
+    batches = [n.shape['b'] for n in m2.nodes.values() if type(n) is nm.Conv]
+    assert batches == [4, 16, 16, 32, 32, 32, 32, 32, 32, 32, 32]
+    # weights carried over
+    a = [p.get_value() for p in m.prediction_node.all_trainable_params.values()]
+    b = [p.get_value() for p in m2.prediction_node.all_trainable_params.values()]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # fragment offsets follow the reference's nesting: newest layer most significant
+    o = onets.neuro3d((22, 184, 184), mfp=True)
+    assert np.array_equal(f2d.parent.shape.mfp_offsets, o.nodes[-2].sh.mfp_offsets)
+
+
+def test_tile_geometry_config4():
+    """512^3 with neuro3d+MFP at patch (22,184,184): pred (2,498,408,408), 2268 tiles."""
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200.neuromancer.dense import tile_geometry, tile_list, shard_tiles
+    m2 = nm.rebuild_model(_build('neuro3d'), override_mfp_to_active=True, imposed_patch_size=(23, 185, 185))
+    tile_sh, prob_sh, pred_sh, n_tiles = tile_geometry(m2.prediction_node, (512, 512, 512))
+    assert list(pred_sh) == [498, 408, 408] and list(prob_sh) == [8, 80, 80] and int(np.prod(n_tiles)) == 2268
+    tiles = tile_list(n_tiles)
+    parts = [shard_tiles(tiles, r, 8) for r in range(8)]
+    assert sum(len(p) for p in parts) == 2268 and sorted(sum(parts, [])) == sorted(tiles)
