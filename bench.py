@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Benchmark of the ELEKTRONN2 volumetric-CNN hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload unet3d] [--impl reference]
+
+Metric (BASELINE.json): 3-D U-Net training voxels/s (+ conv3d TFLOP/s in ``roofline``).
+Workload: ``examples/unet3d.py`` (configs[2]; it is the configuration the metric is quoted
+on and it fits one GPU), one (1,1,116,132,132) float32 patch per GPU, data-parallel over
+N GPUs ("weak" scaling: global batch == N).  Voxels/s follows the reference's own
+convention: prod(input batch shape) / step time (training/trainer.py:283-284).
+
+One JSON line is printed by rank 0.  ``value`` times K steps with inputs resident in
+HBM; ``e2e`` times K calls of ``Model.trainingstep(x_host, t_host)`` -- the call a user
+of the reference makes -- including the pinned H2D copies and the D2H loss read.
+``--impl reference`` times the Theano-equivalent CPU restatement (oracle/theano_cpu.py)
+on the host cores: Theano itself cannot be installed here.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    'unet3d': dict(patch=(116, 132, 132), cpu_patches=[(116, 132, 132), (84, 100, 100), (52, 68, 68)]),
+    'unet3d_litelite': dict(patch=(22, 140, 140), cpu_patches=[(22, 140, 140)]),
+    'neuro3d_lite': dict(patch=(11, 155, 155), cpu_patches=[(11, 155, 155)]),
+    'neuro3d': dict(patch=(23, 185, 185), cpu_patches=[(23, 185, 185)]),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained'),
+                    source='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(',')]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
+                    power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows))
+
+
+def synthetic_batch(model, seed):
+    ish = [1 if s is None else s for s in model.input_node.shape.shape]
+    tsh = [1 if s is None else s for s in model.target_node.shape.shape]
+    x = np.random.RandomState(seed).rand(*ish).astype(np.float32)          # EM-like [0,1) float32
+    t = np.random.RandomState(seed + 1).randint(0, 2, tsh).astype(np.float32)
+    return x, t
+
+
+def cpu_reference(workload, steps, warmup, budget_s=150.0):
+    """Theano-equivalent CPU restatement on all host cores, bounded sample per step."""
+    import torch
+    from oracle import nets as onets, theano_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    builder = onets.BUILDERS[workload]
+    cands = WORKLOADS[workload]['cpu_patches']
+    # calibrate on the smallest candidate, then take the largest patch that fits the budget
+    cal = theano_cpu.time_training(builder, cands[-1], steps=1, warmup=0)
+    rate = cal['voxels_per_s']
+    patch = cands[-1]
+    for c in cands:
+        if (steps + warmup) * float(np.prod(c)) / rate <= budget_s:
+            patch = c
+            break
+    r = theano_cpu.time_training(builder, patch, steps=max(steps, 1), warmup=warmup)
+    return dict(value=r['voxels_per_s'], unit='voxels/s', cores=r['cores'], kind='port',
+                sample='%d fwd+bwd+Adam step(s) of %s on a (1,1,%d,%d,%d) patch, conv3d2d/pool_2d '
+                       'decomposition on torch-CPU float32 (Theano-equivalent restatement, not Theano)'
+                       % ((max(steps, 1), workload) + tuple(patch)),
+                ms_per_step=r['seconds_per_step'] * 1e3, patch=list(patch))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='unet3d', choices=sorted(WORKLOADS))
+    ap.add_argument('--compute', default=None, choices=['tf32', 'f32'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-out', default=None, help='write the per-launch timing table (JSON) here')
+    args = ap.parse_args()
+    W = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    K = max(args.steps, 1)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    config = dict(workload='examples/%s.py training step (fwd + bwd + Adam), patch (1,1,%d,%d,%d) per GPU'
+                           % ((args.workload,) + WORKLOADS[args.workload]['patch']),
+                  global_batch=world, parallelism='dp%d' % world,
+                  l2_policy='activations of one step (~2.5 GB for unet3d) exceed the 126 MB L2')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        r = cpu_reference(args.workload, K, args.warmup)
+        line = dict(metric='3D U-Net train voxels/sec', value=r['value'], unit='voxels/s', n_gpus=world, steps=K,
+                    warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic', config=config, impl='reference',
+                    cpu_baseline=dict(value=r['value'], unit='voxels/s', cores=r['cores'], kind=r['kind'],
+                                      sample=r['sample']),
+                    e2e=dict(value=r['value'], unit='voxels/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import elektronn2_b200
+    from elektronn2_b200 import examples, parallel, neuromancer as nm
+    from elektronn2_b200.config import config as e2cfg
+    if args.compute:
+        e2cfg.compute = args.compute
+    if args.no_graph:
+        e2cfg.use_cuda_graph = False
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dist = torch.distributed
+    np.random.seed(2)                                   # identical initial weights on every rank
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = examples.BUILDERS[args.workload]()
+    dp = None
+    if world > 1:
+        dp = parallel.DataParallel(model)
+    nm.optimiser.Optimiser.setlr(5e-4)                  # examples/unet3d.py optimiser_params
+    nm.optimiser.Optimiser.setwd(0.5e-4)
+    nm.optimiser.Optimiser.setmom(0.9)
+    x, t = synthetic_batch(model, 1000 + rank)
+    plan = model._train_plan(1)
+    if dp is not None:
+        dp.broadcast_parameters(plan.store)
+    opt = model.optimisers['Adam']
+    launches_per_step = plan.launches_per_step() + 2    # + the two Adam region launches
+    n_vox = float(np.prod(x.shape)) * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        plan.execute()
+        opt.step(plan.store)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------
+    plan.feed({model.input_node: x, model.target_node: t})
+    for _ in range(W):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        device_step()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    # ---- e2e: the public API call with host buffers -----------------------------------
+    for _ in range(2):
+        model.trainingstep(x, t, optimiser='Adam')
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss, _, _ = model.trainingstep(x, t, optimiser='Adam')
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel family (eager, per-launch CUDA events) ---------
+    peaks = load_peaks()
+    prof = plan.profile(repeats=3)
+    step_ms = sum(p[4] for p in prof)
+    fam = {}
+    for label, kind, flops, nbytes, ms in prof:
+        key = label.split(':')[0]
+        f = fam.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, n=0, tensor=0))
+        f['ms'] += ms
+        f['flops'] += flops if kind == 'tensor' else 0.0
+        f['bytes'] += nbytes
+        f['n'] += 1
+        f['tensor'] += kind == 'tensor'
+    top = max(fam, key=lambda k: fam[k]['ms'])
+    tf = fam[top]
+    tensor_peak = peaks['bf16'] / 2.0 if e2cfg.compute == 'tf32' else None   # TF32 = half the bf16 rate
+    if tf['tensor'] and tensor_peak:
+        ach = tf['flops'] / (tf['ms'] * 1e-3) / 1e12
+        roof = dict(bound='tensor', kernel=top, achieved=ach, peak=tensor_peak, unit='TFLOP/s', frac=ach / tensor_peak,
+                    traffic=None, launches=tf['n'], avg_launch_ms=tf['ms'] / tf['n'], share_of_step=tf['ms'] / step_ms,
+                    peak_source='%s cuBLAS bf16 %.1f TFLOP/s (burst) / 2 for TF32' % (peaks['source'], peaks['bf16']))
+    else:
+        ach = tf['bytes'] / (tf['ms'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', kernel=top, achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'],
+                    traffic=None, launches=tf['n'], avg_launch_ms=tf['ms'] / tf['n'], share_of_step=tf['ms'] / step_ms,
+                    peak_source='%s copy bandwidth' % peaks['source'])
+    all_flops = sum(p[2] for p in prof)
+    roof['step_conv_tflops'] = all_flops / (dev_ms / K * 1e-3) / 1e12
+    if args.profile_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        json.dump(dict(step_ms_eager=step_ms, families=fam,
+                       launches=[dict(label=p[0], kind=p[1], flops=p[2], bytes=p[3], ms=p[4]) for p in prof]),
+                  open(args.profile_out, 'w'), indent=1)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(args.workload, 1, 0, budget_s=40.0)
+        cpu = dict(value=r['value'], unit='voxels/s', cores=r['cores'], kind=r['kind'], sample=r['sample'])
+
+    in_bytes = x.nbytes + t.nbytes
+    line = dict(metric='3D U-Net train voxels/sec', value=n_vox * K / (dev_ms * 1e-3), unit='voxels/s', n_gpus=world,
+                steps=K, warmup=W, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=e2cfg.compute, data='synthetic', config=config, roofline=roof, cpu_baseline=cpu,
+                e2e=dict(value=n_vox * K / (e2e_ms * 1e-3), unit='voxels/s', h2d_bytes_per_step=in_bytes,
+                         d2h_bytes_per_step=16, ms_per_step=e2e_ms / K),
+                gpu_launches=launches_per_step * K, clocks=clocks, loss=float(loss),
+                cuda_graph=bool(e2cfg.use_cuda_graph and world == 1))
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

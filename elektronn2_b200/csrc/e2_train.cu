@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(256) k_softmax_nll_fwd(const float* __restrict
     }
     float den = 0.f;
     for (int c = 0; c < C; ++c) den += expf(r[c] - mx);  // computations.py:175-176
-    int tc = (int)target[i];
-    float tf = target[i];
-    bool labelled = (tf == (float)tc) && tc >= 0 && tc < C;  // T.eq(target, classes) one-hot, loss.py:271-276
+    // target == NULL: plain Softmax node (inference), no loss / error statistics
+    float tf = target ? target[i] : -1.f;
+    int tc = (int)tf;
+    bool labelled = target && (tf == (float)tc) && tc >= 0 && tc < C;  // T.eq(target, classes), loss.py:271-276
     for (int c = 0; c < C; ++c) {
       float p = expf(r[c] - mx) / den;
       probs[i * pitch + c] = p;
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(256) k_softmax_nll_fwd(const float* __restrict
     }
     if (labelled) l_lab += 1.f;
     // _Errors: mean(int16(target) != argmax) over ALL positions (loss.py:803-807)
-    if ((int)(short)tf != am) l_err += 1.f;
+    if (target && (int)(short)tf != am) l_err += 1.f;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(256) k_softmax_nll_bwd(const float* __restrict
 
 extern "C" int e2_softmax_nll_fwd(e2_handle* h, const e2_tensor* t, const float* x, const float* target, float* probs,
                                   float* out_scalars, void* stream) {
-  E2_REQUIRE(h, e2_tensor_ok(t) && x && target && probs && out_scalars, "softmax_nll_fwd: bad arguments");
+  E2_REQUIRE(h, e2_tensor_ok(t) && x && probs && out_scalars, "softmax_nll_fwd: bad arguments");
+  E2_REQUIRE(h, t->c <= 64, "softmax_nll_fwd: at most 64 classes");
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(out_scalars, 0, 4 * sizeof(float), s);
   int64_t P = e2_positions(t);

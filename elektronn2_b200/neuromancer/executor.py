@@ -57,18 +57,39 @@ class ParamStore(object):
             view.copy_(torch.from_numpy(np.ascontiguousarray(p._host)))
             p._dev = view
             p._grad = self.G[o:o + size].view(*p.shape)
+            p._offset = o
             p._on_set.append(self._bump)
 
     def _bump(self):
         self.version += 1
 
-    def grads_numpy(self):
-        return [p._grad.detach().cpu().numpy().copy() for _, p, _, _ in self.entries]
+
+class Launch(object):
+    """One entry of a plan: a bound C-ABI call plus its algorithmic work (for rooflines:
+    SURVEY.md 8d "Algorithmic work")."""
+    __slots__ = ('label', 'fn', 'flops', 'bytes', 'kind', 'param_end')
+
+    def __init__(self, label, fn, flops=0, nbytes=0, kind='hbm'):
+        self.label, self.fn, self.flops, self.bytes, self.kind = label, fn, float(flops), float(nbytes), kind
+        self.param_end = None  # wgrad launches: end offset (floats) of the gradient region now complete
+
+    def __call__(self):
+        self.fn()
+
+
+def _nel(t):
+    return t.desc.positions * t.desc.c
 
 
 def _nb(node, batch):
     b = node.shape['b']
     return int(batch) if b is None else int(b)
+
+
+def _tensor_shaped(c_in, c_out):
+    """Layers with c_in == 1 or c_out <= 2 are bandwidth-bound and are
+    reported against the HBM roofline, everything else against the tensor pipe."""
+    return c_in > 1 and c_out > 2
 
 
 class Plan(object):
@@ -96,6 +117,10 @@ class Plan(object):
         self.inputs = {}
         self._graph = None
         self._packed_version = -1
+        self.grad_scale = 1.0
+        dp = model.data_parallel
+        if train and dp is not None:
+            self.grad_scale = dp.grad_scale()
         self._build_forward()
         if train:
             self._build_backward()
@@ -113,6 +138,14 @@ class Plan(object):
         if p._dev is None:
             raise RuntimeError("parameter %s is not part of the model's parameter store" % p.name)
         return p._dev
+
+    def _f(self, label, fn, flops=0, nbytes=0, kind='hbm'):
+        self.fwd_ops.append(Launch(label, fn, flops, nbytes, kind))
+
+    def _b(self, label, fn, flops=0, nbytes=0, kind='hbm'):
+        l = Launch(label, fn, flops, nbytes, kind)
+        self.bwd_ops.append(l)
+        return l
 
     # ------------------------------------------------------------------ forward
     def _build_forward(self):
@@ -144,21 +177,24 @@ class Plan(object):
                 self._plan_input(n)
             elif isinstance(n, UpConv):
                 x = self.val[n.parent]
-                y = self.val.get(n) or self._new(n)
+                y = self.val[n] if n in self.val else self._new(n)
                 self.val[n] = y
-                op = ops.UpConvOp(h, x, y, self._pdev(n.w), self._pdev(n.b), n.pool_shape, n.activation_func, self.compute)
+                op = ops.UpConvOp(h, x, y, self._pdev(n.w), self._pdev(n.b), n.pool_shape, n.activation_func,
+                                  self.compute)
                 self.conv_ops[n] = op
                 self.pack_ops.append(op)
-                self.fwd_ops.append(op.fwd)
+                fl = 2.0 * _nel(x) * n.n_f * int(np.prod(n.pool_shape))
+                self._f('upconv_fwd:' + n.name, op.fwd, fl, 4 * (_nel(x) + _nel(y)),
+                        'tensor' if _tensor_shaped(x.desc.c, n.n_f) else 'hbm')
             elif isinstance(n, Conv):
                 self._plan_conv(n)
             elif isinstance(n, Pool):
                 x = self.val[n.parent]
                 y = self._new(n)
                 self.val[n] = y
-                op = ops.PoolOp(h, x, y, n.pool_shape, keep_argmax=self.train)
+                op = ops.PoolOp(h, x, y, n.pool_shape, keep_argmax=self.train, tie_mode=config.pool_tie_mode)
                 self.aux[n] = op
-                self.fwd_ops.append(op.fwd)
+                self._f('pool_fwd:' + n.name, op.fwd, 0, 4 * (_nel(x) + _nel(y)))
             elif isinstance(n, Crop):
                 src = self.val[n.parent]
                 if n in self.crop_into:
@@ -170,13 +206,13 @@ class Plan(object):
                     self.val[n] = dst
                 op = ops.CropConcatOp(h, src, dst, n.crop, c0)
                 self.aux[n] = op
-                self.fwd_ops.append(op.fwd)
+                self._f('crop_concat_fwd:' + n.name, op.fwd, 0, 8 * _nel(self.val[n]))
             elif isinstance(n, Concat):
                 cops = []
                 for p, c0 in self.copy_into.get(n, []):
                     op = ops.CropConcatOp(h, self.val[p], self.val[n], (0, 0, 0), c0)
                     cops.append((p, op))
-                    self.fwd_ops.append(op.fwd)
+                    self._f('concat_copy:' + n.name, op.fwd, 0, 8 * _nel(self.val[p]))
                 self.aux[n] = cops
             elif isinstance(n, FragmentsToDense):
                 x = self.val[n.parent]
@@ -184,7 +220,7 @@ class Plan(object):
                 self.val[n] = y
                 op = ops.Frag2DenseOp(h, x, y, n.parent.shape.mfp_offsets, n.parent.shape.strides)
                 self.aux[n] = op
-                self.fwd_ops.append(op.fwd)
+                self._f('frag2dense_fwd:' + n.name, op.fwd, 0, 8 * _nel(x))
             else:
                 raise NotImplementedError("Node type %s is not on the B200 hot path" % type(n).__name__)
         self._plan_loss_head()
@@ -198,33 +234,38 @@ class Plan(object):
             staging = None  # (b,1,z,x,y) is already channels-last
         else:
             staging = torch.empty(shape, dtype=torch.float32, device=self.device)
-            self.fwd_ops.append(lambda t=t, s=staging: self.h.call('e2_ncdhw_to_ndhwc', C.byref(t.desc), _lib.ptr(s),
-                                                                   t.ptr(), self.h.stream()))
+            self._f('layout_in:' + n.name,
+                    lambda t=t, s=staging: self.h.call('e2_ncdhw_to_ndhwc', C.byref(t.desc), _lib.ptr(s), t.ptr(),
+                                                       self.h.stream()), 0, 8 * _nel(t))
         self.inputs[n] = (t, pinned, staging)
 
     def _plan_conv(self, n):
         h = self.h
         x = self.val[n.parent]
-        y = self.val.get(n) or self._new(n)
+        y = self.val[n] if n in self.val else self._new(n)
         self.val[n] = y
         pooled = any(p > 1 for p in n.pool_shape)
         w, b = self._pdev(n.w), self._pdev(n.b)
+        lsp = [s + 1 - f for s, f in zip(n.parent.shape.spatial_shape, n.filter_shape)]
+        flops = 2.0 * x.desc.n * int(np.prod(lsp)) * int(np.prod(n.w_sh))
+        kind = 'tensor' if _tensor_shaped(x.desc.c, n.n_f) else 'hbm'
         if not pooled:
             op = ops.ConvOp(h, x, y, w, b, n.filter_shape, n.activation_func, self.compute)
-            self.fwd_ops.append(op.fwd)
+            self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(y)), kind)
         else:
             # conv -> pool|MFP -> +bias -> act  (neural.py:662-712): the conv writes raw
             # accumulators, the pooling kernel carries the bias/activation epilogue
-            lsp = [s + 1 - f for s, f in zip(n.parent.shape.spatial_shape, n.filter_shape)]
             lin = DevTensor(x.desc.n, lsp[0], lsp[1], lsp[2], n.n_f, device=self.device)
             op = ops.ConvOp(h, x, lin, w, None, n.filter_shape, 'lin', self.compute)
-            self.fwd_ops.append(op.fwd)
+            self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(lin)), kind)
             if n.mfp:
                 pop = ops.MfpOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train)
+                self._f('mfp_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
             else:
-                pop = ops.PoolOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train)
+                pop = ops.PoolOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train,
+                                 tie_mode=config.pool_tie_mode)
+                self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
             self.aux[n] = (lin, pop)
-            self.fwd_ops.append(pop.fwd)
         self.conv_ops[n] = op
         self.pack_ops.append(op)
 
@@ -245,7 +286,7 @@ class Plan(object):
             raise NotImplementedError("MultinoulliNLL must consume the planned Softmax node")
         self.loss_op = ops.LossOp(self.h, logits, target, probs)
         self.logits_node = sm.parent
-        self.fwd_ops.append(self.loss_op.fwd)
+        self._f('softmax_nll_fwd', self.loss_op.fwd, 0, 4 * (2 * _nel(logits) + logits.desc.positions))
 
     # ----------------------------------------------------------------- backward
     def _build_backward(self):
@@ -253,49 +294,53 @@ class Plan(object):
             raise ValueError("a training plan needs a Softmax -> MultinoulliNLL -> AggregateLoss head")
         h = self.h
         self.grad, written = {}, set()
-        # gradient buffers (aliases follow the forward aliasing)
         for n in self.nodes:
-            if n in self.val and not isinstance(n, (Input,)) and isinstance(self.val[n], DevTensor) \
-                    and not isinstance(n, loss_nodes.Softmax):
+            if n in self.val and not isinstance(n, (Input, loss_nodes.Softmax)):
                 if n in self.alias_of or n in self.crop_into:
                     continue
                 self.grad[n] = self.val[n].like()
         for n, (cat, c0) in self.alias_of.items():
             self.grad[n] = self.grad[cat].channel_slice(c0, n.shape['f'])
-        self.grad_scale = 1.0
         lg = self.logits_node
-        self.bwd_ops.append(lambda: self.loss_op.bwd(self.grad[lg], self.grad_scale))
+        self._b('softmax_nll_bwd', lambda: self.loss_op.bwd(self.grad[lg], self.grad_scale), 0,
+                4 * 3 * _nel(self.grad[lg]))
         written.add(lg)
-        self.wgrad_done = []  # (node, launch index) -- used to place all-reduce buckets
         for n in reversed(self.nodes):
             if n not in written and n not in self.crop_into:
                 continue
             if isinstance(n, UpConv):
                 dy, op = self.grad[n], self.conv_ops[n]
-                if n.activation_func not in ('lin', 'linear'):
-                    self.bwd_ops.append(lambda n=n, dy=dy: ops.act_bwd(h, dy, n.activation_func, self.val[n], dy, dy))
-                self.bwd_ops.append(lambda op=op, dy=dy, n=n: op.wgrad(dy, n.w._grad, n.b._grad))
-                self.wgrad_done.append((n, len(self.bwd_ops)))
-                self._emit_dgrad(op, dy, n.parent, written)
+                self._emit_act_bwd(n, dy)
+                fl = 2.0 * _nel(op.x) * n.n_f * int(np.prod(n.pool_shape))
+                kind = 'tensor' if _tensor_shaped(op.x.desc.c, n.n_f) else 'hbm'
+                l = self._b('upconv_wgrad:' + n.name, lambda op=op, dy=dy, n=n: op.wgrad(dy, n.w._grad, n.b._grad),
+                            fl, 4 * (_nel(op.x) + _nel(dy)), kind)
+                l.param_end = n.w._offset + int(np.prod(n.w.shape))
+                self._emit_dgrad(op, dy, n.parent, written, 'upconv_dgrad:' + n.name, fl, kind)
             elif isinstance(n, Conv):
                 dy, op = self.grad[n], self.conv_ops[n]
-                if n.activation_func not in ('lin', 'linear'):
-                    self.bwd_ops.append(lambda n=n, dy=dy: ops.act_bwd(h, dy, n.activation_func, self.val[n], dy, dy))
+                self._emit_act_bwd(n, dy)
                 if n in self.aux:
                     lin, pop = self.aux[n]
                     dlin = lin.like()
-                    self.bwd_ops.append(lambda pop=pop, dy=dy, dlin=dlin: pop.bwd(dy, dlin))
+                    self._b(('mfp_bwd:' if n.mfp else 'pool_bwd:') + n.name,
+                            lambda pop=pop, dy=dy, dlin=dlin: pop.bwd(dy, dlin), 0, 4 * (2 * _nel(dy) + _nel(dlin)))
                 else:
                     dlin = dy
-                self.bwd_ops.append(lambda op=op, dlin=dlin, n=n: op.wgrad(dlin, n.w._grad, n.b._grad))
-                self.wgrad_done.append((n, len(self.bwd_ops)))
-                self._emit_dgrad(op, dlin, n.parent, written)
+                fl = 2.0 * dlin.desc.positions * int(np.prod(n.w_sh))
+                kind = 'tensor' if _tensor_shaped(op.x.desc.c, n.n_f) else 'hbm'
+                l = self._b('conv_wgrad:' + n.name, lambda op=op, dlin=dlin, n=n: op.wgrad(dlin, n.w._grad, n.b._grad),
+                            fl, 4 * (_nel(op.x) + _nel(dlin)), kind)
+                l.param_end = n.w._offset + int(np.prod(n.w.shape))
+                self._emit_dgrad(op, dlin, n.parent, written, 'conv_dgrad:' + n.name, fl, kind)
             elif isinstance(n, Pool):
                 par = n.parent
                 if isinstance(par, Input):
                     continue
                 acc = par in written
-                self.bwd_ops.append(lambda op=self.aux[n], dy=self.grad[n], dx=self.grad[par], acc=acc: op.bwd(dy, dx, acc))
+                self._b('pool_bwd:' + n.name,
+                        lambda op=self.aux[n], dy=self.grad[n], dx=self.grad[par], acc=acc: op.bwd(dy, dx, acc), 0,
+                        4 * (2 * _nel(self.grad[n]) + _nel(self.grad[par])))
                 written.add(par)
             elif isinstance(n, Crop):
                 par = n.parent
@@ -309,7 +354,9 @@ class Plan(object):
                 else:
                     ddst = self.grad[n]
                 acc = par in written
-                self.bwd_ops.append(lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc: op.bwd(ddst, dx, acc))
+                self._b('crop_concat_bwd:' + n.name,
+                        lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc: op.bwd(ddst, dx, acc), 0,
+                        4 * (_nel(self.val[n]) + (2 if acc else 1) * _nel(self.grad[par])))
                 written.add(par)
             elif isinstance(n, Concat):
                 for p in n.parents:
@@ -319,20 +366,31 @@ class Plan(object):
                     if isinstance(p, Input):
                         continue
                     acc = p in written
-                    self.bwd_ops.append(lambda op=op, ddst=self.grad[n], dx=self.grad[p], acc=acc: op.bwd(ddst, dx, acc))
+                    self._b('concat_copy_bwd:' + n.name,
+                            lambda op=op, ddst=self.grad[n], dx=self.grad[p], acc=acc: op.bwd(ddst, dx, acc), 0,
+                            8 * _nel(self.grad[p]))
                     written.add(p)
             elif isinstance(n, FragmentsToDense):
                 par = n.parent
                 if par in written:
                     raise NotImplementedError("FragmentsToDense parent with several consumers")
-                self.bwd_ops.append(lambda op=self.aux[n], dd=self.grad[n], df=self.grad[par]: op.bwd(dd, df))
+                self._b('frag2dense_bwd:' + n.name,
+                        lambda op=self.aux[n], dd=self.grad[n], df=self.grad[par]: op.bwd(dd, df), 0,
+                        8 * _nel(self.grad[par]))
                 written.add(par)
 
-    def _emit_dgrad(self, op, dy, parent, written):
+    def _emit_act_bwd(self, n, dy):
+        if n.activation_func not in ('lin', 'linear'):
+            h = self.h
+            self._b('act_bwd:' + n.name,
+                    lambda n=n, dy=dy: ops.act_bwd(h, dy, n.activation_func, self.val[n], dy, dy), 0, 12 * _nel(dy))
+
+    def _emit_dgrad(self, op, dy, parent, written, label, flops, kind):
         if isinstance(parent, Input):
             return  # gradients are taken w.r.t. parameters only (model.py:182)
         acc = parent in written
-        self.bwd_ops.append(lambda op=op, dy=dy, dx=self.grad[parent], acc=acc: op.dgrad(dy, dx, acc))
+        self._b(label, lambda op=op, dy=dy, dx=self.grad[parent], acc=acc: op.dgrad(dy, dx, acc), flops,
+                4 * (_nel(dy) + _nel(self.grad[parent])), kind)
         written.add(parent)
 
     # ---------------------------------------------------------------- execution
@@ -343,7 +401,8 @@ class Plan(object):
         self._packed_version = self.store.version
 
     def feed(self, values):
-        """H2D copies of the inputs from pinned host memory (async on the current stream)."""
+        """H2D copies of the inputs from pinned host memory (async on the current stream).
+        Returns the number of bytes copied."""
         nbytes = 0
         for n, a in values.items():
             t, pinned, staging = self.inputs[n]
@@ -356,14 +415,25 @@ class Plan(object):
             nbytes += pinned.numel() * 4
         return nbytes
 
-    def _launch_all(self):
+    def _launch_all(self, hook=None):
         for f in self.fwd_ops:
             f()
         for f in self.bwd_ops:
             f()
+            if hook is not None and f.param_end is not None:
+                hook(f.param_end)
 
     def execute(self):
-        """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph."""
+        """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.
+        With data parallelism the bucketed all-reduce is interleaved with the backward
+        launches (and the step is not graph-captured)."""
+        dp = self.model.data_parallel if self.train else None
+        if dp is not None and dp.world > 1:
+            self.pack()
+            dp.begin_step(self.store)
+            self._launch_all(hook=dp.on_gradients_ready)
+            dp.finish_step(self.store)
+            return
         if self.train:
             # weights change every step: the re-pack is part of the step itself
             if self.use_graph:
@@ -382,7 +452,7 @@ class Plan(object):
                 self._launch_all()
             return
         if self._packed_version != self.store.version:
-            self.pack()
+            self.pack(need_dgrad=False)
         if self.use_graph:
             if self._graph is None:
                 self._launch_all()
@@ -396,10 +466,33 @@ class Plan(object):
             self._launch_all()
 
     def launches_per_step(self):
+        """Kernel launches of one step (counted by the library, eager pass)."""
         before = self.h.launches
         self.pack()
         self._launch_all()
+        torch.cuda.synchronize(self.device)
         return self.h.launches - before
+
+    def profile(self, repeats=3):
+        """Per-launch device times (ms, CUDA events on the launching stream), eager
+        passes after one warm-up; returns [(label, kind, flops, bytes, ms)]."""
+        self.pack()
+        self._launch_all()
+        torch.cuda.synchronize(self.device)
+        all_ops = self.fwd_ops + self.bwd_ops
+        acc = [0.0] * len(all_ops)
+        for _ in range(repeats):
+            evs = []
+            for f in all_ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                f()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize(self.device)
+            for i, (a, b) in enumerate(evs):
+                acc[i] += a.elapsed_time(b)
+        return [(f.label, f.kind, f.flops, f.bytes, acc[i] / repeats) for i, f in enumerate(all_ops)]
 
     def fetch(self, node):
         if isinstance(node, loss_nodes.AggregateLoss):

@@ -52,7 +52,7 @@ class ConvOp(object):
 
     def fwd(self, act=None, has_bias=None, y=None):
         d = self.d if (act is None and has_bias is None and y is None) else self._desc(act=act, has_bias=has_bias, y=y)
-        yy = y or self.y
+        yy = y if y is not None else self.y
         self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), None, 0, self.h.stream())
 
@@ -197,7 +197,8 @@ class LossOp(object):
         self.scalars = _dev_f32(4, logits.buf.device)
 
     def fwd(self):
-        self.h.call('e2_softmax_nll_fwd', C.byref(self.logits.desc), self.logits.ptr(), self.target.ptr(),
+        self.h.call('e2_softmax_nll_fwd', C.byref(self.logits.desc), self.logits.ptr(),
+                    self.target.ptr() if self.target is not None else None,
                     self.probs.ptr(), _lib.ptr(self.scalars), self.h.stream())
 
     def bwd(self, dlogits, grad_scale=1.0):

@@ -1,0 +1,131 @@
+"""Multi-GPU execution: one process per GPU, torch.distributed (NCCL over NVLink /
+NVSwitch) for the plumbing.
+
+The reference has no multi-GPU code at all; both modes below are new
+capabilities whose single-GPU numerics are what the parity tests pin.
+
+* Training shards the batch: every rank holds the full model and its own patch
+  (reference batch_size is 1, so global batch == world size).  Gradients live in ONE
+  flat buffer laid out in reverse graph order, so the backward pass completes it front
+  to back; it is all-reduced in buckets on a side stream, each bucket launched as soon
+  as the wgrad kernels that fill it have been enqueued, overlapping with the remaining
+  dgrad/wgrad work.  The mean over ranks is folded into the loss gradient
+  (grad_scale = 1/world), so the collective is a plain sum.
+  Caveat: MultinoulliNLL normalises by the *local* labelled-voxel count
+  (loss.py:342-345); the mean of shard gradients equals the global-batch gradient when
+  every shard has the same labelled count (true for dense labels).
+* Dense inference shards the tile list (neuromancer/dense.shard_tiles): tiles are
+  independent given their halos, which are re-read from the host volume -> no
+  collective on the data path.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def bucket_ranges(entries, total, bucket_floats):
+    """Split [0,total) of the flat gradient buffer into contiguous buckets of roughly
+    ``bucket_floats`` that end on parameter boundaries.  ``entries``: (key, param, offset,
+    size) in buffer order.  Returns [(start, end, last_entry_index)]."""
+    out, start = [], 0
+    for i, (_, _, off, size) in enumerate(entries):
+        end = off + (size + 3) // 4 * 4
+        last = i == len(entries) - 1
+        if end - start >= bucket_floats or last:
+            out.append((start, total if last else end, i))
+            start = end
+    return out
+
+
+class DataParallel(object):
+    """Gradient all-reduce for a ``neuromancer.Model``."""
+
+    def __init__(self, model, bucket_mb=25.0, overlap=True):
+        self.model = model
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.bucket_floats = int(bucket_mb * 1024 * 1024 / 4)
+        self.overlap = overlap
+        self.comm_stream = None
+        model.data_parallel = self
+        self.bytes_reduced = 0
+
+    def broadcast_parameters(self, store):
+        """Rank 0's weights everywhere (identical init is also given by the shared seed)."""
+        if self.world > 1:
+            dist.broadcast(store.P, src=0)
+            store.version += 1
+
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def allreduce_gradients(self, store):
+        """Simple form: one collective over the whole flat buffer on the current stream.
+        Used when the step did not go through ``begin_step`` / ``finish_step``."""
+        if self.world > 1 and not self._step_reduced:
+            dist.all_reduce(store.G, op=dist.ReduceOp.SUM)
+            self.bytes_reduced += store.G.numel() * 4
+        self._step_reduced = False
+
+    # -- overlapped, bucketed form (driven by executor.Plan.execute) ------------------
+    _step_reduced = False
+
+    def begin_step(self, store):
+        if getattr(self, '_buckets', None) is None:
+            # weight region in buckets, the (tiny) bias tail as the last bucket
+            w_entries = [e for e in store.entries if e[2] < store.n_reg]
+            self._buckets = [(s, e) for s, e, _ in bucket_ranges(w_entries, store.n_reg, self.bucket_floats)]
+            if store.total > store.n_reg:
+                self._buckets.append((store.n_reg, store.total))
+            if torch.cuda.is_available() and store.G.is_cuda:
+                self.comm_stream = torch.cuda.Stream(device=store.G.device)
+        self._next, self._works = 0, []
+
+    def _launch_bucket(self, store, s, e):
+        view = store.G[s:e]
+        if self.comm_stream is not None and self.overlap:
+            ev = torch.cuda.Event()
+            ev.record()                       # everything enqueued so far on the compute stream
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+        else:
+            self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+        self.bytes_reduced += (e - s) * 4
+
+    def on_gradients_ready(self, end_offset):
+        """Called after a wgrad launch: gradients in [0, end_offset) of the weight region
+        are (stream-ordered) complete -> launch every bucket that lies inside."""
+        store = self.model._store
+        while self._next < len(self._buckets) and self._buckets[self._next][1] <= min(end_offset, store.n_reg) \
+                and self._buckets[self._next][0] < store.n_reg:
+            s, e = self._buckets[self._next]
+            self._launch_bucket(store, s, e)
+            self._next += 1
+
+    def finish_step(self, store):
+        while self._next < len(self._buckets):
+            s, e = self._buckets[self._next]
+            self._launch_bucket(store, s, e)
+            self._next += 1
+        for w in self._works:
+            w.wait()                          # compute stream waits for the collectives
+        if self.comm_stream is not None and self.overlap:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._step_reduced = True

@@ -210,7 +210,8 @@ int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, f
  * (loss.py:261-347, EPS=1e-5) -> AggregateLoss mean (loss.py:1346-1363) and
  * Classification/_Errors (loss.py:736-737, 805-807) in one pass.
  * out_scalars (device float[4]): loss_sum (sum of -log(p_t+EPS) over labelled voxels), n_labelled, n_errors, unused.
- * The caller finishes: loss = loss_sum / (n_labelled + EPS). */
+ * The caller finishes: loss = loss_sum / (n_labelled + EPS).
+ * target == NULL computes the Softmax node alone (inference). */
 int e2_softmax_nll_fwd(e2_handle* h, const e2_tensor* logits, const float* x, const float* target, float* probs,
                        float* out_scalars, void* stream);
 /* dlogits given scalars from the forward pass; grad_scale multiplies the result (1/N for data parallel means) */

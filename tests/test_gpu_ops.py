@@ -1,0 +1,405 @@
+"""GPU parity tests: every op of the hot path, called through the C ABI
+(elektronn2_b200.ops -> ctypes -> libe2b200.so), against the CPU oracle on the same
+seeded inputs, plus the committed golden vectors.
+
+Tolerances (north star): pooling / MFP / fragments->dense / crop-concat and all index
+outputs are BIT-EXACT; conv / upconv forward, dgrad and wgrad must satisfy
+max|got-ref| / max|ref| <= 1e-3 in TF32 mode (tcgen05 kind::tf32, fp32 accumulate) and
+<= 2e-5 in F32 mode (CUDA-core FFMA; differences are summation order only).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import ops as oo, loss as ol, adam as oadam  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = {'f32': 2e-5, 'tf32': 1e-3}
+
+
+@pytest.fixture(scope='module')
+def h():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from elektronn2_b200 import _lib
+    return _lib.get_handle(0)
+
+
+def dev(a):
+    from elektronn2_b200.devtensor import DevTensor
+    return DevTensor.from_numpy(np.asarray(a, np.float32))
+
+
+def empty(n, c, sp):
+    from elektronn2_b200.devtensor import DevTensor
+    return DevTensor(n, sp[0], sp[1], sp[2], c)
+
+
+def rel(got, ref):
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(np.asarray(got, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+
+
+# ------------------------------------------------------------------------ layout
+@pytest.mark.parametrize('shape', [(1, 1, 3, 5, 7), (2, 20, 4, 9, 33), (1, 45, 2, 3, 4), (3, 64, 5, 6, 7)])
+def test_layout_roundtrip(h, shape):
+    a = np.random.RandomState(0).rand(*shape).astype(np.float32)
+    d = dev(a)
+    assert np.array_equal(d.numpy(), a)
+    # the device image really is channels-last with the advertised pitch
+    raw = d.buf.cpu().numpy().reshape(shape[0], shape[2], shape[3], shape[4], d.desc.c_pitch)
+    assert np.array_equal(raw[..., :shape[1]], a.transpose(0, 2, 3, 4, 1))
+
+
+def test_u8_scaling_bit_exact(h):
+    from elektronn2_b200 import _lib
+    raw = np.arange(256, dtype=np.uint8).repeat(5)[:1277]
+    src = torch.from_numpy(raw).cuda()
+    dst = torch.empty(raw.size, dtype=torch.float32, device='cuda')
+    h.call('e2_u8_to_f32', _lib.ptr(src), _lib.ptr(dst), raw.size, _lib.C.c_float(255.0), h.stream())
+    assert np.array_equal(dst.cpu().numpy(), raw.astype(np.float32) / 255)   # node_basic.py:910
+    p = np.random.RandomState(1).rand(1000).astype(np.float32)
+    out = torch.empty(1000, dtype=torch.uint8, device='cuda')
+    h.call('e2_f32_to_u8', _lib.ptr(t(p)), _lib.ptr(out), 1000, _lib.C.c_float(255.0), h.stream())
+    assert np.array_equal(out.cpu().numpy(), (p * 255).astype(np.uint8))     # node_basic.py:990-996
+
+
+# -------------------------------------------------------------------------- conv
+CONV_CASES = [
+    # (n, c_in, spatial, c_out, k)
+    (1, 1, (5, 20, 21), 20, (1, 4, 4)),      # first layer of neuro3d_lite (c_in == 1 kernel)
+    (1, 1, (6, 12, 12), 32, (3, 3, 3)),      # first layer of unet3d
+    (2, 20, (5, 12, 11), 40, (3, 3, 3)),     # odd channel counts
+    (1, 40, (4, 9, 9), 150, (2, 4, 4)),      # even, asymmetric kernel
+    (1, 35, (3, 8, 8), 42, (1, 3, 3)),       # litelite channels
+    (1, 32, (6, 10, 18), 64, (3, 3, 3)),     # unet3d conv1 shape family
+    (1, 64, (5, 9, 10), 64, (3, 3, 3)),
+    (1, 200, (2, 6, 6), 200, (1, 1, 1)),     # 1x1x1 (the reference's tensordot shortcut)
+    (1, 200, (2, 6, 6), 2, (1, 1, 1)),       # last layer, c_out == 2
+    (1, 128, (4, 6, 6), 256, (3, 3, 3)),
+]
+
+
+@pytest.mark.parametrize('compute', ['f32', 'tf32'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(h, case, compute):
+    from elektronn2_b200.ops import ConvOp
+    n, ci, sp, co, k = case
+    r = np.random.RandomState(hash(case) % 2**31)
+    x = r.rand(n, ci, *sp).astype(np.float32)
+    w = (r.randn(co, ci, *k) * np.sqrt(2.0 / (ci * np.prod(k)))).astype(np.float32)
+    b = (r.randn(co) * 0.1).astype(np.float32)
+    osp = [s - f + 1 for s, f in zip(sp, k)]
+    xd, yd = dev(x), empty(n, co, osp)
+    op = ConvOp(h, xd, yd, t(w), t(b), k, 'relu', compute)
+    op.pack()
+    op.fwd()
+    ref = oo.activation(oo.conv3d(x, w) + b.reshape(1, -1, 1, 1, 1), 'relu')
+    assert rel(yd.numpy(), ref) <= TOL[compute]
+    # linear epilogue, no bias
+    op.fwd(act='lin', has_bias=0)
+    assert rel(yd.numpy(), oo.conv3d(x, w)) <= TOL[compute]
+    dy = r.randn(n, co, *osp).astype(np.float32)
+    dyd = dev(dy)
+    if ci > 1:
+        dxd = empty(n, ci, sp)
+        op.dgrad(dyd, dxd)
+        ref_dx = oo.conv3d_dgrad(dy, w, x.shape)
+        assert rel(dxd.numpy(), ref_dx) <= TOL[compute]
+        op.dgrad(dyd, dxd, accumulate=True)          # second consumer of the same tensor
+        assert rel(dxd.numpy(), 2 * ref_dx) <= TOL[compute]
+    dw = torch.zeros(w.shape, device='cuda')
+    db = torch.zeros(co, device='cuda')
+    op.wgrad(dyd, dw, db)
+    assert rel(dw.cpu().numpy(), oo.conv3d_wgrad(dy, x, w.shape)) <= TOL[compute]
+    assert rel(db.cpu().numpy(), oo.bias_grad(dy)) <= 1e-5
+
+
+def test_conv_matches_np_convolve(h):
+    """The reference's own known answer (tests/test_conv.py:89-104): true convolution."""
+    from elektronn2_b200.ops import ConvOp
+    r = np.random.RandomState(3)
+    x = r.rand(1, 1, 1, 1, 300).astype(np.float32)
+    w = r.randn(1, 1, 1, 1, 9).astype(np.float32)
+    xd, yd = dev(x), empty(1, 1, (1, 1, 292))
+    op = ConvOp(h, xd, yd, t(w), None, (1, 1, 9), 'lin', 'f32')
+    op.pack()
+    op.fwd()
+    assert np.allclose(yd.numpy()[0, 0, 0, 0], np.convolve(x[0, 0, 0, 0], w[0, 0, 0, 0], 'valid'), atol=1e-5)
+
+
+def test_conv_golden(h):
+    from elektronn2_b200.ops import ConvOp, PoolOp
+    g = np.load(os.path.join(HERE, 'golden', 'ops_small.npz'))
+    x, w, b = g['conv_x'], g['conv_w'], g['conv_b']
+    xd, lin = dev(x), empty(2, 7, g['conv_lin'].shape[2:])
+    op = ConvOp(h, xd, lin, t(w), None, (2, 3, 4), 'lin', 'f32')
+    op.pack()
+    op.fwd()
+    assert rel(lin.numpy(), g['conv_lin']) <= 2e-5
+    y = empty(2, 7, g['conv_y_pool122_relu'].shape[2:])
+    PoolOp(h, lin, y, (1, 2, 2), bias=t(b), act='relu').fwd()         # conv -> pool -> +bias -> relu
+    assert rel(y.numpy(), g['conv_y_pool122_relu']) <= 2e-5
+    dyd, dxd = dev(g['conv_dy']), empty(2, 5, x.shape[2:])
+    op.dgrad(dyd, dxd)
+    assert rel(dxd.numpy(), g['conv_dx']) <= 2e-5
+    dw, db = torch.zeros(w.shape, device='cuda'), torch.zeros(7, device='cuda')
+    op.wgrad(dyd, dw, db)
+    assert rel(dw.cpu().numpy(), g['conv_dw']) <= 2e-5 and rel(db.cpu().numpy(), g['conv_db']) <= 1e-5
+
+
+def test_conv_invalid_descriptor_raises(h):
+    from elektronn2_b200.ops import ConvOp
+    from elektronn2_b200._lib import E2InvalidError
+    xd, yd = empty(1, 4, (5, 5, 5)), empty(1, 4, (4, 4, 4))   # wrong output extent for k=3
+    op = ConvOp(h, xd, yd, torch.zeros(4, 4, 3, 3, 3, device='cuda'), None, (3, 3, 3), 'lin', 'f32')
+    with pytest.raises(ValueError):
+        op.pack()
+    with pytest.raises(E2InvalidError, match="output extents"):
+        op.fwd()
+
+
+# ------------------------------------------------------------------------ upconv
+@pytest.mark.parametrize('compute', ['f32', 'tf32'])
+@pytest.mark.parametrize('case', [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (2, 6, (3, 4, 5), 4, (1, 2, 2)),
+                                  (1, 64, (3, 4, 5), 64, (2, 2, 2)), (1, 35, (2, 5, 5), 30, (1, 2, 2))])
+def test_upconv(h, case, compute):
+    from elektronn2_b200.ops import UpConvOp
+    n, ci, sp, co, p = case
+    r = np.random.RandomState(11)
+    x = r.rand(n, ci, *sp).astype(np.float32)
+    w = (r.randn(co, ci, *p) * 0.2).astype(np.float32)
+    b = (r.randn(co) * 0.1).astype(np.float32)
+    osp = [s * q for s, q in zip(sp, p)]
+    xd, yd = dev(x), empty(n, co, osp)
+    op = UpConvOp(h, xd, yd, t(w), t(b), p, 'relu', compute)
+    op.pack()
+    op.fwd()
+    ref, _ = oo.upconv_node_fwd(x, w, b, p, 'relu')
+    assert rel(yd.numpy(), ref) <= TOL[compute]
+    dy = r.randn(n, co, *osp).astype(np.float32)
+    dyd, dxd = dev(dy), empty(n, ci, sp)
+    op.dgrad(dyd, dxd)
+    assert rel(dxd.numpy(), oo.upconv3d_dgrad(dy, w, p)) <= TOL[compute]
+    dw, db = torch.zeros(w.shape, device='cuda'), torch.zeros(co, device='cuda')
+    op.wgrad(dyd, dw, db)
+    assert rel(dw.cpu().numpy(), oo.upconv3d_wgrad(dy, x, p)) <= TOL[compute]
+    assert rel(db.cpu().numpy(), oo.bias_grad(dy)) <= 1e-5
+
+
+def test_upconv_writes_into_concat_slice(h):
+    """UpConv output lands directly in channels [0,F) of a wider Concat buffer."""
+    from elektronn2_b200.ops import UpConvOp, CropConcatOp
+    r = np.random.RandomState(5)
+    x = r.rand(1, 6, 2, 3, 3).astype(np.float32)
+    w = (r.randn(5, 6, 1, 2, 2) * 0.3).astype(np.float32)
+    skip = r.rand(1, 3, 4, 10, 10).astype(np.float32)
+    cat = empty(1, 8, (2, 6, 6))
+    op = UpConvOp(h, dev(x), cat.channel_slice(0, 5), t(w), None, (1, 2, 2), 'lin', 'f32')
+    op.pack()
+    op.fwd()
+    CropConcatOp(h, dev(skip), cat, (1, 2, 2), 5).fwd()
+    ref = oo.concat_f([oo.upconv3d(x, w, (1, 2, 2)), oo.crop(skip, (1, 2, 2))])   # (lo_res, hi_res) order
+    assert rel(cat.numpy(), ref) <= 2e-5
+
+
+# -------------------------------------------------------------------------- pool
+@pytest.mark.parametrize('case', [(2, 3, (4, 6, 8), (2, 2, 2)), (1, 20, (5, 12, 10), (1, 2, 2)),
+                                  (1, 64, (4, 8, 8), (2, 2, 2)), (1, 150, (4, 5, 5), (2, 1, 1)),
+                                  (1, 7, (6, 9, 4), (2, 3, 2))])
+def test_maxpool_bit_exact(h, case):
+    from elektronn2_b200.ops import PoolOp
+    n, c, sp, p = case
+    r = np.random.RandomState(21)
+    x = r.rand(n, c, *sp).astype(np.float32)
+    x[0, 0, :p[0], :p[1], :p[2]] = 0.5          # a window of ties
+    x = np.maximum(x - 0.3, 0)                  # plenty of exact zeros (post-ReLU-like ties)
+    osp = [s // q for s, q in zip(sp, p)]
+    xd, yd = dev(x), empty(n, c, osp)
+    op = PoolOp(h, xd, yd, p)
+    op.fwd()
+    assert np.array_equal(yd.numpy(), oo.pooling(x, p))
+    assert np.array_equal(yd.numpy(), oo.pooling_theano_shaped(x, p))
+    assert np.array_equal(op.argmax.int_numpy(), oo.pooling_argmax(x, p))       # first max in (z,x,y) scan order
+    dy = r.randn(n, c, *osp).astype(np.float32)
+    dyd, dxd = dev(dy), empty(n, c, sp)
+    op.bwd(dyd, dxd)
+    assert np.array_equal(dxd.numpy(), oo.pooling_bwd(dy, x, p, 'first').astype(np.float32))
+    op.bwd(dyd, dxd, accumulate=True)
+    assert np.array_equal(dxd.numpy(), (2 * oo.pooling_bwd(dy, x, p, 'first')).astype(np.float32))
+    op_all = PoolOp(h, xd, yd, p, tie_mode='all')
+    op_all.fwd()
+    op_all.bwd(dyd, dxd)
+    assert np.array_equal(dxd.numpy(), oo.pooling_bwd(dy, x, p, 'all').astype(np.float32))   # Theano-CPU rule
+
+
+def test_maxpool_golden_and_fused_epilogue(h):
+    from elektronn2_b200.ops import PoolOp
+    g = np.load(os.path.join(HERE, 'golden', 'ops_small.npz'))
+    x = g['pool_x']
+    xd, yd = dev(x), empty(2, 3, (2, 3, 4))
+    op = PoolOp(h, xd, yd, (2, 2, 2))
+    op.fwd()
+    assert np.array_equal(yd.numpy(), g['pool_y222']) and np.array_equal(op.argmax.int_numpy(), g['pool_idx222'])
+    dxd = empty(2, 3, (4, 6, 8))
+    op.bwd(dev(g['pool_dy']), dxd)
+    assert np.array_equal(dxd.numpy(), g['pool_dx_first'].astype(np.float32))
+    b = np.array([0.25, -0.5, 0.125], np.float32)
+    PoolOp(h, xd, yd, (2, 2, 2), bias=t(b), act='relu').fwd()
+    assert np.array_equal(yd.numpy(), np.maximum(g['pool_y222'] + b.reshape(1, 3, 1, 1, 1), 0))
+
+
+def test_maxpool_rejects_non_dividing_axes(h):
+    from elektronn2_b200.ops import PoolOp
+    with pytest.raises(ValueError, match="cannot downsample"):
+        PoolOp(h, empty(1, 4, (5, 6, 6)), empty(1, 4, (2, 3, 3)), (2, 2, 2)).fwd()
+
+
+# --------------------------------------------------------------------------- MFP
+@pytest.mark.parametrize('case', [(1, 3, (7, 9, 11), (2, 2, 2)), (1, 20, (5, 13, 13), (1, 2, 2)),
+                                  (4, 8, (7, 7, 7), (2, 1, 1)), (1, 5, (9, 8, 11), (2, 3, 2))])
+def test_mfp_bit_exact_fragment_order(h, case):
+    from elektronn2_b200.ops import MfpOp, Frag2DenseOp
+    n, c, sp, p = case
+    r = np.random.RandomState(31)
+    x = np.maximum(r.rand(n, c, *sp).astype(np.float32) - 0.2, 0)
+    old_off = [[0, 0, 0]] if n == 1 else [[i, j, 0] for i in range(2) for j in range(2)]
+    old_st = [1, 1, 1] if n == 1 else [2, 2, 1]
+    ref, off, st = oo.fragmentpool(x, p, old_off, old_st)
+    xd, yd = dev(x), empty(ref.shape[0], c, ref.shape[2:])
+    op = MfpOp(h, xd, yd, p)
+    op.fwd()
+    assert np.array_equal(yd.numpy(), ref)           # values AND fragment order (new-offset-major)
+    dy = r.randn(*ref.shape).astype(np.float32)
+    dxd = empty(n, c, sp)
+    op.bwd(dev(dy), dxd)
+    assert rel(dxd.numpy(), oo.fragmentpool_bwd(dy, x, p, 'first')) <= 1e-6   # sums of <= prod(p) terms
+    if n == 1:
+        dd = empty(1, c, [s * q for s, q in zip(ref.shape[2:], st)])
+        f2d = Frag2DenseOp(h, yd, dd, off, st)
+        f2d.fwd()
+        assert np.array_equal(dd.numpy(), oo.fragments2dense(ref, off, st))
+        back = empty(ref.shape[0], c, ref.shape[2:])
+        f2d.bwd(dd, back)
+        assert np.array_equal(back.numpy(), ref)     # round trip
+
+
+def test_mfp_two_layers_golden(h):
+    from elektronn2_b200.ops import MfpOp, Frag2DenseOp
+    g = np.load(os.path.join(HERE, 'golden', 'ops_small.npz'))
+    xd = dev(g['mfp_x'])
+    y1 = empty(8, 3, g['mfp_y'].shape[2:])
+    MfpOp(h, xd, y1, (2, 2, 2)).fwd()
+    assert np.array_equal(y1.numpy(), g['mfp_y'])
+    x2 = dev(g['mfp_y'][:, :, :, :3, :3])
+    y2 = empty(32, 3, g['mfp2_y'].shape[2:])
+    MfpOp(h, x2, y2, (1, 2, 2)).fwd()
+    assert np.array_equal(y2.numpy(), g['mfp2_y'])
+    dd = empty(1, 3, g['f2d_y'].shape[2:])
+    Frag2DenseOp(h, y1, dd, g['mfp_off'], g['mfp_st']).fwd()
+    assert np.array_equal(dd.numpy(), g['f2d_y'])
+
+
+def test_mfp_rule_and_f2d_count_errors(h):
+    from elektronn2_b200.ops import MfpOp, Frag2DenseOp
+    with pytest.raises(ValueError, match="using MFP"):                           # neural.py:739-744
+        MfpOp(h, empty(1, 4, (6, 6, 6)), empty(8, 4, (2, 2, 2)), (2, 2, 2)).fwd()
+    with pytest.raises(ValueError, match="fragments on the batch axis"):         # neural.py:873-875
+        Frag2DenseOp(h, empty(4, 2, (2, 2, 2)), empty(1, 2, (4, 4, 4)), [[0, 0, 0]] * 4, (2, 2, 2)).fwd()
+
+
+# ------------------------------------------------------------------ crop + concat
+def test_crop_concat(h):
+    from elektronn2_b200.ops import CropConcatOp
+    r = np.random.RandomState(41)
+    a = r.rand(2, 5, 6, 10, 12).astype(np.float32)
+    dst = empty(2, 9, (4, 6, 6))
+    op = CropConcatOp(h, dev(a), dst, (1, 2, 3), 4)
+    op.fwd()
+    got = dst.numpy()
+    assert np.array_equal(got[:, 4:], oo.crop(a, (1, 2, 3))) and np.all(got[:, :4] == 0)
+    dd = r.randn(2, 9, 4, 6, 6).astype(np.float32)
+    ds = empty(2, 5, (6, 10, 12))
+    op.bwd(dev(dd), ds)
+    ref = oo.crop_bwd(dd[:, 4:], (1, 2, 3), a.shape).astype(np.float32)
+    assert np.array_equal(ds.numpy(), ref)
+    op.bwd(dev(dd), ds, accumulate=True)
+    assert np.array_equal(ds.numpy(), 2 * ref)
+
+
+# --------------------------------------------------------------------- loss head
+def test_softmax_nll_errors(h):
+    from elektronn2_b200.ops import LossOp
+    r = np.random.RandomState(51)
+    logits = r.randn(2, 2, 4, 6, 6).astype(np.float32) * 2
+    target = r.randint(0, 2, (2, 1, 4, 6, 6)).astype(np.float32)
+    target[0, 0, 0, :2, :2] = -1                       # unlabelled voxels
+    ld, td, pd = dev(logits), dev(target), empty(2, 2, (4, 6, 6))
+    op = LossOp(h, ld, td, pd)
+    op.fwd()
+    L, dl, p = ol.loss_and_dlogits(logits, target)
+    loss, err = op.read()
+    assert abs(loss - L) <= 1e-5 * abs(L)
+    assert rel(pd.numpy(), p) <= 1e-6
+    assert abs(err - ol.errors(p, target)) < 1e-7
+    gd = empty(2, 2, (4, 6, 6))
+    op.bwd(gd)
+    assert rel(gd.numpy(), dl) <= 1e-5
+
+
+# --------------------------------------------------------------------- optimisers
+def test_adam_and_sgd_match_reference_formulas(h):
+    from elektronn2_b200 import _lib
+    r = np.random.RandomState(61)
+    p0, g0 = r.randn(1001).astype(np.float32), r.randn(1001).astype(np.float32)
+    p, g = t(p0), t(g0)
+    m, s = torch.zeros_like(p), torch.zeros_like(p)
+    st = oadam.AdamState([p0])
+    ref = [p0]
+    for step in (1, 2, 3):
+        h.call('e2_adam_step', _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(s), 1001, 5e-4, 0.9, 0.999, 0.5e-4, 1,
+               step, h.stream())
+        ref = oadam.adam_step(ref, [g0], st, [True], lr=5e-4, mom=0.9, beta2=0.999, wd=0.5e-4)
+        assert rel(p.cpu().numpy(), ref[0]) <= 1e-6
+    p, d = t(p0), torch.zeros(1001, device='cuda')
+    last = [np.zeros(1001)]
+    h.call('e2_sgd_step', _lib.ptr(p), _lib.ptr(g), _lib.ptr(d), 1001, 1e-2, 0.9, 1e-3, 0, h.stream())
+    ref = oadam.sgd_step([p0], [g0], last, [False], lr=1e-2, mom=0.9, wd=1e-3)
+    assert rel(p.cpu().numpy(), ref[0]) <= 1e-6
+
+
+# -------------------------------------------- size-independent properties at full size
+def test_full_size_properties_unet3d_conv1(h):
+    """unet3d conv1 (1,32,114,130,130) -> (1,64,112,128,128), the largest layer of the
+    BASELINE workload: linearity in x and agreement on a random sample of outputs with
+    the oracle formula (the full oracle conv would take minutes)."""
+    from elektronn2_b200.ops import ConvOp
+    from elektronn2_b200.config import config
+    r = np.random.RandomState(71)
+    sp, k = (114, 130, 130), (3, 3, 3)
+    x1 = r.rand(1, 32, *sp).astype(np.float32)
+    x2 = r.rand(1, 32, *sp).astype(np.float32)
+    w = (r.randn(64, 32, *k) * np.sqrt(2.0 / (32 * 27))).astype(np.float32)
+    osp = (112, 128, 128)
+    ys = []
+    for x in (x1, x2, x1 + x2):
+        xd, yd = dev(x), empty(1, 64, osp)
+        op = ConvOp(h, xd, yd, t(w), None, k, 'lin', config.compute)
+        op.pack()
+        op.fwd()
+        ys.append(yd.numpy())
+    tol = TOL[config.compute]
+    assert rel(ys[2], ys[0] + ys[1]) <= 2 * tol
+    wf = w[:, :, ::-1, ::-1, ::-1].astype(np.float64)
+    for _ in range(64):
+        o, z, xx, yy = r.randint(64), r.randint(112), r.randint(128), r.randint(128)
+        ref = float((x1[0, :, z:z + 3, xx:xx + 3, yy:yy + 3].astype(np.float64) * wf[o]).sum())
+        assert abs(ys[0][0, o, z, xx, yy] - ref) <= tol * np.abs(ys[0]).max()
