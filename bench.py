@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    'unet3d': dict(patch=(116, 132, 132), cpu_patches=[(116, 132, 132), (84, 100, 100), (52, 68, 68)]),
+    'unet3d': dict(patch=(116, 132, 132), cpu_patches=[(116, 132, 132), (100, 116, 116), (92, 100, 100), (92, 92, 92)]),
     'unet3d_litelite': dict(patch=(22, 140, 140), cpu_patches=[(22, 140, 140)]),
     'neuro3d_lite': dict(patch=(11, 155, 155), cpu_patches=[(11, 155, 155)]),
     'neuro3d': dict(patch=(23, 185, 185), cpu_patches=[(23, 185, 185)]),
@@ -55,10 +55,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index=0):
         super(ClockSampler, self).__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
@@ -67,10 +67,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])

@@ -69,12 +69,12 @@ class UpConvDesc(C.Structure):
 
 class PoolDesc(C.Structure):
     _fields_ = [('x', Tensor), ('y', Tensor), ('pz', i32), ('px', i32), ('py', i32), ('act', i32),
-                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32)]
+                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32), ('round_tf32', i32)]
 
 
 class MfpDesc(C.Structure):
     _fields_ = [('x', Tensor), ('y', Tensor), ('pz', i32), ('px', i32), ('py', i32), ('act', i32),
-                ('has_bias', i32)]
+                ('has_bias', i32), ('round_tf32', i32)]
 
 
 class F2DDesc(C.Structure):

@@ -550,7 +550,9 @@ static void conv_fwd_problem(const e2_conv_desc* d, const float* x, const float*
   g->sz = g->sx = g->sy = 1;
   g->bias = d->has_bias ? bias : nullptr;
   g->act = d->act;
-  g->round_tf32 = 0;
+  // tensors that feed a kind::tf32 MMA are rounded to tf32 (round-to-nearest) by their
+  // producer, so the hardware's truncation of the low 13 mantissa bits is exact
+  g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
 }
 
 extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
@@ -589,6 +591,7 @@ extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float*
   g.oz = -(d->kz - 1), g.ox = -(d->kx - 1), g.oy = -(d->ky - 1);
   g.sz = g.sx = g.sy = 1;
   g.accumulate = d->accumulate;
+  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
   return e2_launch_gather_gemm_ffma(h, g, s);
@@ -638,6 +641,7 @@ extern "C" int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const floa
   g.bias = d->has_bias ? bias : nullptr;
   g.act = d->act;
   g.shuffle = 1, g.pz = d->pz, g.px = d->px, g.py = d->py, g.Fo = d->y.c;
+  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
   return e2_launch_gather_gemm_ffma(h, g, s);
@@ -660,6 +664,7 @@ extern "C" int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const fl
   g.tz = d->pz, g.tx = d->px, g.ty = d->py;
   g.sz = d->pz, g.sx = d->px, g.sy = d->py;
   g.accumulate = d->accumulate;
+  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
   return e2_launch_gather_gemm_ffma(h, g, s);

@@ -1,12 +1,325 @@
-// tcgen05 / TMEM / TMA implicit-GEMM kernels (placeholder until the kernels land).
+// tcgen05 / TMEM / TMA implicit-GEMM kernels (E2_COMPUTE_TF32).
+//
+// gather-GEMM  C[m, n] = sum_{tap, k} A[pos(m) + tap + org][k] * B[n][tap][k]
+//   M tile  = 128 output positions forming a (tz, tx, ty) box of the output grid, so that for
+//             every filter tap the A operand is ONE 5-D TMA box load of the activation tensor
+//             shifted by the tap offset: rows land in shared memory in (z,x,y) order, 32 fp32
+//             channels (128 B) per row, 128B-swizzled -> exactly the canonical K-major UMMA
+//             layout.  Out-of-range coordinates (dgrad halo, ragged edge tiles, channel tail)
+//             are zero-filled by the TMA unit: no padding copies, no im2col buffer.
+//   N tile  = up to 256 output channels, B operand = packed weights [n][tap][k], 3-D TMA box.
+//   K loop  = taps x ceil(K/32) blocks through a multi-stage mbarrier ring.
+//   MMA     = tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8, fp32 accumulators in TMEM.
+//   roles   = warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+//             (tcgen05.ld -> +bias -> activation -> (accumulate) -> store).
+// Several CTAs share an SM (smem permitting), so one CTA's epilogue overlaps another's MMAs.
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
+#include "e2_tc_ptx.cuh"
 
-bool e2_gather_gemm_tc_ok(const e2_handle*, const GatherGemm&) { return false; }
-int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm&, cudaStream_t) {
-  return e2_fail(h, E2_ERR_UNSUPPORTED, "tcgen05 gather-GEMM not built");
+namespace {
+
+constexpr int BM = 128;          // rows per tile (TMEM lanes)
+constexpr int BK = 32;           // fp32 per K block = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 4;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  int On, Oz, Ox, Oy;        // output position grid
+  int tz, tx, ty;            // tile box (tz*tx*ty == 128)
+  int ntz, ntx, nty;         // tiles per axis
+  int kz, kx, ky;            // taps
+  int oz, ox, oy;            // origin
+  int K, N;                  // reduction channels per tap, output channels (GEMM N)
+  int BN;                    // N tile (multiple of 16, <= 256)
+  int stages;
+  int tmem_cols;
+  float* C;
+  int c_pitch;
+  const float* bias;
+  int act, accumulate, round_tf32;
+  int shuffle, pz, px, py, Fo;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned stage bases
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.BN * BK * 4;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + p.stages * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.stages * b_stage_bytes);
+  uint64_t* full = bars;                 // [stages]
+  uint64_t* empty = bars + p.stages;     // [stages]
+  uint64_t* acc_full = bars + 2 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int ity = tile % p.nty;
+  tile /= p.nty;
+  const int itx = tile % p.ntx;
+  tile /= p.ntx;
+  const int itz = tile % p.ntz;
+  const int in_ = tile / p.ntz;
+  const int z0 = itz * p.tz, x0 = itx * p.tx, y0 = ity * p.ty;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int T = p.kz * p.kx * p.ky;
+  const int total = T * kblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tap = 0; tap < T; ++tap) {
+        const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          tc::mbar_wait(&empty[s], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+          tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 + k3 + p.oy, x0 + j3 + p.ox,
+                          z0 + i3 + p.oz, in_);
+          tc::tma_load_3d(smB + s * b_stage_bytes, &tmB, &full[s], kb * BK, tap, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(&full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t a_addr = tc::smem_u32(smA + s * A_STAGE_BYTES);
+        const uint32_t b_addr = tc::smem_u32(smB + s * b_stage_bytes);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart; advancing K by
+          // 8 tf32 = 32 bytes inside the swizzle row is a plain start-address advance
+          const uint64_t ad = tc::make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+          const uint64_t bd = tc::make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+          tc::mma_tf32_ss(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(&empty[s]);   // frees the smem stage when these MMAs have read it
+      }
+      tc::mma_commit(acc_full);      // accumulator complete
+    }
+  } else {
+    // ----------------------------------------------------------------- epilogue
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;          // row of the tile == position inside the box
+    const int ly = row % p.ty, lx = (row / p.ty) % p.tx, lz = row / (p.ty * p.tx);
+    const int oz = z0 + lz, ox = x0 + lx, oy = y0 + ly;
+    const bool row_ok = oz < p.Oz && ox < p.Ox && oy < p.Oy;
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    const int64_t pos = (((int64_t)in_ * p.Oz + oz) * p.Ox + ox) * p.Oy + oy;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      if (p.BN - c0 >= 32) {
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      } else {
+        tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 16; j < 32; ++j) r[j] = 0u;
+      }
+      tc::tmem_ld_wait();
+      if (!row_ok) continue;
+      if (!p.shuffle) {
+        float* out = p.C + pos * p.c_pitch + n0 + c0;
+        const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + c0 + j4 + j;
+            float a = __uint_as_float(r[j4 + j]);
+            if (n < p.N) {
+              if (p.bias) a += __ldg(p.bias + n);
+              a = e2_apply_act(a, p.act);
+              if (p.accumulate) a += out[j4 + j];
+              if (p.round_tf32) a = e2_round_tf32(a);
+            }
+            v[j] = a;
+          }
+          if (vec && n0 + c0 + j4 + 3 < p.N) {
+            *reinterpret_cast<float4*>(out + j4) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n0 + c0 + j4 + j < p.N) out[j4 + j] = v[j];
+          }
+        }
+      } else {
+        // upconv forward: column n = tap' * Fo + o  ->  position (pos*p + tap'), channel o
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n >= p.N) continue;
+          const int tp = n / p.Fo, ch = n - tp * p.Fo;
+          const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+          const int64_t ofs = ((((int64_t)in_ * (p.Oz * p.pz) + oz * p.pz + i3) * (p.Ox * p.px) + ox * p.px + j3) *
+                                   (p.Oy * p.py) + oy * p.py + k3) * p.c_pitch + ch;
+          float a = __uint_as_float(r[j]);
+          if (p.bias) a += __ldg(p.bias + ch);
+          a = e2_apply_act(a, p.act);
+          if (p.accumulate) a += p.C[ofs];
+          if (p.round_tf32) a = e2_round_tf32(a);
+          p.C[ofs] = a;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
-bool e2_reduce_gemm_tc_ok(const e2_handle*, const ReduceGemm&) { return false; }
-int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm&, cudaStream_t) {
-  return e2_fail(h, E2_ERR_UNSUPPORTED, "tcgen05 reduce-GEMM not built");
+
+// ------------------------------------------------------------------ host side
+EncodeTiledFn get_encode() { return e2_get_tmap_encode(); }
+
+}  // namespace
+
+EncodeTiledFn e2_get_tmap_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
 }
+
+namespace {
+
+bool pick_tile(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
+  // all (tz,tx,ty) with product 128; minimise padded volume, prefer long y runs
+  static const int opts[][3] = {{1, 8, 16}, {2, 8, 8},  {1, 4, 32}, {2, 4, 16}, {4, 4, 8},  {1, 16, 8}, {1, 2, 64},
+                                {2, 2, 32}, {4, 8, 4},  {8, 4, 4},  {1, 1, 128}, {2, 16, 4}, {4, 2, 16}, {1, 32, 4},
+                                {2, 1, 64}, {4, 1, 32}, {8, 2, 8},  {8, 1, 16}, {16, 2, 4}, {8, 8, 2},  {4, 16, 2},
+                                {2, 32, 2}, {1, 64, 2}, {16, 4, 2}, {16, 8, 1}, {8, 16, 1}, {4, 32, 1}, {2, 64, 1},
+                                {1, 128, 1}, {32, 2, 2}, {32, 4, 1}, {16, 1, 8}, {32, 1, 4}};
+  int64_t best = -1;
+  for (auto& o : opts) {
+    int64_t v = (int64_t)((Oz + o[0] - 1) / o[0]) * o[0] * ((Ox + o[1] - 1) / o[1]) * o[1] * ((Oy + o[2] - 1) / o[2]) * o[2];
+    if (best < 0 || v < best) {
+      best = v;
+      *tz = o[0], *tx = o[1], *ty = o[2];
+    }
+  }
+  return best > 0;
+}
+
+}  // namespace
+
+bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g) {
+  if (!get_encode()) return false;
+  if (g.sz != 1 || g.sx != 1 || g.sy != 1) return false;   // strided gather (upconv dgrad) stays on CUDA cores
+  if (g.K < 8 || g.N < 8) return false;                    // not tensor-core shaped (HBM-bound layers)
+  if (g.a_pitch % 4 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if ((g.b_row % 4) || (g.b_tap % 4)) return false;
+  return true;
+}
+
+int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.On = g.On, p.Oz = g.Oz, p.Ox = g.Ox, p.Oy = g.Oy;
+  pick_tile(g.Oz, g.Ox, g.Oy, &p.tz, &p.tx, &p.ty);
+  p.ntz = (g.Oz + p.tz - 1) / p.tz, p.ntx = (g.Ox + p.tx - 1) / p.tx, p.nty = (g.Oy + p.ty - 1) / p.ty;
+  p.kz = g.tz, p.kx = g.tx, p.ky = g.ty;
+  p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
+  p.K = g.K, p.N = g.N;
+  int bn = (g.N + 15) / 16 * 16;
+  if (bn > 256) bn = 256;
+  p.BN = bn;
+  const int b_stage = bn * BK * 4;
+  p.stages = (bn <= 64) ? 4 : (bn <= 128 ? 3 : 4);
+  int cols = 32;
+  while (cols < bn) cols *= 2;
+  p.tmem_cols = cols;
+  p.C = g.C, p.c_pitch = g.c_pitch, p.bias = g.bias, p.act = g.act, p.accumulate = g.accumulate;
+  p.round_tf32 = g.round_tf32;
+  p.shuffle = g.shuffle, p.pz = g.pz, p.px = g.px, p.py = g.py, p.Fo = g.Fo;
+  p.idesc = tc::make_idesc(2 /*TF32*/, 0, 0, BM, (uint32_t)bn);
+
+  // A: activations (c, y, x, z, n), box (32, ty, tx, tz, 1), 128B swizzle, zero OOB fill
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)g.K, (cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
+    cuuint64_t pitch = (cuuint64_t)g.a_pitch * 4;
+    cuuint64_t strides[4] = {pitch, pitch * g.Ay, pitch * g.Ay * g.Ax, pitch * g.Ay * g.Ax * g.Az};
+    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.A), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    const int T = g.tz * g.tx * g.ty;
+    // B: packed weights [n][tap][k]: (k, tap, n) with byte strides (b_tap, b_row); b_tap == 0 when T == 1
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)T, (cuuint64_t)g.N};
+    cuuint64_t tap_stride = (cuuint64_t)(T > 1 ? g.b_tap : g.b_row) * 4;
+    cuuint64_t strides[2] = {tap_stride, (cuuint64_t)g.b_row * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)bn};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.B), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  const size_t smem = 1024 + (size_t)p.stages * (A_STAGE_BYTES + b_stage) + (2 * p.stages + 1) * 8 + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(k_gather_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) !=
+        cudaSuccess)
+      return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
+    configured = 227 * 1024;
+  }
+  dim3 grid((unsigned)(p.On * p.ntz * p.ntx * p.nty), (unsigned)((g.N + bn - 1) / bn));
+  k_gather_gemm_tc<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
+  h->launches++;
+  E2_CUDA_CHECK(h, "gather_gemm_tc");
+  return E2_OK;
+}
+

@@ -54,7 +54,7 @@ struct PoolP {
   int n, Z, X, Y, C, xp;  // input dims, input pitch
   int Zo, Xo, Yo, yp;     // output dims, output pitch
   int pz, px, py;
-  int act, has_bias, tie, accumulate;
+  int act, has_bias, tie, accumulate, round_tf32;
 };
 
 // ------------------------------------------------------------------ max-pool forward
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, const float* __res
     for (int j = 0; j < V; ++j) {
       float r = best[j];
       if (p.has_bias) r += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
-      o.v[j] = e2_apply_act(r, p.act);
+      r = e2_apply_act(r, p.act);
+      o.v[j] = p.round_tf32 ? e2_round_tf32(r) : r;
       oi.v[j] = bi[j];
     }
     int64_t oofs = pos * p.yp + c;
@@ -181,6 +182,7 @@ static int fill_pool(e2_handle* h, const e2_pool_desc* d, PoolP* p) {
   p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
   p->pz = d->pz, p->px = d->px, p->py = d->py;
   p->act = d->act, p->has_bias = d->has_bias, p->tie = d->tie_mode, p->accumulate = d->accumulate;
+  p->round_tf32 = d->round_tf32;
   return E2_OK;
 }
 
@@ -263,7 +265,8 @@ __global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, const float* __restric
     for (int j = 0; j < V; ++j) {
       float r = best[j];
       if (p.has_bias) r += __ldg(bias + c + j);
-      o.v[j] = e2_apply_act(r, p.act);
+      r = e2_apply_act(r, p.act);
+      o.v[j] = p.round_tf32 ? e2_round_tf32(r) : r;
       oi.v[j] = bi[j];
     }
     o.store(y + pos * p.yp + c);
@@ -339,6 +342,7 @@ static int fill_mfp(e2_handle* h, const e2_mfp_desc* d, PoolP* p) {
   p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
   p->pz = d->pz, p->px = d->px, p->py = d->py;
   p->act = d->act, p->has_bias = d->has_bias, p->tie = 0, p->accumulate = 0;
+  p->round_tf32 = d->round_tf32;
   return E2_OK;
 }
 

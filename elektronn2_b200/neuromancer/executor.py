@@ -258,12 +258,14 @@ class Plan(object):
             lin = DevTensor(x.desc.n, lsp[0], lsp[1], lsp[2], n.n_f, device=self.device)
             op = ops.ConvOp(h, x, lin, w, None, n.filter_shape, 'lin', self.compute)
             self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(lin)), kind)
+            rnd = self.compute == 'tf32'
             if n.mfp:
-                pop = ops.MfpOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train)
+                pop = ops.MfpOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train,
+                                round_tf32=rnd)
                 self._f('mfp_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
             else:
                 pop = ops.PoolOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train,
-                                 tie_mode=config.pool_tie_mode)
+                                 tie_mode=config.pool_tie_mode, round_tf32=rnd)
                 self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
             self.aux[n] = (lin, pop)
         self.conv_ops[n] = op

@@ -111,11 +111,11 @@ class PoolOp(object):
     """computations.pooling 3-D max (computations.py:538-649) with optional fused
     +bias -> act (Conv nodes that carry a pool, neural.py:678, 711-712)."""
 
-    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, tie_mode='first'):
+    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, tie_mode='first', round_tf32=False):
         self.h, self.x, self.y, self.bias = h, x, y, bias
         self.pool = tuple(int(v) for v in pool)
         self.d = _lib.PoolDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
-                               1 if bias is not None else 0, TIE[tie_mode], 0)
+                               1 if bias is not None else 0, TIE[tie_mode], 0, int(bool(round_tf32)))
         self.argmax = y.like(dtype=torch.int32) if keep_argmax else None
 
     def fwd(self):
@@ -133,11 +133,11 @@ class PoolOp(object):
 class MfpOp(object):
     """computations.fragmentpool (computations.py:652-678)."""
 
-    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True):
+    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, round_tf32=False):
         self.h, self.x, self.y, self.bias = h, x, y, bias
         self.pool = tuple(int(v) for v in pool)
         self.d = _lib.MfpDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
-                              1 if bias is not None else 0)
+                              1 if bias is not None else 0, int(bool(round_tf32)))
         self.argmax = y.like(dtype=torch.int32) if keep_argmax else None
 
     def fwd(self):

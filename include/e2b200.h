@@ -150,6 +150,7 @@ typedef struct {
   int32_t act, has_bias; /* fused epilogue, fwd only                 */
   int32_t tie_mode;      /* e2_tie_mode, bwd only                    */
   int32_t accumulate;    /* bwd only: dx += instead of dx =          */
+  int32_t round_tf32;    /* fwd only: round the output to tf32 (it feeds a kind::tf32 MMA) */
 } e2_pool_desc;
 
 int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,
@@ -168,6 +169,7 @@ typedef struct {
   e2_tensor y; /* (n*pz*px*py, (Z-pz+1)/pz, (X-px+1)/px, (Y-py+1)/py, c) */
   int32_t pz, px, py;
   int32_t act, has_bias;
+  int32_t round_tf32; /* fwd only, as in e2_pool_desc */
 } e2_mfp_desc;
 
 int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, const float* bias, float* y, int32_t* argmax,

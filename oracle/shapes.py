@@ -56,6 +56,8 @@ def conv_shape(sh, n_f, k, pool=(1, 1, 1), mfp=False):
         elif (s_in + 1 - f) % p != 0:
             raise ValueError("pool: axis %d len %d pool %d kernel %d" % (j, s_in, p, f))
         out.spatial[j] = (s_in + 1 - f) // p
+        if out.spatial[j] < 1:
+            raise ValueError("axis %d of length %d is too short for kernel %d / pool %d" % (j, s_in, f, p))
         out.fov[j] = sh.fov[j] + (f + p - 2) * sh.strides[j] if sh.fov[j] > 0 else -1
     if mfp:
         b = 1 if sh.b is None else sh.b
