@@ -6,7 +6,7 @@
 // both operands are "MN-major": a shared-memory row is one position holding 32 consecutive
 // channels (128 B).  That is exactly what a channels-last TMA box load produces, so P and the
 // tap-shifted Q tiles go from HBM/L2 to the tensor core without any transpose:
-//   A = P tile   : 4 chunks of 32 r-channels x 64 positions  (MN-major, 128B swizzle)
+//   A = P tile   : 4 chunks of 32 r-channels x 64 positions  (MN-major, 128B swizzle / 32B atom)
 //   B = Q_tap    : NCH chunks of 32 s-channels x 64 positions
 //   D            : TMEM, 128 lanes (r) x [taps of this CTA][NCH*32] columns, fp32
 // The P tile is loaded once per position tile and reused for every tap of the CTA's tap group.
@@ -133,9 +133,11 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
           const uint32_t b_addr = tc::smem_u32(smB + bs * b_bytes);
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {
-            // MN-major, 128B swizzle: one 8-position group = 1024 B; 32-channel chunks CHUNK_BYTES apart
-            const uint64_t ad = tc::make_smem_desc(a_addr + k * 1024, CHUNK_BYTES, 1024, 2);
-            const uint64_t bd = tc::make_smem_desc(b_addr + k * 1024, CHUNK_BYTES, 1024, 2);
+            // MN-major tf32 operands exist only in the "128B swizzle, 32B atom" layout (UMMA layout
+            // type 1 == TMA SWIZZLE_128B_ATOM_32B): rows (positions) 128 B apart, swizzle period
+            // 4 rows = 512 B (SBO), 32-channel chunks CHUNK_BYTES apart (LBO); K = 8 rows per MMA
+            const uint64_t ad = tc::make_smem_desc(a_addr + k * 1024, CHUNK_BYTES, 512, 1);
+            const uint64_t bd = tc::make_smem_desc(b_addr + k * 1024, CHUNK_BYTES, 512, 1);
             tc::mma_tf32_ss(tmem_base + (uint32_t)tl * ncols, ad, bd, p.idesc, (ti > 0 || k > 0) ? 1u : 0u);
           }
           tc::mma_commit(&b_empty[bs]);
@@ -249,7 +251,7 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
     cuuint32_t box[5] = {32, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.P), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
   }
@@ -260,7 +262,7 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
     cuuint32_t box[5] = {32, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.Q), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(Q) failed: %d", (int)r);
   }
