@@ -104,22 +104,22 @@ SIGNATURES = {
     'e2_conv3d_pack_weights': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp]),
     'e2_conv3d_workspace_size': (C.c_int, [P(ConvDesc), P(sz)]),
     'e2_conv3d_fwd': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
-    'e2_conv3d_dgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, sz, vp]),
+    'e2_conv3d_dgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_wgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_packed_floats': (C.c_int, [P(UpConvDesc), P(sz), P(sz)]),
     'e2_upconv3d_pack_weights': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp]),
     'e2_upconv3d_fwd': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, sz, vp]),
-    'e2_upconv3d_dgrad': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, sz, vp]),
+    'e2_upconv3d_dgrad': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_wgrad': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_act_bwd': (C.c_int, [vp, P(Tensor), i32, vp, vp, vp, vp]),
     'e2_maxpool3d_fwd': (C.c_int, [vp, P(PoolDesc), vp, vp, vp, vp, vp]),
-    'e2_maxpool3d_bwd': (C.c_int, [vp, P(PoolDesc), vp, vp, vp, vp, vp]),
+    'e2_maxpool3d_bwd': (C.c_int, [vp, P(PoolDesc), vp, vp, vp, vp, vp, vp]),
     'e2_mfp_fwd': (C.c_int, [vp, P(MfpDesc), vp, vp, vp, vp, vp]),
     'e2_mfp_bwd': (C.c_int, [vp, P(MfpDesc), vp, vp, vp, vp]),
     'e2_frag2dense_fwd': (C.c_int, [vp, P(F2DDesc), vp, vp, vp, vp]),
     'e2_frag2dense_bwd': (C.c_int, [vp, P(F2DDesc), vp, vp, vp, vp]),
     'e2_crop_concat_fwd': (C.c_int, [vp, P(CropDesc), vp, vp, vp]),
-    'e2_crop_concat_bwd': (C.c_int, [vp, P(CropDesc), vp, vp, vp]),
+    'e2_crop_concat_bwd': (C.c_int, [vp, P(CropDesc), vp, vp, vp, vp]),
     'e2_softmax_nll_fwd': (C.c_int, [vp, P(Tensor), vp, vp, vp, vp, vp]),
     'e2_softmax_nll_bwd': (C.c_int, [vp, P(Tensor), vp, vp, vp, C.c_float, vp, vp]),
     'e2_adam_step': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]),

@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256) k_gather_gemm(GatherGemm g) {
       }
       if (g.bias) v += __ldg(g.bias + ch);
       v = e2_apply_act(v, g.act);
+      if (g.gate && !(__ldg(g.gate + ofs) > 0.f)) v = 0.f;
       if (g.accumulate) v += g.C[ofs];
       if (g.round_tf32) v = e2_round_tf32(v);
       g.C[ofs] = v;
@@ -575,12 +576,13 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
 }
 
 extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float* dy, const float* wd, float* dx,
-                               void* ws, size_t ws_bytes, void* stream) {
+                               const float* relu_gate, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_conv(h, d);
   if (rc) return rc;
   E2_REQUIRE(h, dy && wd && dx, "conv3d_dgrad: null pointer");
   GatherGemm g;
   memset(&g, 0, sizeof(g));
+  g.gate = relu_gate;
   int T = d->kz * d->kx * d->ky, op = round_up(d->y.c, 4);
   g.A = dy, g.a_pitch = d->y.c_pitch, g.K = d->y.c;
   g.An = d->y.n, g.Az = d->y.z, g.Ax = d->y.x, g.Ay = d->y.y;
@@ -648,13 +650,14 @@ extern "C" int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const floa
 }
 
 extern "C" int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const float* dy, const float* wd, float* dx,
-                                 void* ws, size_t ws_bytes, void* stream) {
+                                 const float* relu_gate, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_upconv(h, d);
   if (rc) return rc;
   E2_REQUIRE(h, dy && wd && dx, "upconv3d_dgrad: null pointer");
   // dx[m][c] = sum_{tap,o} dy[m*p + tap][o] * w[o][c][tap]  -- a strided gather-GEMM
   GatherGemm g;
   memset(&g, 0, sizeof(g));
+  g.gate = relu_gate;
   int T = d->pz * d->px * d->py, np = round_up(T * d->y.c, 4);
   g.A = dy, g.a_pitch = d->y.c_pitch, g.K = d->y.c;
   g.An = d->y.n, g.Az = d->y.z, g.Ax = d->y.x, g.Ay = d->y.y;

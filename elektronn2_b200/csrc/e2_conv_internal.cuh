@@ -18,6 +18,7 @@ struct GatherGemm {
   const float* bias;
   int act, accumulate, round_tf32;
   int shuffle, pz, px, py, Fo;  // pixel-shuffle epilogue (upconv fwd)
+  const float* gate;            // fused ReLU backward: zero the result where gate <= 0 (same layout as C)
 };
 
 // W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]

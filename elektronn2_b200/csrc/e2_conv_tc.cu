@@ -39,6 +39,8 @@ struct TcParams {
   const float* bias;
   int act, accumulate, round_tf32;
   int shuffle, pz, px, py, Fo;
+  int sz, sx, sy;            // position stride of the gather (upconv dgrad: pool factors)
+  const float* gate;         // fused ReLU backward
   uint32_t idesc;
 };
 
@@ -105,8 +107,8 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
           const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
           tc::mbar_wait(&empty[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
-          tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 + k3 + p.oy, x0 + j3 + p.ox,
-                          z0 + i3 + p.oz, in_);
+          tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 * p.sy + k3 + p.oy,
+                          x0 * p.sx + j3 + p.ox, z0 * p.sz + i3 + p.oz, in_);
           tc::tma_load_3d(smB + s * b_stage_bytes, &tmB, &full[s], kb * BK, tap, n0);
         }
       }
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
             if (n < p.N) {
               if (p.bias) a += __ldg(p.bias + n);
               a = e2_apply_act(a, p.act);
+              if (p.gate && !(__ldg(p.gate + (out - p.C) + j4 + j) > 0.f)) a = 0.f;
               if (p.accumulate) a += out[j4 + j];
               if (p.round_tf32) a = e2_round_tf32(a);
             }
@@ -178,6 +181,34 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (n0 + c0 + j4 + j < p.N) out[j4 + j] = v[j];
+          }
+        }
+      } else if ((p.Fo & 31) == 0 && (p.c_pitch & 3) == 0 && n0 + c0 < p.N) {
+        // upconv forward, fast path: the 32 columns of this chunk are 32 consecutive channels of ONE
+        // tap -> one contiguous 128-byte run at the shuffled output position
+        const int n = n0 + c0;
+        const int tp = n / p.Fo, ch = n - tp * p.Fo;
+        const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+        const int64_t ofs = ((((int64_t)in_ * (p.Oz * p.pz) + oz * p.pz + i3) * (p.Ox * p.px) + ox * p.px + j3) *
+                                 (p.Oy * p.py) + oy * p.py + k3) * p.c_pitch + ch;
+        float* out = p.C + ofs;
+        const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = __uint_as_float(r[j4 + j]);
+            if (p.bias) a += __ldg(p.bias + ch + j4 + j);
+            a = e2_apply_act(a, p.act);
+            if (p.round_tf32) a = e2_round_tf32(a);
+            v[j] = a;
+          }
+          if (vec) {
+            *reinterpret_cast<float4*>(out + j4) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[j4 + j] = v[j];
           }
         }
       } else {
@@ -229,7 +260,7 @@ EncodeTiledFn e2_get_tmap_encode() {
 
 namespace {
 
-bool pick_tile(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
+bool pick_tile(int Oz, int Ox, int Oy, int sz, int sx, int sy, int* tz, int* tx, int* ty) {
   // all (tz,tx,ty) with product 128; minimise padded volume, prefer long y runs
   static const int opts[][3] = {{1, 8, 16}, {2, 8, 8},  {1, 4, 32}, {2, 4, 16}, {4, 4, 8},  {1, 16, 8}, {1, 2, 64},
                                 {2, 2, 32}, {4, 8, 4},  {8, 4, 4},  {1, 1, 128}, {2, 16, 4}, {4, 2, 16}, {1, 32, 4},
@@ -238,6 +269,7 @@ bool pick_tile(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
                                 {1, 128, 1}, {32, 2, 2}, {32, 4, 1}, {16, 1, 8}, {32, 1, 4}};
   int64_t best = -1;
   for (auto& o : opts) {
+    if (o[0] * sz > 256 || o[1] * sx > 256 || o[2] * sy > 256) continue;   // TMA box extent limit (strided gather)
     int64_t v = (int64_t)((Oz + o[0] - 1) / o[0]) * o[0] * ((Ox + o[1] - 1) / o[1]) * o[1] * ((Oy + o[2] - 1) / o[2]) * o[2];
     if (best < 0 || v < best) {
       best = v;
@@ -251,7 +283,7 @@ bool pick_tile(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
 
 bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g) {
   if (!get_encode()) return false;
-  if (g.sz != 1 || g.sx != 1 || g.sy != 1) return false;   // strided gather (upconv dgrad) stays on CUDA cores
+  if (g.sz < 1 || g.sx < 1 || g.sy < 1 || g.sz > 8 || g.sx > 8 || g.sy > 8) return false;   // TMA element-stride limit
   if (g.K < 8 || g.N < 8) return false;                    // not tensor-core shaped (HBM-bound layers)
   if (g.a_pitch % 4 || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
   if ((g.b_row % 4) || (g.b_tap % 4)) return false;
@@ -264,7 +296,9 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.On = g.On, p.Oz = g.Oz, p.Ox = g.Ox, p.Oy = g.Oy;
-  pick_tile(g.Oz, g.Ox, g.Oy, &p.tz, &p.tx, &p.ty);
+  pick_tile(g.Oz, g.Ox, g.Oy, g.sz, g.sx, g.sy, &p.tz, &p.tx, &p.ty);
+  p.sz = g.sz, p.sx = g.sx, p.sy = g.sy;
+  p.gate = g.gate;
   p.ntz = (g.Oz + p.tz - 1) / p.tz, p.ntx = (g.Ox + p.tx - 1) / p.tx, p.nty = (g.Oy + p.ty - 1) / p.ty;
   p.kz = g.tz, p.kx = g.tx, p.ky = g.ty;
   p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
@@ -288,8 +322,9 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     cuuint64_t dims[5] = {(cuuint64_t)g.K, (cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
     cuuint64_t pitch = (cuuint64_t)g.a_pitch * 4;
     cuuint64_t strides[4] = {pitch, pitch * g.Ay, pitch * g.Ay * g.Ax, pitch * g.Ay * g.Ax * g.Az};
-    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    // strided gather (upconv dgrad): traverse ty*sy elements, keep every sy-th -> ty rows
+    cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)(p.ty * g.sy), (cuuint32_t)(p.tx * g.sx), (cuuint32_t)(p.tz * g.sz), 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)g.sy, (cuuint32_t)g.sx, (cuuint32_t)g.sz, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.A), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

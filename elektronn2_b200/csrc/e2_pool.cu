@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, const float* __res
 // Windows do not overlap and tile the input, so each dx element is written exactly once.
 template <int V>
 __global__ void __launch_bounds__(256) k_maxpool_bwd(PoolP p, const float* __restrict__ dy, const int* __restrict__ amax,
-                                                     const float* __restrict__ x, float* __restrict__ dx) {
+                                                     const float* __restrict__ x, float* __restrict__ dx,
+                                                     const float* __restrict__ gate) {
   const int cv = p.C / V;
   const int64_t total = (int64_t)p.n * p.Zo * p.Xo * p.Yo * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -156,6 +157,13 @@ __global__ void __launch_bounds__(256) k_maxpool_bwd(PoolP p, const float* __res
             v.load(x + ofs);
 #pragma unroll
             for (int j = 0; j < V; ++j) o.v[j] = (v.v[j] == mx[j]) ? g.v[j] : 0.f;
+          }
+          if (gate) {  // fused ReLU backward of the layer that produced the pooled tensor
+            Vec<V> gt;
+            gt.load(gate + ofs);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (!(gt.v[j] > 0.f)) o.v[j] = 0.f;
           }
           if (p.accumulate) {
             Vec<V> old;
@@ -204,7 +212,7 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
 }
 
 extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax,
-                                const float* x, float* dx, void* stream) {
+                                const float* x, float* dx, const float* relu_gate, void* stream) {
   PoolP p;
   int rc = fill_pool(h, d, &p);
   if (rc) return rc;
@@ -213,9 +221,11 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
              "maxpool3d_bwd: tie_mode FIRST needs argmax, tie_mode ALL needs x");
   int64_t work = e2_positions(&d->y) * d->y.c;
   if (vec4_ok({dy, dx, argmax, x}, {p.C, p.xp, p.yp})) {
-    k_maxpool_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx);
+    k_maxpool_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx,
+                                                                                               relu_gate);
   } else {
-    k_maxpool_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx);
+    k_maxpool_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx,
+                                                                                           relu_gate);
   }
   h->launches++;
   E2_CUDA_CHECK(h, "maxpool3d_bwd");
@@ -473,7 +483,8 @@ __global__ void __launch_bounds__(256) k_crop_fwd(CropP p, const float* __restri
 }
 
 template <int V>
-__global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restrict__ ddst, float* __restrict__ dsrc) {
+__global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restrict__ ddst, float* __restrict__ dsrc,
+                                                  const float* __restrict__ gate) {
   const int cv = p.C / V;
   const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -491,6 +502,13 @@ __global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restri
     if (inside) {
       int64_t dpos = (((int64_t)n * p.Zd + zd) * p.Xd + xd) * p.Yd + yd;
       v.load(ddst + dpos * p.dp + p.c0 + c);
+      if (gate) {  // fused ReLU backward of the layer that produced src
+        Vec<V> gt;
+        gt.load(gate + pos * p.sp + c);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (!(gt.v[j] > 0.f)) v.v[j] = 0.f;
+      }
       if (p.accumulate) {
         Vec<V> old;
         old.load(dsrc + pos * p.sp + c);
@@ -534,16 +552,17 @@ extern "C" int e2_crop_concat_fwd(e2_handle* h, const e2_crop_desc* d, const flo
   return E2_OK;
 }
 
-extern "C" int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc, void* stream) {
+extern "C" int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc,
+                                  const float* relu_gate, void* stream) {
   CropP p;
   int rc = fill_crop(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, ddst && dsrc, "crop_concat_bwd: null pointer");
   int64_t work = e2_positions(&d->src) * d->src.c;
   if (vec4_ok({ddst, dsrc}, {p.C, p.sp, p.dp, p.c0}))
-    k_crop_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc);
+    k_crop_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc, relu_gate);
   else
-    k_crop_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc);
+    k_crop_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc, relu_gate);
   h->launches++;
   E2_CUDA_CHECK(h, "crop_concat_bwd");
   return E2_OK;

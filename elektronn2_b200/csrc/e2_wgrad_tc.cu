@@ -2,16 +2,21 @@
 //
 // reduce-GEMM  W[r][tap][s] = sum_m P[m][r] * Q[pos(m) + tap + org][s]      (conv: P = dy, Q = x)
 //
-// Per filter tap this is D[r, s] = P^T Q_tap with the reduction running over positions, i.e.
+// Per filter tap this is D_tap[s, r] = Q_tap^T P with the reduction running over positions, i.e.
 // both operands are "MN-major": a shared-memory row is one position holding 32 consecutive
-// channels (128 B).  That is exactly what a channels-last TMA box load produces, so P and the
-// tap-shifted Q tiles go from HBM/L2 to the tensor core without any transpose:
-//   A = P tile   : 4 chunks of 32 r-channels x 64 positions  (MN-major, 128B swizzle / 32B atom)
-//   B = Q_tap    : NCH chunks of 32 s-channels x 64 positions
-//   D            : TMEM, 128 lanes (r) x [taps of this CTA][NCH*32] columns, fp32
-// The P tile is loaded once per position tile and reused for every tap of the CTA's tap group.
-// Each CTA owns (r-chunk, s-chunk, tap-group) and a slice of the position tiles (split-K over
-// positions); partial sums are added to dw with fp32 atomics in the reference's weight layout.
+// channels (128 B).  That is exactly what a channels-last TMA box load produces, so the dy tile
+// and the tap-shifted x tiles go from L2 to the tensor core without any transpose.
+//
+//   M (128 TMEM lanes) = [taps of one MMA group] x [s-channel block]: several taps are stacked
+//                        along M when the layer has few input channels (S <= 32: 4 taps,
+//                        S <= 64: 2 taps), so small layers still issue full 128-row MMAs
+//   N (<= 128 columns) = r-channel chunk of dy
+//   A = 4 chunks of (32 channels x 64 positions), one TMA box each (tap shift = box coordinates)
+//   B = dy tile, N/32 chunks, loaded once per position tile and reused by every tap group
+//   D = TMEM, [group][N] column blocks, fp32, accumulated over the CTA's slice of position tiles
+// MN-major tf32 operands exist only in the "128B swizzle, 32B atom" layout (UMMA layout type 1 ==
+// TMA SWIZZLE_128B_ATOM_32B).  Partial sums go to dw (reference layout) with fp32 atomics.
+#include <algorithm>
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
 #include "e2_tc_ptx.cuh"
@@ -20,21 +25,23 @@ namespace {
 
 constexpr int KP = 64;                    // positions per tile (reduction depth per stage)
 constexpr int CHUNK_BYTES = KP * 128;     // 32 channels x KP positions
-constexpr int A_CHUNKS = 4;               // M = 128 r-channels
+constexpr int A_CHUNKS = 4;               // M = 128 lanes
 constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;
-constexpr int A_SLOTS = 2;
+constexpr int B_SLOTS = 2;
 constexpr int WG_THREADS = 192;
 
 struct WgParams {
-  int Mn, Mz, Mx, My;      // P position grid
+  int Mn, Mz, Mx, My;      // position grid of P
   int tz, tx, ty;          // position tile box (product KP)
   int ntz, ntx, nty;
   int kz, kx, ky, oz, ox, oy;
   int R, S;
-  int nch;                 // B chunks (N = 32*nch)
-  int tg;                  // taps per CTA
-  int n_tg, n_rc, n_sc;    // tap groups, r chunks, s chunks
-  int b_slots;
+  int sw;                  // s-channels per tap inside one MMA group: 32, 64 or 128
+  int tpm;                 // taps per MMA group = 128 / sw
+  int n_cols;              // N = r-chunk width (multiple of 32, <= 128)
+  int gpc;                 // groups per CTA = 512 / n_cols (TMEM capacity)
+  int n_gs, n_rc, n_sc;    // group sets, r chunks, s chunks
+  int a_slots;
   int tmem_cols;
   int tiles_total, tiles_per_split;
   float* W;
@@ -46,28 +53,31 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap tmQ, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.nch * CHUNK_BYTES;
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + A_SLOTS * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + p.b_slots * b_bytes);
-  uint64_t* a_full = bars;                       // [A_SLOTS]
-  uint64_t* a_empty = a_full + A_SLOTS;          // [A_SLOTS]
-  uint64_t* b_full = a_empty + A_SLOTS;          // [b_slots]
-  uint64_t* b_empty = b_full + p.b_slots;        // [b_slots]
-  uint64_t* acc_full = b_empty + p.b_slots;
+  const int b_chunks = p.n_cols / 32;
+  const int b_bytes = b_chunks * CHUNK_BYTES;
+  uint8_t* smB = smem;
+  uint8_t* smA = smem + B_SLOTS * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smA + p.a_slots * A_BYTES);
+  uint64_t* b_full = bars;                       // [B_SLOTS]
+  uint64_t* b_empty = b_full + B_SLOTS;          // [B_SLOTS]
+  uint64_t* a_full = b_empty + B_SLOTS;          // [a_slots]
+  uint64_t* a_empty = a_full + p.a_slots;        // [a_slots]
+  uint64_t* acc_full = a_empty + p.a_slots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // unit decode: blockIdx.x = ((rc * n_sc) + sc) * n_tg + tgi
+  // unit decode: blockIdx.x = ((rc * n_sc) + sc) * n_gs + gs
   int u = blockIdx.x;
-  const int tgi = u % p.n_tg;
-  u /= p.n_tg;
+  const int gs = u % p.n_gs;
+  u /= p.n_gs;
   const int sc = u % p.n_sc;
   const int rc = u / p.n_sc;
   const int T = p.kz * p.kx * p.ky;
-  const int tap0 = tgi * p.tg;
-  const int ntap = min(p.tg, T - tap0);
-  const int r0 = rc * 128, s0 = sc * p.nch * 32;
+  const int tap0 = gs * p.gpc * p.tpm;                       // first tap of this CTA
+  const int ntap = min(p.gpc * p.tpm, T - tap0);
+  const int ngroups = (ntap + p.tpm - 1) / p.tpm;
+  const int r0 = rc * p.n_cols, s0 = sc * p.sw;
+  const int spb = p.sw / 32;                                 // 32-channel blocks per tap
   const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
   const int ntiles = max(t_end - t_begin, 0);
@@ -75,8 +85,8 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmP);
     tc::prefetch_tmap(&tmQ);
-    for (int i = 0; i < A_SLOTS; ++i) tc::mbar_init(&a_full[i], 1), tc::mbar_init(&a_empty[i], 1);
-    for (int i = 0; i < p.b_slots; ++i) tc::mbar_init(&b_full[i], 1), tc::mbar_init(&b_empty[i], 1);
+    for (int i = 0; i < B_SLOTS; ++i) tc::mbar_init(&b_full[i], 1), tc::mbar_init(&b_empty[i], 1);
+    for (int i = 0; i < p.a_slots; ++i) tc::mbar_init(&a_full[i], 1), tc::mbar_init(&a_empty[i], 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
@@ -90,8 +100,9 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int bit = 0;
+      int ait = 0;
       for (int ti = 0; ti < ntiles; ++ti) {
         int t = t_begin + ti;
         const int ity = t % p.nty;
@@ -101,72 +112,79 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
         const int itz = t % p.ntz;
         const int in_ = t / p.ntz;
         const int z0 = itz * p.tz, x0 = itx * p.tx, y0 = ity * p.ty;
-        const int as = ti % A_SLOTS;
-        tc::mbar_wait(&a_empty[as], ((uint32_t)(ti / A_SLOTS) & 1u) ^ 1u);
-        tc::mbar_arrive_expect_tx(&a_full[as], (uint32_t)A_BYTES);
-        for (int c = 0; c < A_CHUNKS; ++c)
-          tc::tma_load_5d(smA + as * A_BYTES + c * CHUNK_BYTES, &tmP, &a_full[as], r0 + c * 32, y0, x0, z0, in_);
-        for (int tl = 0; tl < ntap; ++tl, ++bit) {
-          const int tap = tap0 + tl;
-          const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
-          const int bs = bit % p.b_slots;
-          tc::mbar_wait(&b_empty[bs], ((uint32_t)(bit / p.b_slots) & 1u) ^ 1u);
-          tc::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
-          for (int c = 0; c < p.nch; ++c)
-            tc::tma_load_5d(smB + bs * b_bytes + c * CHUNK_BYTES, &tmQ, &b_full[bs], s0 + c * 32, y0 + k3 + p.oy,
+        const int bs = ti % B_SLOTS;
+        tc::mbar_wait(&b_empty[bs], ((uint32_t)(ti / B_SLOTS) & 1u) ^ 1u);
+        tc::mbar_arrive_expect_tx(&b_full[bs], (uint32_t)b_bytes);
+        for (int c = 0; c < b_chunks; ++c)
+          tc::tma_load_5d(smB + bs * b_bytes + c * CHUNK_BYTES, &tmP, &b_full[bs], r0 + c * 32, y0, x0, z0, in_);
+        for (int g = 0; g < ngroups; ++g, ++ait) {
+          const int as = ait % p.a_slots;
+          tc::mbar_wait(&a_empty[as], ((uint32_t)(ait / p.a_slots) & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(&a_full[as], (uint32_t)A_BYTES);
+          for (int ci = 0; ci < A_CHUNKS; ++ci) {
+            const int tl = g * p.tpm + ci / spb;
+            const int sb = ci % spb;
+            // taps past the end of the filter: any in-range box, its rows are never stored
+            const int tap = min(tap0 + tl, T - 1);
+            const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
+            tc::tma_load_5d(smA + as * A_BYTES + ci * CHUNK_BYTES, &tmQ, &a_full[as], s0 + sb * 32, y0 + k3 + p.oy,
                             x0 + j3 + p.ox, z0 + i3 + p.oz, in_);
+          }
         }
       }
     }
   } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      int bit = 0;
-      const uint32_t ncols = (uint32_t)p.nch * 32u;
+      int ait = 0;
       for (int ti = 0; ti < ntiles; ++ti) {
-        const int as = ti % A_SLOTS;
-        tc::mbar_wait(&a_full[as], (uint32_t)(ti / A_SLOTS) & 1u);
-        const uint32_t a_addr = tc::smem_u32(smA + as * A_BYTES);
-        for (int tl = 0; tl < ntap; ++tl, ++bit) {
-          const int bs = bit % p.b_slots;
-          tc::mbar_wait(&b_full[bs], (uint32_t)(bit / p.b_slots) & 1u);
+        const int bs = ti % B_SLOTS;
+        tc::mbar_wait(&b_full[bs], (uint32_t)(ti / B_SLOTS) & 1u);
+        const uint32_t b_addr = tc::smem_u32(smB + bs * b_bytes);
+        for (int g = 0; g < ngroups; ++g, ++ait) {
+          const int as = ait % p.a_slots;
+          tc::mbar_wait(&a_full[as], (uint32_t)(ait / p.a_slots) & 1u);
           tc::tc_fence_after();
-          const uint32_t b_addr = tc::smem_u32(smB + bs * b_bytes);
+          const uint32_t a_addr = tc::smem_u32(smA + as * A_BYTES);
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) {
-            // MN-major tf32 operands exist only in the "128B swizzle, 32B atom" layout (UMMA layout
-            // type 1 == TMA SWIZZLE_128B_ATOM_32B): rows (positions) 128 B apart, swizzle period
-            // 4 rows = 512 B (SBO), 32-channel chunks CHUNK_BYTES apart (LBO); K = 8 rows per MMA
+            // rows (positions) 128 B apart, swizzle period 4 rows = 512 B (SBO), 32-channel chunks
+            // CHUNK_BYTES apart (LBO); one MMA consumes K = 8 positions = 1024 B
             const uint64_t ad = tc::make_smem_desc(a_addr + k * 1024, CHUNK_BYTES, 512, 1);
             const uint64_t bd = tc::make_smem_desc(b_addr + k * 1024, CHUNK_BYTES, 512, 1);
-            tc::mma_tf32_ss(tmem_base + (uint32_t)tl * ncols, ad, bd, p.idesc, (ti > 0 || k > 0) ? 1u : 0u);
+            tc::mma_tf32_ss(tmem_base + (uint32_t)(g * p.n_cols), ad, bd, p.idesc, (ti > 0 || k > 0) ? 1u : 0u);
           }
-          tc::mma_commit(&b_empty[bs]);
+          tc::mma_commit(&a_empty[as]);
         }
-        tc::mma_commit(&a_empty[as]);
+        tc::mma_commit(&b_empty[bs]);
       }
       tc::mma_commit(acc_full);
     }
   } else {
+    // ---------------------------------------------------------------------- epilogue
     const int q = warp & 3;
-    const int r = r0 + q * 32 + lane;
+    const int row = q * 32 + lane;                  // TMEM lane = (tap_local, s)
+    const int tl_in_group = row / p.sw;
+    const int s = s0 + row % p.sw;
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
     if (ntiles > 0) {
-      const int ncols = p.nch * 32;
-      for (int tl = 0; tl < ntap; ++tl) {
-        const int tap = tap0 + tl;
-        const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
+      for (int g = 0; g < ngroups; ++g) {
+        const int tap = tap0 + g * p.tpm + tl_in_group;
+        const bool row_ok = tap < T && tap < tap0 + ntap && s < p.S;
+        const int tq = min(tap, T - 1);
+        const int k3 = tq % p.ky, j3 = (tq / p.ky) % p.kx, i3 = tq / (p.ky * p.kx);
         const int tflip = ((p.kz - 1 - i3) * p.kx + (p.kx - 1 - j3)) * p.ky + (p.ky - 1 - k3);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = 0; c0 < p.n_cols; c0 += 32) {
           uint32_t v[32];
-          tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * ncols + c0), v);
+          tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_cols + c0), v);
           tc::tmem_ld_wait();
-          if (r >= p.R) continue;
+          if (!row_ok) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int s = s0 + c0 + j;
-            if (s >= p.S) continue;
-            const int64_t ofs = (p.out_mode == 0) ? ((int64_t)r * p.S + s) * T + tflip : ((int64_t)s * p.R + r) * T + tap;
+            const int r = r0 + c0 + j;
+            if (r >= p.R) continue;
+            const int64_t ofs = (p.out_mode == 0) ? ((int64_t)r * p.S + s) * T + tflip : ((int64_t)s * p.R + r) * T + tq;
             atomicAdd(p.W + ofs, __uint_as_float(v[j]));
           }
         }
@@ -216,32 +234,34 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
   p.kz = g.tz, p.kx = g.tx, p.ky = g.ty, p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
   p.R = g.R, p.S = g.S;
   const int T = g.tz * g.tx * g.ty;
-  int nch = (g.S + 31) / 32;
-  if (nch > 4) nch = 4;                      // N <= 128 per tap keeps the B ring at 3-4 slots
-  p.nch = nch;
-  p.n_sc = (g.S + nch * 32 - 1) / (nch * 32);
-  p.n_rc = (g.R + 127) / 128;
-  int tg = 512 / (nch * 32);
-  if (tg > T) tg = T;
-  p.tg = tg;
-  p.n_tg = (T + tg - 1) / tg;
+  p.sw = g.S <= 32 ? 32 : (g.S <= 64 ? 64 : 128);
+  p.tpm = 128 / p.sw;
+  p.n_sc = (g.S + p.sw - 1) / p.sw;
+  int ncols = (g.R + 31) / 32 * 32;
+  if (ncols > 128) ncols = 128;
+  p.n_cols = ncols;
+  p.n_rc = (g.R + ncols - 1) / ncols;
+  p.gpc = 512 / ncols;
+  const int taps_per_cta = p.gpc * p.tpm;
+  p.n_gs = (T + taps_per_cta - 1) / taps_per_cta;
+  const int groups_max = (std::min(taps_per_cta, T) + p.tpm - 1) / p.tpm;
   int cols = 32;
-  while (cols < tg * nch * 32) cols *= 2;
+  while (cols < groups_max * ncols) cols *= 2;
   p.tmem_cols = cols;
-  const int b_bytes = nch * CHUNK_BYTES;
-  int b_slots = (int)((200 * 1024 - A_SLOTS * A_BYTES) / b_bytes);
-  if (b_slots > 6) b_slots = 6;
-  if (b_slots < 2) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: shared memory budget");
-  p.b_slots = b_slots;
+  const int b_bytes = (ncols / 32) * CHUNK_BYTES;
+  int a_slots = (int)((208 * 1024 - B_SLOTS * b_bytes) / A_BYTES);
+  if (a_slots > 5) a_slots = 5;
+  if (a_slots < 2) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: shared memory budget");
+  p.a_slots = a_slots;
   p.tiles_total = g.Mn * p.ntz * p.ntx * p.nty;
-  const int units = p.n_rc * p.n_sc * p.n_tg;
+  const int units = p.n_rc * p.n_sc * p.n_gs;
   int splits = (2 * h->sm_count + units - 1) / units;
   if (splits > p.tiles_total) splits = p.tiles_total;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
   p.W = g.W, p.out_mode = g.out_mode;
-  p.idesc = tc::make_idesc(2 /*TF32*/, 1, 1, 128, (uint32_t)(nch * 32));
+  p.idesc = tc::make_idesc(2 /*TF32*/, 1, 1, 128, (uint32_t)ncols);
 
   CUtensorMap tmP, tmQ;
   {
@@ -251,8 +271,8 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
     cuuint32_t box[5] = {32, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.P), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(P) failed: %d", (int)r);
   }
   {
@@ -262,12 +282,12 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
     cuuint32_t box[5] = {32, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.Q), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(Q) failed: %d", (int)r);
   }
   cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
-  const size_t smem = 1024 + (size_t)A_SLOTS * A_BYTES + (size_t)b_slots * b_bytes + (2 * A_SLOTS + 2 * b_slots + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)B_SLOTS * b_bytes + (size_t)a_slots * A_BYTES + (2 * B_SLOTS + 2 * a_slots + 1) * 8 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)

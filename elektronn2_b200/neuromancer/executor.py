@@ -296,6 +296,7 @@ class Plan(object):
             raise ValueError("a training plan needs a Softmax -> MultinoulliNLL -> AggregateLoss head")
         h = self.h
         self.grad, written = {}, set()
+        self._contrib = {}   # node -> [bool]: was each gradient contribution ReLU-gated by its producer?
         for n in self.nodes:
             if n in self.val and not isinstance(n, (Input, loss_nodes.Softmax)):
                 if n in self.alias_of or n in self.crop_into:
@@ -340,8 +341,10 @@ class Plan(object):
                 if isinstance(par, Input):
                     continue
                 acc = par in written
+                gate = self._gate_for(par)
                 self._b('pool_bwd:' + n.name,
-                        lambda op=self.aux[n], dy=self.grad[n], dx=self.grad[par], acc=acc: op.bwd(dy, dx, acc), 0,
+                        lambda op=self.aux[n], dy=self.grad[n], dx=self.grad[par], acc=acc, gate=gate:
+                        op.bwd(dy, dx, acc, relu_gate=gate), 0,
                         4 * (2 * _nel(self.grad[n]) + _nel(self.grad[par])))
                 written.add(par)
             elif isinstance(n, Crop):
@@ -356,8 +359,10 @@ class Plan(object):
                 else:
                     ddst = self.grad[n]
                 acc = par in written
+                gate = self._gate_for(par)
                 self._b('crop_concat_bwd:' + n.name,
-                        lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc: op.bwd(ddst, dx, acc), 0,
+                        lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc, gate=gate:
+                        op.bwd(ddst, dx, acc, relu_gate=gate), 0,
                         4 * (_nel(self.val[n]) + (2 if acc else 1) * _nel(self.grad[par])))
                 written.add(par)
             elif isinstance(n, Concat):
@@ -368,6 +373,7 @@ class Plan(object):
                     if isinstance(p, Input):
                         continue
                     acc = p in written
+                    self._contrib.setdefault(p, []).append(False)
                     self._b('concat_copy_bwd:' + n.name,
                             lambda op=op, ddst=self.grad[n], dx=self.grad[p], acc=acc: op.bwd(ddst, dx, acc), 0,
                             8 * _nel(self.grad[p]))
@@ -376,12 +382,34 @@ class Plan(object):
                 par = n.parent
                 if par in written:
                     raise NotImplementedError("FragmentsToDense parent with several consumers")
+                self._contrib.setdefault(par, []).append(False)
                 self._b('frag2dense_bwd:' + n.name,
                         lambda op=self.aux[n], dd=self.grad[n], df=self.grad[par]: op.bwd(dd, df), 0,
                         8 * _nel(self.grad[par]))
                 written.add(par)
 
+    def _gate_for(self, parent):
+        """Tensor to ReLU-gate a gradient contribution into ``grad[parent]`` with (fused ReLU
+        backward), or None.  Also records whether the contribution is gated."""
+        def relu_node(n):
+            return isinstance(n, Conv) and n.activation_func == 'relu'
+        gate = None
+        if relu_node(parent):
+            gate = self.val[parent]
+        elif isinstance(parent, Concat) and parent not in self.copy_into and all(
+                (q in self.alias_of and relu_node(q)) or (q in self.crop_into and relu_node(q.parent))
+                for q in parent.parents):
+            gate = self.val[parent]   # every channel of the buffer is a (copied) post-ReLU value
+            for q in parent.parents:
+                if q in self.alias_of:
+                    self._contrib.setdefault(q, []).append(True)
+        self._contrib.setdefault(parent, []).append(gate is not None)
+        return gate
+
     def _emit_act_bwd(self, n, dy):
+        c = self._contrib.get(n)
+        if n.activation_func == 'relu' and c and all(c):
+            return  # every producer of this gradient already applied the ReLU gate
         if n.activation_func not in ('lin', 'linear'):
             h = self.h
             self._b('act_bwd:' + n.name,
@@ -391,8 +419,9 @@ class Plan(object):
         if isinstance(parent, Input):
             return  # gradients are taken w.r.t. parameters only (model.py:182)
         acc = parent in written
-        self._b(label, lambda op=op, dy=dy, dx=self.grad[parent], acc=acc: op.dgrad(dy, dx, acc), flops,
-                4 * (_nel(dy) + _nel(self.grad[parent])), kind)
+        gate = self._gate_for(parent)
+        self._b(label, lambda op=op, dy=dy, dx=self.grad[parent], acc=acc, gate=gate:
+                op.dgrad(dy, dx, acc, relu_gate=gate), flops, 4 * (_nel(dy) + _nel(self.grad[parent])), kind)
         written.add(parent)
 
     # ---------------------------------------------------------------- execution

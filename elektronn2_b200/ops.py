@@ -56,9 +56,11 @@ class ConvOp(object):
         self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), None, 0, self.h.stream())
 
-    def dgrad(self, dy, dx, accumulate=False):
+    def dgrad(self, dy, dx, accumulate=False, relu_gate=None):
+        """relu_gate: post-ReLU output of the layer that produced x (fused ReLU backward)."""
         d = self._desc(x=dx, y=dy, accumulate=accumulate)
-        self.h.call('e2_conv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(), None, 0, self.h.stream())
+        self.h.call('e2_conv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(),
+                    relu_gate.ptr() if relu_gate is not None else None, None, 0, self.h.stream())
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
@@ -97,9 +99,10 @@ class UpConvOp(object):
         self.h.call('e2_upconv3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if self.d.has_bias else None, self.y.ptr(), None, 0, self.h.stream())
 
-    def dgrad(self, dy, dx, accumulate=False):
+    def dgrad(self, dy, dx, accumulate=False, relu_gate=None):
         d = self._desc(x=dx, y=dy, accumulate=accumulate)
-        self.h.call('e2_upconv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(), None, 0, self.h.stream())
+        self.h.call('e2_upconv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(),
+                    relu_gate.ptr() if relu_gate is not None else None, None, 0, self.h.stream())
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
@@ -122,12 +125,12 @@ class PoolOp(object):
         self.h.call('e2_maxpool3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.bias), self.y.ptr(),
                     self.argmax.ptr() if self.argmax is not None else None, self.h.stream())
 
-    def bwd(self, dy, dx, accumulate=False):
+    def bwd(self, dy, dx, accumulate=False, relu_gate=None):
         d = _lib.PoolDesc()
         C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
         d.x, d.y, d.accumulate = dx.desc, dy.desc, int(accumulate)
         self.h.call('e2_maxpool3d_bwd', C.byref(d), dy.ptr(), self.argmax.ptr() if self.argmax is not None else None,
-                    self.x.ptr(), dx.ptr(), self.h.stream())
+                    self.x.ptr(), dx.ptr(), relu_gate.ptr() if relu_gate is not None else None, self.h.stream())
 
 
 class MfpOp(object):
@@ -179,11 +182,12 @@ class CropConcatOp(object):
     def fwd(self):
         self.h.call('e2_crop_concat_fwd', C.byref(self.d), self.src.ptr(), self.dst.ptr(), self.h.stream())
 
-    def bwd(self, ddst, dsrc, accumulate=False):
+    def bwd(self, ddst, dsrc, accumulate=False, relu_gate=None):
         d = _lib.CropDesc()
         C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
         d.accumulate = int(accumulate)
-        self.h.call('e2_crop_concat_bwd', C.byref(d), ddst.ptr(), dsrc.ptr(), self.h.stream())
+        self.h.call('e2_crop_concat_bwd', C.byref(d), ddst.ptr(), dsrc.ptr(),
+                    relu_gate.ptr() if relu_gate is not None else None, self.h.stream())
 
 
 class LossOp(object):

@@ -103,9 +103,13 @@ int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes);
 /* y = act(conv(x, w) + bias) */
 int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x, const float* wf, const float* bias,
                   float* y, void* ws, size_t ws_bytes, void* stream);
-/* dx (=|+=) full-correlation(dy, w) */
+/* dx (=|+=) full-correlation(dy, w).
+ * relu_gate (nullable, all four *_dgrad / *_bwd entry points that take it): the post-ReLU
+ * output of the layer that produced x (same geometry and pitch as dx).  When given, the
+ * contribution computed by this call is zeroed wherever relu_gate <= 0, i.e. the ReLU
+ * backward of the upstream layer is fused into this kernel's epilogue. */
 int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float* dy, const float* wd, float* dx,
-                    void* ws, size_t ws_bytes, void* stream);
+                    const float* relu_gate, void* ws, size_t ws_bytes, void* stream);
 /* dw (reference layout, overwritten) and optional db = sum dy */
 int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float* x, const float* dy, float* dw, float* db,
                     void* ws, size_t ws_bytes, void* stream);
@@ -127,7 +131,7 @@ int e2_upconv3d_pack_weights(e2_handle* h, const e2_upconv_desc* d, const float*
 int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* wf, const float* bias,
                     float* y, void* ws, size_t ws_bytes, void* stream);
 int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const float* dy, const float* wd, float* dx,
-                      void* ws, size_t ws_bytes, void* stream);
+                      const float* relu_gate, void* ws, size_t ws_bytes, void* stream);
 int e2_upconv3d_wgrad(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* dy, float* dw, float* db,
                       void* ws, size_t ws_bytes, void* stream);
 
@@ -158,7 +162,7 @@ int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const 
 /* E2_TIE_FIRST routes dy through argmax (x may be NULL); E2_TIE_ALL (Theano-CPU
  * semantics) needs x and the pooled pre-bias maximum is recomputed from it. */
 int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax, const float* x,
-                     float* dx, void* stream);
+                     float* dx, const float* relu_gate, void* stream);
 
 /* ------------------------------------------------------ max-fragment-pooling
  * computations.fragmentpool, computations.py:652-678.  Output batch = prod(p) * n,
@@ -205,7 +209,8 @@ typedef struct {
 
 int e2_crop_concat_fwd(e2_handle* h, const e2_crop_desc* d, const float* src, float* dst, void* stream);
 /* dsrc[.. cropped region ..] (=|+=) ddst[..., dst_c0 + c]; with accumulate==0 the border of dsrc is zeroed */
-int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc, void* stream);
+int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const float* ddst, float* dsrc, const float* relu_gate,
+                       void* stream);
 
 /* ------------------------------------------------ loss head (next-row 8f-2)
  * Softmax (computations.py:170-177) -> MultinoulliNLL sparse target
