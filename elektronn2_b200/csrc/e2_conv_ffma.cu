@@ -10,6 +10,7 @@
 //                 upconv fwd (taps=1, N=(tap,o), pixel-shuffle epilogue)
 //   reduce-GEMM   W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]
 //                 conv wgrad (P=dy,Q=x), upconv wgrad (P=x,Q=dy,st=p)
+#include <stdlib.h>
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
 
@@ -538,6 +539,15 @@ extern "C" int e2_act_bwd(e2_handle* h, const e2_tensor* t, int32_t act, const f
 }
 
 // ------------------------------------------------------------------- op front-ends
+int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s) {
+  static const bool no_plane = getenv("E2_DISABLE_PLANE") != nullptr;   // A/B switch for profiling
+  if (compute == E2_COMPUTE_TF32) {
+    if (!no_plane && e2_gather_gemm_tc_ok(h, g) && e2_conv_plane_tc_ok(h, g)) return e2_launch_conv_plane_tc(h, g, s);
+    if (e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
+  }
+  return e2_launch_gather_gemm_ffma(h, g, s);
+}
+
 static void conv_fwd_problem(const e2_conv_desc* d, const float* x, const float* wf, const float* bias, float* y,
                              GatherGemm* g) {
   memset(g, 0, sizeof(*g));
@@ -571,8 +581,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   conv_fwd_problem(d, x, wf, bias, y, &g);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->x.c == 1) return e2_launch_conv_c1_fwd(h, g, s);
-  if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
-  return e2_launch_gather_gemm_ffma(h, g, s);
+  return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
 extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float* dy, const float* wd, float* dx,
@@ -595,8 +604,7 @@ extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float*
   g.accumulate = d->accumulate;
   g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
-  return e2_launch_gather_gemm_ffma(h, g, s);
+  return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
 extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float* x, const float* dy, float* dw,
@@ -645,8 +653,7 @@ extern "C" int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const floa
   g.shuffle = 1, g.pz = d->pz, g.px = d->px, g.py = d->py, g.Fo = d->y.c;
   g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
-  return e2_launch_gather_gemm_ffma(h, g, s);
+  return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
 extern "C" int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const float* dy, const float* wd, float* dx,
@@ -669,8 +676,7 @@ extern "C" int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const fl
   g.accumulate = d->accumulate;
   g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->compute == E2_COMPUTE_TF32 && e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
-  return e2_launch_gather_gemm_ffma(h, g, s);
+  return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
 extern "C" int e2_upconv3d_wgrad(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* dy, float* dw,

@@ -106,6 +106,11 @@ def main():
     cases = [(1, 32, (4, 10, 18), 64, (1, 1, 1)), (1, 32, (6, 10, 18), 64, (3, 3, 3)), (2, 20, (5, 12, 11), 40, (3, 3, 3)),
              (1, 40, (4, 9, 9), 150, (2, 4, 4)), (1, 64, (5, 9, 10), 64, (3, 3, 3)), (1, 128, (4, 6, 6), 256, (3, 3, 3)),
              (1, 200, (2, 6, 6), 200, (1, 1, 1)), (1, 256, (5, 7, 7), 512, (3, 3, 3)), (1, 768, (5, 6, 6), 256, (3, 3, 3))]
+    # shapes that qualify for the halo-reuse (plane) kernel: ragged edges, several channel blocks,
+    # even / asymmetric filters, more than one N tile
+    cases += [(1, 32, (6, 30, 18), 48, (3, 3, 3)), (1, 20, (5, 30, 26), 40, (3, 3, 3)), (2, 64, (4, 18, 18), 128, (1, 3, 3)),
+              (1, 40, (7, 19, 19), 80, (4, 4, 4)), (1, 64, (3, 18, 18), 300, (3, 3, 3)), (1, 100, (5, 27, 19), 36, (2, 4, 4)),
+              (1, 32, (9, 34, 34), 64, (3, 3, 3))]
     for c in cases:
         ok &= check_conv(h, *c)
     for c in [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (1, 64, (3, 4, 5), 64, (2, 2, 2)), (1, 512, (7, 9, 9), 512, (2, 2, 2))]:
