@@ -6,13 +6,14 @@
 //
 //   tile     = TZ output z-planes x (16 x-lines x 8 y) positions x BN channels; one accumulator
 //              of [128 lanes x BN columns] per output plane, all TZ of them live in TMEM
-//   plane    = one TMA box (32 channels, 16 y, 16+kx-1 x, 1 z): rows of 128 B in (x,y) order, 16
-//              rows per x-line, 128B-swizzled
+//   plane    = one TMA box (32 channels, YP = 8+ky-1 y, 16+kx-1 x, 1 z): rows of 128 B in (x,y)
+//              order, YP rows per x-line, 128B-swizzled
 //   A view   = for tap (i,j,k) and output plane zl the 128 rows needed are 16 groups (x-lines) of
-//              8 consecutive rows starting at row (j*16 + k) of input plane zl+i.  A UMMA K-major
-//              descriptor expresses exactly that: start address = plane + (j*16+k)*128 B,
-//              stride between 8-row groups (SBO) = 16*128 B, and the 128B-swizzle phase of the
-//              start row goes into the descriptor's base-offset field.  No data movement per tap.
+//              8 consecutive rows starting at row (j*YP + k) of input plane zl+i.  A UMMA K-major
+//              descriptor expresses exactly that: start address = plane + (j*YP+k)*128 B, stride
+//              between 8-row groups (SBO) = YP*128 B.  The 128B swizzle of both TMA and UMMA is a
+//              pure function of the shared-memory address bits (measured on B200: views starting
+//              at any 128-B row work with base_offset = 0), so no data movement per tap.
 //   weights  = [BN x 32] block per (channel block, tap) through a small TMA ring; each block is
 //              used by TZ MMAs groups (one per output plane), dividing the weight traffic by TZ
 //   schedule = channel block (outer) -> z tap i -> (j,k) taps -> output planes; an input plane is
@@ -21,24 +22,25 @@
 //              epilogue.  Persistent CTAs (one per SM) loop over tiles; with 2*TZ*BN <= 512 the
 //              accumulators are double-buffered so the epilogue of tile t overlaps tile t+1.
 #include <algorithm>
+#include <stdlib.h>
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
 #include "e2_tc_ptx.cuh"
 
 namespace {
 
-constexpr int TX = 16, TY = 8, YP = 16;   // tile x/y extent, rows per x-line in smem
+constexpr int TX = 16, TY = 8;   // tile x/y extent
 constexpr int PL_THREADS = 256;
 constexpr int MAX_SLOTS = 8;
 
 struct PlaneParams {
   int On, Oz, Ox, Oy;
   int ntz, ntx, nty, ntn;     // tiles per axis, N tiles
-  int TZ, NP, XH;
+  int TZ, NP, XH, YP;
   int kz, kx, ky, oz, ox, oy;
   int K, N, BN, CB;
   int nslot, wslot, acc_bufs;
-  int plane_bytes, w_bytes;
+  int plane_bytes, plane_stride, w_bytes;
   int tmem_cols;
   int num_tiles;
   float* C;
@@ -49,20 +51,13 @@ struct PlaneParams {
   uint32_t idesc;
 };
 
-__device__ __forceinline__ uint64_t a_view_desc(uint32_t addr) {
-  // K-major, 128B swizzle, 8-row groups YP*128 B apart; base offset = swizzle phase of the start row
-  uint64_t d = tc::make_smem_desc(addr, 16, YP * 128, 2);
-  d |= (uint64_t)((addr >> 7) & 7u) << 49;
-  return d;
-}
-
 __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const PlaneParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smP = smem;                                   // plane slots
-  uint8_t* smW = smem + p.nslot * p.plane_bytes;         // weight ring
+  uint8_t* smW = smem + p.nslot * p.plane_stride;        // weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(smW + p.wslot * p.w_bytes);
   uint64_t* pl_full = bars;
   uint64_t* pl_empty = pl_full + MAX_SLOTS;
@@ -115,7 +110,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_co
             const int s = pc % p.nslot;
             tc::mbar_wait(&pl_empty[s], ((uint32_t)(pc / p.nslot) & 1u) ^ 1u);
             tc::mbar_arrive_expect_tx(&pl_full[s], (uint32_t)p.plane_bytes);
-            tc::tma_load_5d(smP + s * p.plane_bytes, &tmA, &pl_full[s], cb * 32, y0 + p.oy, x0 + p.ox,
+            tc::tma_load_5d(smP + s * p.plane_stride, &tmA, &pl_full[s], cb * 32, y0 + p.oy, x0 + p.ox,
                             z0 + p.oz + pl, in_);
           }
       }
@@ -141,6 +136,11 @@ __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_co
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int pc0 = 0, wc = 0, tcount = 0;
+      const uint32_t smP_addr = tc::smem_u32(smP), smW_addr = tc::smem_u32(smW);
+      // K-major 128B-swizzle descriptor templates (start address added per MMA):
+      // A: 8-row groups YP*128 B apart (shifted view into a halo plane); B: dense, 1024 B apart
+      const uint64_t a_tmpl = tc::make_smem_desc(0, 16, (uint32_t)(p.YP * 128), 2);
+      const uint64_t b_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
         const int buf = tcount % p.acc_bufs;
         tc::mbar_wait(&acc_empty[buf], ((uint32_t)(tcount / p.acc_bufs) & 1u) ^ 1u);
@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_co
               const int j = jk / p.ky, k = jk % p.ky;
               const int ws = wc % p.wslot;
               tc::mbar_wait(&w_full[ws], (uint32_t)(wc / p.wslot) & 1u);
-              const uint32_t b_addr = tc::smem_u32(smW + ws * p.w_bytes);
+              const uint64_t bd0 = b_tmpl + (uint64_t)((smW_addr + (uint32_t)(ws * p.w_bytes)) >> 4);
+              const uint32_t row_off = (uint32_t)((j * p.YP + k) * 128);
+              const uint32_t first = (cb == 0 && i == 0 && jk == 0) ? 0u : 1u;
               for (int zl = 0; zl < p.TZ; ++zl) {
                 const int pl = zl + i;
                 const int pc = pc0 + pl;
@@ -163,15 +165,13 @@ __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_co
                   waited |= 1u << pl;
                 }
                 tc::tc_fence_after();
-                const uint32_t a_addr = tc::smem_u32(smP + s * p.plane_bytes) + (uint32_t)((j * YP + k) * 128);
+                // descriptors differ only in the start-address field (low 14 bits, 16-byte units)
+                const uint64_t ad0 = a_tmpl + (uint64_t)((smP_addr + (uint32_t)(s * p.plane_stride) + row_off) >> 4);
                 const uint32_t acc = acc0 + (uint32_t)(zl * p.BN);
-                const uint32_t first = (cb == 0 && i == 0 && jk == 0) ? 0u : 1u;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t ad = a_view_desc(a_addr + ks * 32);
-                  const uint64_t bd = tc::make_smem_desc(b_addr + ks * 32, 16, 1024, 2);
-                  tc::mma_tf32_ss(acc, ad, bd, p.idesc, (first | (uint32_t)ks) ? 1u : 0u);
-                }
+                tc::mma_tf32_ss(acc, ad0, bd0, p.idesc, first);
+                tc::mma_tf32_ss(acc, ad0 + 2, bd0 + 2, p.idesc, 1u);
+                tc::mma_tf32_ss(acc, ad0 + 4, bd0 + 4, p.idesc, 1u);
+                tc::mma_tf32_ss(acc, ad0 + 6, bd0 + 6, p.idesc, 1u);
               }
               tc::mma_commit(&w_empty[ws]);
             }
@@ -268,7 +268,9 @@ static bool plan_plane(const e2_handle* h, const GatherGemm& g, PlaneParams* p) 
   if (g.Ox < 12 || g.Oy < 6) return false;       // tile quantisation would waste too much
   memset(p, 0, sizeof(*p));
   p->XH = TX + g.tx - 1;
-  p->plane_bytes = p->XH * YP * 128;
+  p->YP = TY + g.ty - 1;
+  p->plane_bytes = p->XH * p->YP * 128;
+  p->plane_stride = (p->plane_bytes + 1023) / 1024 * 1024;   // slots stay 1024-B aligned (swizzle period)
   int bn = (g.N + 15) / 16 * 16;
   if (bn > 256) bn = 256;
   // prefer an N tile that divides N into equal parts
@@ -282,7 +284,7 @@ static bool plan_plane(const e2_handle* h, const GatherGemm& g, PlaneParams* p) 
     if (tz * bn > 512) continue;
     const int np = tz + g.tz - 1;
     if (np > MAX_SLOTS) continue;
-    const int need = np * p->plane_bytes + 3 * p->w_bytes;
+    const int need = np * p->plane_stride + 3 * p->w_bytes;
     if (need <= budget) {
       best_tz = tz;
       break;
@@ -292,12 +294,13 @@ static bool plan_plane(const e2_handle* h, const GatherGemm& g, PlaneParams* p) 
   if (best_tz > g.Oz) best_tz = g.Oz;
   p->TZ = best_tz;
   p->NP = best_tz + g.tz - 1;
-  int rest = budget - p->NP * p->plane_bytes;
-  // spare memory: first one extra plane slot (prefetch across units), then weight slots
+  int rest = budget - p->NP * p->plane_stride;
+  // spare memory: extra plane slots first (the next unit's first z-tap phase needs TZ planes
+  // in flight while the current unit finishes), then weight slots
   p->nslot = p->NP;
-  if (p->nslot < MAX_SLOTS && rest - p->plane_bytes >= 4 * p->w_bytes) {
+  while (p->nslot < MAX_SLOTS && p->nslot < p->NP + p->TZ && rest - p->plane_stride >= 4 * p->w_bytes) {
     p->nslot += 1;
-    rest -= p->plane_bytes;
+    rest -= p->plane_stride;
   }
   p->wslot = std::min(MAX_SLOTS, rest / p->w_bytes);
   if (p->wslot < 2) return false;
@@ -334,7 +337,7 @@ int e2_launch_conv_plane_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
     cuuint64_t dims[5] = {(cuuint64_t)g.K, (cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
     cuuint64_t pitch = (cuuint64_t)g.a_pitch * 4;
     cuuint64_t strides[4] = {pitch, pitch * g.Ay, pitch * g.Ay * g.Ax, pitch * g.Ay * g.Ax * g.Az};
-    cuuint32_t box[5] = {32, (cuuint32_t)YP, (cuuint32_t)p.XH, 1, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.YP, (cuuint32_t)p.XH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.A), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -352,7 +355,7 @@ int e2_launch_conv_plane_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + (size_t)p.nslot * p.plane_bytes + (size_t)p.wslot * p.w_bytes + (4 * MAX_SLOTS + 4) * 8 + 16;
+  const size_t smem = 1024 + (size_t)p.nslot * p.plane_stride + (size_t)p.wslot * p.w_bytes + (4 * MAX_SLOTS + 4) * 8 + 16;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(k_conv_plane_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) !=

@@ -116,21 +116,22 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
+      const uint64_t desc_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
+      const uint32_t smA_addr = tc::smem_u32(smA), smB_addr = tc::smem_u32(smB);
       for (int it = 0; it < total; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
-        const uint32_t a_addr = tc::smem_u32(smA + s * A_STAGE_BYTES);
-        const uint32_t b_addr = tc::smem_u32(smB + s * b_stage_bytes);
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart; advancing K by
-          // 8 tf32 = 32 bytes inside the swizzle row is a plain start-address advance
-          const uint64_t ad = tc::make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-          const uint64_t bd = tc::make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-          tc::mma_tf32_ss(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
+        // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart; advancing K by
+        // 8 tf32 = 32 bytes inside the swizzle row is a plain start-address advance (+2 in the
+        // descriptor's 16-byte start-address field)
+        const uint64_t ad = desc_tmpl + (uint64_t)((smA_addr + (uint32_t)(s * A_STAGE_BYTES)) >> 4);
+        const uint64_t bd = desc_tmpl + (uint64_t)((smB_addr + (uint32_t)(s * b_stage_bytes)) >> 4);
+        tc::mma_tf32_ss(tmem_base, ad, bd, p.idesc, it > 0 ? 1u : 0u);
+        tc::mma_tf32_ss(tmem_base, ad + 2, bd + 2, p.idesc, 1u);
+        tc::mma_tf32_ss(tmem_base, ad + 4, bd + 4, p.idesc, 1u);
+        tc::mma_tf32_ss(tmem_base, ad + 6, bd + 6, p.idesc, 1u);
         tc::mma_commit(&empty[s]);   // frees the smem stage when these MMAs have read it
       }
       tc::mma_commit(acc_full);      // accumulator complete

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
     // -------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       int ait = 0;
+      const uint64_t desc_tmpl = tc::make_smem_desc(0, CHUNK_BYTES, 512, 1);
       for (int ti = 0; ti < ntiles; ++ti) {
         const int bs = ti % B_SLOTS;
         tc::mbar_wait(&b_full[bs], (uint32_t)(ti / B_SLOTS) & 1u);
@@ -146,14 +147,15 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
           tc::mbar_wait(&a_full[as], (uint32_t)(ait / p.a_slots) & 1u);
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(smA + as * A_BYTES);
+          // rows (positions) 128 B apart, swizzle period 4 rows = 512 B (SBO), 32-channel chunks
+          // CHUNK_BYTES apart (LBO); one MMA consumes K = 8 positions = 1024 B (+64 in the
+          // descriptor's 16-byte start-address field)
+          const uint64_t ad = desc_tmpl + (uint64_t)(a_addr >> 4);
+          const uint64_t bd = desc_tmpl + (uint64_t)(b_addr >> 4);
+          const uint32_t acc = tmem_base + (uint32_t)(g * p.n_cols);
 #pragma unroll
-          for (int k = 0; k < KP / 8; ++k) {
-            // rows (positions) 128 B apart, swizzle period 4 rows = 512 B (SBO), 32-channel chunks
-            // CHUNK_BYTES apart (LBO); one MMA consumes K = 8 positions = 1024 B
-            const uint64_t ad = tc::make_smem_desc(a_addr + k * 1024, CHUNK_BYTES, 512, 1);
-            const uint64_t bd = tc::make_smem_desc(b_addr + k * 1024, CHUNK_BYTES, 512, 1);
-            tc::mma_tf32_ss(tmem_base + (uint32_t)(g * p.n_cols), ad, bd, p.idesc, (ti > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < KP / 8; ++k)
+            tc::mma_tf32_ss(acc, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), p.idesc, (ti > 0 || k > 0) ? 1u : 0u);
           tc::mma_commit(&a_empty[as]);
         }
         tc::mma_commit(&b_empty[bs]);
