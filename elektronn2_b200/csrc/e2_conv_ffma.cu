@@ -541,7 +541,9 @@ extern "C" int e2_act_bwd(e2_handle* h, const e2_tensor* t, int32_t act, const f
 // ------------------------------------------------------------------- op front-ends
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s) {
   static const bool no_plane = getenv("E2_DISABLE_PLANE") != nullptr;   // A/B switch for profiling
+  static const bool no_zstack = getenv("E2_DISABLE_ZSTACK") != nullptr;
   if (compute == E2_COMPUTE_TF32) {
+    if (!no_zstack && e2_gather_gemm_tc_ok(h, g) && e2_conv_zstack_tc_ok(h, g)) return e2_launch_conv_zstack_tc(h, g, s);
     if (!no_plane && e2_gather_gemm_tc_ok(h, g) && e2_conv_plane_tc_ok(h, g)) return e2_launch_conv_plane_tc(h, g, s);
     if (e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
   }

@@ -46,7 +46,10 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // halo-reuse variant of the gather-GEMM (e2_conv_plane_tc.cu); preferred when it qualifies
 bool e2_conv_plane_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_conv_plane_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
-// picks plane kernel / tap kernel / CUDA cores for a TF32 request
+// halo planes + z-taps stacked along N (e2_conv_zstack_tc.cu); preferred over both when it qualifies
+bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g);
+int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+// picks zstack / plane kernel / tap kernel / CUDA cores for a TF32 request
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s);
 bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);

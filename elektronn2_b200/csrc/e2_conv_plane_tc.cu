@@ -134,56 +134,77 @@ __global__ void __launch_bounds__(PL_THREADS, 1) k_conv_plane_tc(const __grid_co
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
+    // All ring indices / parities are kept incrementally: no integer division in the hot loop.
     if (lane == 0) {
-      int pc0 = 0, wc = 0, tcount = 0;
       const uint32_t smP_addr = tc::smem_u32(smP), smW_addr = tc::smem_u32(smW);
       // K-major 128B-swizzle descriptor templates (start address added per MMA):
       // A: 8-row groups YP*128 B apart (shifted view into a halo plane); B: dense, 1024 B apart
       const uint64_t a_tmpl = tc::make_smem_desc(0, 16, (uint32_t)(p.YP * 128), 2);
       const uint64_t b_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
-        const int buf = tcount % p.acc_bufs;
-        tc::mbar_wait(&acc_empty[buf], ((uint32_t)(tcount / p.acc_bufs) & 1u) ^ 1u);
+      int pslot = 0;            // slot of plane 0 of the current unit
+      uint32_t ppar = 0;        // full-barrier parity of that slot
+      int ws = 0;
+      uint32_t wpar = 0;
+      int buf = 0;
+      uint32_t bpar = 1;        // acc_empty parity to wait for (first use passes)
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        tc::mbar_wait(&acc_empty[buf], bpar);
         tc::tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.TZ * p.BN);
-        for (int cb = 0; cb < p.CB; ++cb, pc0 += p.NP) {
+        for (int cb = 0; cb < p.CB; ++cb) {
+          // slot / parity / encoded address of every plane of this unit
+          uint32_t pl_enc[MAX_SLOTS], pl_par[MAX_SLOTS];
+          int pl_slot[MAX_SLOTS];
+          {
+            int s = pslot;
+            uint32_t par = ppar;
+#pragma unroll
+            for (int pl = 0; pl < MAX_SLOTS; ++pl) {
+              pl_slot[pl] = s, pl_par[pl] = par;
+              pl_enc[pl] = (smP_addr + (uint32_t)(s * p.plane_stride)) >> 4;
+              if (++s == p.nslot) s = 0, par ^= 1u;
+              if (pl + 1 == p.NP) pslot = s, ppar = par;   // first plane of the next unit
+            }
+          }
           uint32_t waited = 0;
           for (int i = 0; i < p.kz; ++i) {
-            for (int jk = 0; jk < T9; ++jk, ++wc) {
-              const int j = jk / p.ky, k = jk % p.ky;
-              const int ws = wc % p.wslot;
-              tc::mbar_wait(&w_full[ws], (uint32_t)(wc / p.wslot) & 1u);
+            int j = 0, k = 0;
+            for (int jk = 0; jk < T9; ++jk) {
+              tc::mbar_wait(&w_full[ws], wpar);
               const uint64_t bd0 = b_tmpl + (uint64_t)((smW_addr + (uint32_t)(ws * p.w_bytes)) >> 4);
-              const uint32_t row_off = (uint32_t)((j * p.YP + k) * 128);
+              const uint32_t row_enc = (uint32_t)((j * p.YP + k) * 8);      // (rows * 128 B) >> 4
               const uint32_t first = (cb == 0 && i == 0 && jk == 0) ? 0u : 1u;
-              for (int zl = 0; zl < p.TZ; ++zl) {
-                const int pl = zl + i;
-                const int pc = pc0 + pl;
-                const int s = pc % p.nslot;
-                if (!(waited & (1u << pl))) {
-                  tc::mbar_wait(&pl_full[s], (uint32_t)(pc / p.nslot) & 1u);
-                  waited |= 1u << pl;
+#pragma unroll
+              for (int zl = 0; zl < 4; ++zl) {
+                if (zl < p.TZ) {
+                  const int pl = zl + i;
+                  if (!(waited & (1u << pl))) {
+                    tc::mbar_wait(&pl_full[pl_slot[pl]], pl_par[pl]);
+                    waited |= 1u << pl;
+                  }
+                  tc::tc_fence_after();
+                  const uint64_t ad0 = a_tmpl + (uint64_t)(pl_enc[pl] + row_enc);
+                  const uint32_t acc = acc0 + (uint32_t)(zl * p.BN);
+                  tc::mma_tf32_ss(acc, ad0, bd0, p.idesc, first);
+                  tc::mma_tf32_ss(acc, ad0 + 2, bd0 + 2, p.idesc, 1u);
+                  tc::mma_tf32_ss(acc, ad0 + 4, bd0 + 4, p.idesc, 1u);
+                  tc::mma_tf32_ss(acc, ad0 + 6, bd0 + 6, p.idesc, 1u);
                 }
-                tc::tc_fence_after();
-                // descriptors differ only in the start-address field (low 14 bits, 16-byte units)
-                const uint64_t ad0 = a_tmpl + (uint64_t)((smP_addr + (uint32_t)(s * p.plane_stride) + row_off) >> 4);
-                const uint32_t acc = acc0 + (uint32_t)(zl * p.BN);
-                tc::mma_tf32_ss(acc, ad0, bd0, p.idesc, first);
-                tc::mma_tf32_ss(acc, ad0 + 2, bd0 + 2, p.idesc, 1u);
-                tc::mma_tf32_ss(acc, ad0 + 4, bd0 + 4, p.idesc, 1u);
-                tc::mma_tf32_ss(acc, ad0 + 6, bd0 + 6, p.idesc, 1u);
               }
               tc::mma_commit(&w_empty[ws]);
+              if (++ws == p.wslot) ws = 0, wpar ^= 1u;
+              if (++k == p.ky) k = 0, ++j;
             }
             // input planes whose last z-tap phase was i can go back to the producer
             if (i < p.kz - 1) {
-              tc::mma_commit(&pl_empty[(pc0 + i) % p.nslot]);
+              tc::mma_commit(&pl_empty[pl_slot[i]]);
             } else {
-              for (int pl = p.kz - 1; pl < p.NP; ++pl) tc::mma_commit(&pl_empty[(pc0 + pl) % p.nslot]);
+              for (int pl = p.kz - 1; pl < p.NP; ++pl) tc::mma_commit(&pl_empty[pl_slot[pl]]);
             }
           }
         }
         tc::mma_commit(&acc_full[buf]);
+        if (++buf == p.acc_bufs) buf = 0, bpar ^= 1u;
       }
     }
   } else if (warp >= 4) {

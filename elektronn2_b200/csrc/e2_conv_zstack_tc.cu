@@ -1,0 +1,502 @@
+// tcgen05 implicit-GEMM convolution, halo planes in shared memory, z-taps stacked along the MMA N axis.
+//
+// Why this shape (measured on B200 with scripts/mma_bench.cu): a kind::tf32 M128 x N x K8 MMA costs
+// max(48, N/2) cycles and at least ~55-85 cycles of issue work when every MMA needs fresh descriptors,
+// so MMAs with N = F_out = 64 cap the tensor pipe at <= 67 % (in practice ~35 %).  N >= 128 per MMA is
+// needed.  F_out of the big U-Net layers is 64, therefore N is widened with the filter's z-taps:
+//
+//   tile     = TZ output z-planes x (16 x-lines x 8 y) positions x BN output channels.  One TMEM
+//              accumulator block of [128 lanes x BN columns] per output plane, blocks in DESCENDING
+//              plane order (plane zl lives at column (TZ-1-zl)*BN).
+//   plane    = one TMA box of the input (32 channels, YP = 8+ky-1 y, XH = 16+kx-1 x, 1 z), rows of 128 B,
+//              128B-swizzled.  A tile needs NP = TZ+kz-1 input planes per 32-channel block.
+//   A view   = for an in-plane tap (j,k): 16 groups of 8 consecutive rows starting at row j*YP+k, groups
+//              YP rows apart -> a K-major UMMA descriptor with SBO = YP*128 B (the 128B swizzle is a
+//              function of the smem address bits, so any 128-B-row start works).
+//   B        = weights of ALL kz z-taps of in-plane tap (j,k), stacked [i][n] -> [kz*BN rows x 32 ch].
+//   MMA      = input plane q times the stacked weights gives, in one instruction, the contributions of
+//              plane q to output planes q, q-1, ..., q-kz+1 (z-tap i = q - zl): D = accumulator blocks of
+//              those planes (contiguous because of the descending order), N = (#planes)*BN, B rows start
+//              at block i_lo.  For kz = 3, BN = 64: N = 192 -> 96 cycles per MMA = full tensor rate, and
+//              6 MMA groups per (j,k) instead of 12.
+//   schedule = channel block -> in-plane tap (j,k) -> input plane q.  All NP planes of a unit stay
+//              resident; the weight block of (cb, j, k) is streamed once per unit (2-stage ring).
+//   roles    = warp 0 plane TMA, warp 1 MMA issuer (whole warp runs the loop with uniform values so the
+//              descriptor arithmetic stays in uniform registers; one elected lane issues), warp 2 weight
+//              TMA (+TMEM alloc), warps 4-7 epilogue.  Persistent CTAs, double-buffered accumulators.
+#include <algorithm>
+#include <stdlib.h>
+#include "e2_common.cuh"
+#include "e2_conv_internal.cuh"
+#include "e2_tc_ptx.cuh"
+
+namespace {
+
+constexpr int TX = 16, TY = 8;   // tile x/y extent (16 groups of 8 rows = 128 MMA rows)
+constexpr int ZS_THREADS = 256;
+constexpr int MAX_PSLOTS = 12;
+constexpr int MAX_WSLOTS = 4;
+
+struct ZsParams {
+  int On, Oz, Ox, Oy;
+  int ntz, ntx, nty, ntn;     // tiles per axis, N tiles
+  int TZ, NP, XH, YP;
+  int kz, kx, ky, oz, ox, oy;
+  int K, N, BN, CB;
+  int nslot, wslot, acc_bufs;
+  int plane_bytes, plane_stride, w_bytes, wblk_bytes;
+  int tmem_cols;
+  int num_tiles;
+  float* C;
+  int c_pitch;
+  const float* bias;
+  const float* gate;
+  int act, accumulate, round_tf32;
+  uint32_t idesc0, idesc_step;   // idesc for N = nblk*BN is idesc0 + nblk*idesc_step
+  int epi_off;                   // byte offset of the epilogue staging area (1024-aligned)
+};
+
+// lean bounded wait for the issuing warp (all lanes poll; try_wait suspends in hardware)
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!tc::mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 24)) {
+      printf("e2b200: zstack mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mma4(uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t first_acc) {
+  tc::mma_tf32_ss(acc, ad, bd, idesc, first_acc);
+  tc::mma_tf32_ss(acc, ad + 2, bd + 2, idesc, 1u);
+  tc::mma_tf32_ss(acc, ad + 4, bd + 4, idesc, 1u);
+  tc::mma_tf32_ss(acc, ad + 6, bd + 6, idesc, 1u);
+}
+
+__global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmC,
+                                                                  const __grid_constant__ CUtensorMap tmG,
+                                                                  const ZsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smP = smem;                                   // plane slots
+  uint8_t* smW = smem + p.nslot * p.plane_stride;        // weight ring
+  uint8_t* smE = smem + p.epi_off;                       // epilogue: per warp 4 KB staging + 4 KB aux, then bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + 4 * 8192 + 4 * p.BN * 4);
+  uint64_t* pl_full = bars;
+  uint64_t* pl_empty = pl_full + MAX_PSLOTS;
+  uint64_t* w_full = pl_empty + MAX_PSLOTS;
+  uint64_t* w_empty = w_full + MAX_WSLOTS;
+  uint64_t* acc_full = w_empty + MAX_WSLOTS;             // [2]
+  uint64_t* acc_empty = acc_full + 2;                    // [2]
+  uint64_t* aux_bar = acc_empty + 2;                     // [4] one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    tc::prefetch_tmap(&tmC);
+    if (p.gate) tc::prefetch_tmap(&tmG);
+    for (int i = 0; i < p.nslot; ++i) tc::mbar_init(&pl_full[i], 1), tc::mbar_init(&pl_empty[i], 1);
+    for (int i = 0; i < p.wslot; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 4);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&aux_bar[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T9 = p.kx * p.ky;
+
+  auto tile_coords = [&](int t, int& in_, int& z0, int& x0, int& y0, int& n0) {
+    const int nt = t % p.ntn;
+    t /= p.ntn;
+    const int ity = t % p.nty;
+    t /= p.nty;
+    const int itx = t % p.ntx;
+    t /= p.ntx;
+    const int itz = t % p.ntz;
+    in_ = t / p.ntz;
+    z0 = itz * p.TZ, x0 = itx * TX, y0 = ity * TY, n0 = nt * p.BN;
+  };
+
+  if (warp == 0) {
+    // ----------------------------------------------------------- plane producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 1;   // parity to wait for on pl_empty (first round passes)
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int in_, z0, x0, y0, n0;
+        tile_coords(t, in_, z0, x0, y0, n0);
+        for (int cb = 0; cb < p.CB; ++cb)
+          for (int pl = 0; pl < p.NP; ++pl) {
+            tc::mbar_wait(&pl_empty[s], par);
+            tc::mbar_arrive_expect_tx(&pl_full[s], (uint32_t)p.plane_bytes);
+            tc::tma_load_5d(smP + s * p.plane_stride, &tmA, &pl_full[s], cb * 32, y0 + p.oy, x0 + p.ox,
+                            z0 + p.oz + pl, in_);
+            if (++s == p.nslot) s = 0, par ^= 1u;
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------- weight producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t par = 1;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int in_, z0, x0, y0, n0;
+        tile_coords(t, in_, z0, x0, y0, n0);
+        for (int cb = 0; cb < p.CB; ++cb)
+          for (int jk = 0; jk < T9; ++jk) {
+            tc::mbar_wait(&w_empty[s], par);
+            tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)p.w_bytes);
+            for (int i = 0; i < p.kz; ++i)
+              tc::tma_load_3d(smW + s * p.w_bytes + i * p.wblk_bytes, &tmB, &w_full[s], cb * 32, i * T9 + jk, n0);
+            if (++s == p.wslot) s = 0, par ^= 1u;
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    // Executed by all 32 lanes with warp-uniform values; only the tcgen05 instructions are predicated
+    // on the elected lane.  Ring indices / parities are kept incrementally (no division in the loop).
+    const uint32_t smP_enc = tc::smem_u32(smP) >> 4, smW_enc = tc::smem_u32(smW) >> 4;
+    const uint32_t pstride_enc = (uint32_t)p.plane_stride >> 4, w_enc = (uint32_t)p.w_bytes >> 4;
+    const uint32_t wblk_enc = (uint32_t)p.wblk_bytes >> 4;
+    const uint64_t a_tmpl = tc::make_smem_desc(0, 16, (uint32_t)(p.YP * 128), 2);
+    const uint64_t b_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
+    const int kz1 = p.kz - 1;
+    int pslot = 0;
+    uint32_t ppar = 0;
+    int ws = 0;
+    uint32_t wpar = 0;
+    int buf = 0;
+    uint32_t bpar = 1;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      wait_bar(&acc_empty[buf], bpar);
+      tc::tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.TZ * p.BN);
+      for (int cb = 0; cb < p.CB; ++cb) {
+        int j = 0, k = 0;
+        int s_end = pslot;
+        uint32_t par_end = ppar;
+        for (int jk = 0; jk < T9; ++jk) {
+          wait_bar(&w_full[ws], wpar);
+          tc::tc_fence_after();
+          const uint64_t bd0 = b_tmpl + (uint64_t)(smW_enc + (uint32_t)ws * w_enc);
+          const uint32_t row_enc = (uint32_t)((j * p.YP + k) * 8);      // (rows * 128 B) >> 4
+          const bool first_stage = (cb == 0 && jk == 0);
+          const bool last_stage = (jk == T9 - 1);
+          int s = pslot;
+          uint32_t par = ppar;
+          for (int q = 0; q < p.NP; ++q) {
+            if (jk == 0) {
+              wait_bar(&pl_full[s], par);
+              tc::tc_fence_after();
+            }
+            const int zl_hi = min(q, p.TZ - 1), zl_lo = max(0, q - kz1);
+            const int i_lo = q - zl_hi, nblk = zl_hi - zl_lo + 1;
+            const uint64_t ad = a_tmpl + (uint64_t)(smP_enc + (uint32_t)s * pstride_enc + row_enc);
+            const uint64_t bd = bd0 + (uint64_t)((uint32_t)i_lo * wblk_enc);
+            const uint32_t dcol = acc0 + (uint32_t)((p.TZ - 1 - zl_hi) * p.BN);
+            if (tc::elect_one()) {
+              if (first_stage && q < p.TZ) {
+                // output plane q is touched for the first time (z-tap 0 = block i_lo = 0): overwrite
+                mma4(dcol, ad, bd, p.idesc0 + p.idesc_step, 0u);
+                if (nblk > 1) mma4(dcol + (uint32_t)p.BN, ad, bd + wblk_enc, p.idesc0 + (uint32_t)(nblk - 1) * p.idesc_step, 1u);
+              } else {
+                mma4(dcol, ad, bd, p.idesc0 + (uint32_t)nblk * p.idesc_step, 1u);
+              }
+              if (last_stage) tc::mma_commit(&pl_empty[s]);   // plane slot free once these MMAs have read it
+            }
+            __syncwarp();
+            if (++s == p.nslot) s = 0, par ^= 1u;
+          }
+          s_end = s, par_end = par;
+          if (tc::elect_one()) tc::mma_commit(&w_empty[ws]);
+          __syncwarp();
+          if (++ws == p.wslot) ws = 0, wpar ^= 1u;
+          if (++k == p.ky) k = 0, ++j;
+        }
+        pslot = s_end, ppar = par_end;
+      }
+      if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
+      __syncwarp();
+      if (++buf == p.acc_bufs) buf = 0, bpar ^= 1u;
+    }
+  } else if (warp >= 4) {
+    // ----------------------------------------------------------------- epilogue
+    // Warp q owns TMEM lanes 32q..32q+31 = x-lines 4q..4q+3 of the tile.  Per output plane and 32-column
+    // chunk: tcgen05.ld -> +bias -> act -> (gate / accumulate from a TMA-loaded aux tile) -> tf32 round ->
+    // swizzled st.shared -> ONE TMA store of the [32 ch x 8 y x 4 x] box.  No per-thread global stores:
+    // with ~220 KB of shared memory in use the L1 is gone and scattered 16-byte STGs ran at ~300 GB/s.
+    const int q = warp & 3;
+    uint8_t* stage = smE + q * 8192;
+    uint8_t* aux = stage + 4096;
+    float* bias_w = reinterpret_cast<float*>(smE + 4 * 8192) + q * p.BN;
+    uint64_t* abar = &aux_bar[q];
+    uint32_t apar = 0;
+    const int r8 = lane & 7;
+    int buf = 0;
+    uint32_t fpar = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int in_, z0, x0, y0, n0;
+      tile_coords(t, in_, z0, x0, y0, n0);
+      for (int i = lane; i < p.BN; i += 32) bias_w[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      __syncwarp();
+      tc::mbar_wait(&acc_full[buf], fpar);
+      tc::tc_fence_after();
+      for (int zl = 0; zl < p.TZ; ++zl) {
+        const uint32_t acc = tmem_base + (uint32_t)((buf * p.TZ + (p.TZ - 1 - zl)) * p.BN) + ((uint32_t)(q * 32) << 16);
+        if (z0 + zl >= p.Oz) break;                       // uniform: whole plane outside the tensor
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;                      // uniform: chunk entirely past the last channel
+          const bool has_aux = p.gate || p.accumulate;
+          if (has_aux && lane == 0) {
+            tc::mbar_arrive_expect_tx(abar, 4096u);
+            tc::tma_load_5d(aux, p.gate ? &tmG : &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+          }
+          uint32_t r[32];
+          if (p.BN - c0 >= 32) {
+            tc::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+          } else {
+            tc::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
+#pragma unroll
+            for (int jj = 16; jj < 32; ++jj) r[jj] = 0u;
+          }
+          tc::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + j4 < p.BN) b4 = *reinterpret_cast<const float4*>(bias_w + c0 + j4);
+            v[j4 + 0] = e2_apply_act(__uint_as_float(r[j4 + 0]) + b4.x, p.act);
+            v[j4 + 1] = e2_apply_act(__uint_as_float(r[j4 + 1]) + b4.y, p.act);
+            v[j4 + 2] = e2_apply_act(__uint_as_float(r[j4 + 2]) + b4.z, p.act);
+            v[j4 + 3] = e2_apply_act(__uint_as_float(r[j4 + 3]) + b4.w, p.act);
+          }
+          if (has_aux) {
+            tc::mbar_wait(abar, apar);
+            apar ^= 1u;
+            if (p.gate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 g4 = *reinterpret_cast<const float4*>(aux + lane * 128 + ((j ^ r8) << 4));
+                if (!(g4.x > 0.f)) v[4 * j + 0] = 0.f;
+                if (!(g4.y > 0.f)) v[4 * j + 1] = 0.f;
+                if (!(g4.z > 0.f)) v[4 * j + 2] = 0.f;
+                if (!(g4.w > 0.f)) v[4 * j + 3] = 0.f;
+              }
+              if (p.accumulate) {      // rare: both -> second aux load of the destination tile
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  tc::mbar_arrive_expect_tx(abar, 4096u);
+                  tc::tma_load_5d(aux, &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+                }
+                tc::mbar_wait(abar, apar);
+                apar ^= 1u;
+              }
+            }
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 c4 = *reinterpret_cast<const float4*>(aux + lane * 128 + ((j ^ r8) << 4));
+                v[4 * j + 0] += c4.x, v[4 * j + 1] += c4.y, v[4 * j + 2] += c4.z, v[4 * j + 3] += c4.w;
+              }
+            }
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
+          }
+          // the previous TMA store must have finished reading the staging buffer
+          if (lane == 0) tc::bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ r8) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tc::tma_store_5d(&tmC, stage, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+            tc::bulk_commit();
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the buffer back
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+      if (++buf == p.acc_bufs) buf = 0, fpar ^= 1u;
+    }
+    if (lane == 0) tc::bulk_wait0();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+// Decide whether the kernel applies and is worthwhile for this problem; fill the geometry.
+static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
+  if (g.sz != 1 || g.sx != 1 || g.sy != 1 || g.shuffle) return false;
+  if (g.ty > 9 || g.tx > 9 || g.tz > 4) return false;
+  const int T = g.tz * g.tx * g.ty;
+  if (T < 2) return false;                       // 1x1x1: nothing to reuse, the tap kernel is fine
+  if (g.Ox < 12 || g.Oy < 6) return false;       // tile quantisation would waste too much
+  memset(p, 0, sizeof(*p));
+  const int S = g.tz;
+  p->XH = TX + g.tx - 1;
+  p->YP = TY + g.ty - 1;
+  p->plane_bytes = p->XH * p->YP * 128;
+  p->plane_stride = (p->plane_bytes + 1023) / 1024 * 1024;   // slots stay 1024-B aligned (swizzle period)
+  // N tile: multiple of 16 with S*BN <= 256; minimise the padded width, prefer wide tiles
+  const int bn_max = (256 / S) / 16 * 16;
+  int bn = 0, ntn = 0;
+  double bn_cost = 0;
+  for (int b = bn_max; b >= 16; b -= 16) {
+    const int n = (g.N + b - 1) / b;
+    if (n > 1 && (b % 32)) continue;   // the epilogue stores 32-channel boxes: inner N tiles must be whole boxes
+    const double c = n * std::max(56.0, S * b / 2.0);   // cycles per K step of a full-span MMA, all N tiles
+    if (bn == 0 || c < bn_cost) bn = b, ntn = n, bn_cost = c;
+  }
+  p->BN = bn, p->ntn = ntn;
+  p->wblk_bytes = bn * 128;
+  p->w_bytes = S * bn * 128;
+  if (g.c_pitch % 4 || (reinterpret_cast<uintptr_t>(g.C) & 15) || (reinterpret_cast<uintptr_t>(g.gate) & 15)) return false;
+  const int epi_bytes = 4 * 8192 + 4 * bn * 4;  // per epilogue warp: 4 KB staging + 4 KB aux; bias copies
+  const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;   // alignment slack + barriers + epilogue
+  // TZ: as many output planes as TMEM (double-buffered) and shared memory allow; among those, the one
+  // with the least z-quantisation / wave-quantisation waste
+  const int ntx = (g.Ox + TX - 1) / TX, nty = (g.Oy + TY - 1) / TY;
+  int best_tz = 0;
+  double best_cost = 0;
+  for (int tz = 8; tz >= 1; --tz) {
+    if (2 * tz * bn > 512) continue;
+    const int np = tz + S - 1;
+    if (np > MAX_PSLOTS) continue;
+    if (np * p->plane_stride + 2 * p->w_bytes > budget) continue;
+    const int ntz = (g.Oz + tz - 1) / tz;
+    const int64_t tiles = (int64_t)g.On * ntz * ntx * nty * ntn;
+    const int64_t waves = (tiles + h->sm_count - 1) / h->sm_count;
+    // per-tile time ~ MMA cycles of the planes (np groups; edge groups are narrower) + fixed overhead
+    double mma = 0;
+    for (int q = 0; q < np; ++q) {
+      const int nblk = std::min(q, tz - 1) - std::max(0, q - (S - 1)) + 1;
+      mma += std::max(50.0, nblk * bn / 2.0);
+    }
+    const double cost = (double)waves * (mma + 30.0);
+    if (best_tz == 0 || cost < best_cost * 0.97) best_tz = tz, best_cost = cost;
+  }
+  if (best_tz == 0) return false;
+  p->TZ = best_tz;
+  p->NP = best_tz + S - 1;
+  int rest = budget - p->NP * p->plane_stride - 2 * p->w_bytes;
+  p->nslot = p->NP;
+  p->wslot = 2;
+  // spare memory: one extra plane slot first (prefetch across unit boundaries), then weight slots, then planes
+  if (p->nslot < MAX_PSLOTS && rest >= p->plane_stride) p->nslot++, rest -= p->plane_stride;
+  if (rest >= p->w_bytes) p->wslot++, rest -= p->w_bytes;
+  while (p->nslot < MAX_PSLOTS && p->nslot < 2 * p->NP && rest >= p->plane_stride) p->nslot++, rest -= p->plane_stride;
+  p->acc_bufs = 2;
+  int cols = 32;
+  while (cols < p->acc_bufs * p->TZ * bn) cols *= 2;
+  p->tmem_cols = cols;
+  p->On = g.On, p->Oz = g.Oz, p->Ox = g.Ox, p->Oy = g.Oy;
+  p->ntz = (g.Oz + p->TZ - 1) / p->TZ, p->ntx = ntx, p->nty = nty;
+  p->kz = g.tz, p->kx = g.tx, p->ky = g.ty, p->oz = g.oz, p->ox = g.ox, p->oy = g.oy;
+  p->K = g.K, p->N = g.N, p->CB = (g.K + 31) / 32;
+  p->num_tiles = p->On * p->ntz * p->ntx * p->nty * p->ntn;
+  p->epi_off = (p->nslot * p->plane_stride + p->wslot * p->w_bytes + 1023) / 1024 * 1024;
+  // tile-quantisation efficiency: useful outputs / computed outputs
+  const double eff = (double)g.Oz * g.Ox * g.Oy * g.N /
+                     ((double)p->ntz * p->TZ * p->ntx * TX * p->nty * TY * p->ntn * bn);
+  if (eff < 0.5) return false;
+  return true;
+}
+
+bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g) {
+  ZsParams p;
+  return plan_zstack(h, g, &p);
+}
+
+int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
+  EncodeTiledFn enc = e2_get_tmap_encode();
+  if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
+  ZsParams p;
+  if (!plan_zstack(h, g, &p)) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: problem does not qualify");
+  p.C = g.C, p.c_pitch = g.c_pitch, p.bias = g.bias, p.gate = g.gate;
+  p.act = g.act, p.accumulate = g.accumulate, p.round_tf32 = g.round_tf32;
+  p.idesc0 = tc::make_idesc(2 /*TF32*/, 0, 0, 128, 0);
+  p.idesc_step = (uint32_t)(p.BN >> 3) << 17;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)g.K, (cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
+    cuuint64_t pitch = (cuuint64_t)g.a_pitch * 4;
+    cuuint64_t strides[4] = {pitch, pitch * g.Ay, pitch * g.Ay * g.Ax, pitch * g.Ay * g.Ax * g.Az};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.YP, (cuuint32_t)p.XH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.A), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(plane) failed: %d", (int)r);
+  }
+  {
+    const int T = g.tz * g.tx * g.ty;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)T, (cuuint64_t)g.N};
+    cuuint64_t strides[2] = {(cuuint64_t)g.b_tap * 4, (cuuint64_t)g.b_row * 4};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)p.BN};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.B), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+  }
+  // C (and the gate, same geometry) as 32-channel x 8 y x 4 x boxes for the epilogue's TMA store / aux loads
+  CUtensorMap tmC, tmG;
+  for (int which = 0; which < 2; ++which) {
+    const float* base = which == 0 ? g.C : g.gate;
+    if (!base) {
+      tmG = tmC;
+      continue;
+    }
+    cuuint64_t dims[5] = {(cuuint64_t)g.N, (cuuint64_t)g.Oy, (cuuint64_t)g.Ox, (cuuint64_t)g.Oz, (cuuint64_t)g.On};
+    cuuint64_t pitch = (cuuint64_t)g.c_pitch * 4;
+    cuuint64_t strides[4] = {pitch, pitch * g.Oy, pitch * g.Oy * g.Ox, pitch * g.Oy * g.Ox * g.Oz};
+    cuuint32_t box[5] = {32, 8, 4, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(which == 0 ? &tmC : &tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides,
+                     box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+  }
+  const size_t smem = 1024 + (size_t)p.epi_off + 4 * 8192 + 4 * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 8) * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_conv_zstack_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) !=
+        cudaSuccess)
+      return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
+    configured = true;
+  }
+  if (smem > 227 * 1024) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: shared memory plan exceeds 227 KB");
+  const int grid = std::min(p.num_tiles, h->sm_count);
+  k_conv_zstack_tc<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, tmC, tmG, p);
+  h->launches++;
+  E2_CUDA_CHECK(h, "conv_zstack_tc");
+  return E2_OK;
+}
