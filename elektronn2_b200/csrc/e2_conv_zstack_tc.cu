@@ -279,10 +279,18 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
           for (int j4 = 0; j4 < 32; j4 += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c0 + j4 < p.BN) b4 = *reinterpret_cast<const float4*>(bias_w + c0 + j4);
-            v[j4 + 0] = e2_apply_act(__uint_as_float(r[j4 + 0]) + b4.x, p.act);
-            v[j4 + 1] = e2_apply_act(__uint_as_float(r[j4 + 1]) + b4.y, p.act);
-            v[j4 + 2] = e2_apply_act(__uint_as_float(r[j4 + 2]) + b4.z, p.act);
-            v[j4 + 3] = e2_apply_act(__uint_as_float(r[j4 + 3]) + b4.w, p.act);
+            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + b4.x;
+            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + b4.y;
+            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + b4.z;
+            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + b4.w;
+          }
+          // one (uniform) branch per chunk, not one switch per value
+          if (p.act == E2_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act != E2_ACT_LIN) {
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) v[j] = e2_apply_act(v[j], p.act);
           }
           if (has_aux) {
             tc::mbar_wait(abar, apar);
