@@ -582,7 +582,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   GatherGemm g;
   conv_fwd_problem(d, x, wf, bias, y, &g);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->x.c == 1) return e2_launch_conv_c1_fwd(h, g, s);
+  if (d->x.c == 1) return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
@@ -624,8 +624,12 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   g.sz = g.sx = g.sy = 1;
   g.W = dw, g.out_mode = 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
+  if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
+    rc = e2_launch_conv_c1_wgrad_line(h, g, s);
+  else if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
     rc = e2_launch_conv_c1_wgrad(h, g, s);
+  else if (d->compute == E2_COMPUTE_TF32 && e2_wgrad_halo_tc_ok(h, g))
+    rc = e2_launch_wgrad_halo_tc(h, g, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))
     rc = e2_launch_reduce_gemm_tc(h, g, s);
   else

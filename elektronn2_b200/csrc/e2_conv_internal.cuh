@@ -38,6 +38,11 @@ int e2_launch_gather_gemm_ffma(e2_handle* h, const GatherGemm& g, cudaStream_t s
 int e2_launch_reduce_gemm_ffma(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
 int e2_launch_conv_c1_fwd(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 int e2_launch_conv_c1_wgrad(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+// line-staged first-layer kernels (e2_conv_c1.cu); preferred when they qualify
+bool e2_conv_c1_fwd_line_ok(const GatherGemm& g);
+int e2_launch_conv_c1_fwd_line(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+bool e2_conv_c1_wgrad_line_ok(const ReduceGemm& g);
+int e2_launch_conv_c1_wgrad_line(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
 int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pitch, float* db, cudaStream_t s);
 
 // tcgen05 path (e2_conv_tc.cu)
@@ -53,3 +58,6 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s);
 bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+// halo-reuse wgrad (e2_wgrad_halo_tc.cu): x tile loaded once, taps are shifted descriptor views
+bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g);
+int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
