@@ -153,6 +153,7 @@ class Handle(object):
         if rc != OK:
             raise E2Error(rc, "e2_create(device=%d) failed" % self.device)
         self._h = h
+        self._ws, self._ws_old = None, []     # caller-owned scratch shared by all ops of this handle's stream
         msg = lib.e2_last_error(self._h)
         if msg:
             raise E2Error(ERR_UNSUPPORTED, msg.decode())
@@ -160,6 +161,22 @@ class Handle(object):
     def stream(self):
         import torch
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reserve_workspace(self, nbytes):
+        """Grow the shared scratch buffer (e2_*_workspace_size).  Old buffers stay alive: a captured
+        CUDA graph may still reference them."""
+        import torch
+        nbytes = int(nbytes)
+        if nbytes and (self._ws is None or self._ws.numel() < nbytes):
+            if self._ws is not None:
+                self._ws_old.append(self._ws)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda:%d' % self.device)
+
+    def workspace(self):
+        """(void* ws, size_t ws_bytes) for the entry points that take a workspace."""
+        if self._ws is None:
+            return None, 0
+        return C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel())
 
     def call(self, name, *args):
         rc = getattr(lib, name)(self._h, *args)

@@ -568,9 +568,34 @@ static void conv_fwd_problem(const e2_conv_desc* d, const float* x, const float*
   g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
 }
 
+static void conv_wgrad_problem(const e2_conv_desc* d, const float* x, const float* dy, float* dw, ReduceGemm* gp) {
+  ReduceGemm& g = *gp;
+  memset(&g, 0, sizeof(g));
+  g.P = dy, g.p_pitch = d->y.c_pitch, g.R = d->y.c;
+  g.Mn = d->y.n, g.Mz = d->y.z, g.Mx = d->y.x, g.My = d->y.y;
+  g.Q = x, g.q_pitch = d->x.c_pitch, g.S = d->x.c;
+  g.Qn = d->x.n, g.Qz = d->x.z, g.Qx = d->x.x, g.Qy = d->x.y;
+  g.tz = d->kz, g.tx = d->kx, g.ty = d->ky;
+  g.sz = g.sx = g.sy = 1;
+  g.W = dw, g.out_mode = 0;
+}
+
 extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
   if (!d || !bytes) return E2_ERR_INVALID;
   *bytes = 0;
+  // only the tcgen05 wgrad uses a workspace (per-CTA partial weight tiles, summed by a second kernel)
+  if (d->compute == E2_COMPUTE_TF32 && d->x.c > 1) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        sm_count = 148;
+    }
+    ReduceGemm g;
+    alignas(16) static float dummy[4];
+    conv_wgrad_problem(d, dummy, dummy, dummy, &g);
+    if (e2_wgrad_halo_tc_ok(nullptr, g)) *bytes = e2_wgrad_halo_workspace_bytes(sm_count, g);
+  }
   return E2_OK;
 }
 
@@ -615,21 +640,14 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   if (rc) return rc;
   E2_REQUIRE(h, x && dy && dw, "conv3d_wgrad: null pointer");
   ReduceGemm g;
-  memset(&g, 0, sizeof(g));
-  g.P = dy, g.p_pitch = d->y.c_pitch, g.R = d->y.c;
-  g.Mn = d->y.n, g.Mz = d->y.z, g.Mx = d->y.x, g.My = d->y.y;
-  g.Q = x, g.q_pitch = d->x.c_pitch, g.S = d->x.c;
-  g.Qn = d->x.n, g.Qz = d->x.z, g.Qx = d->x.x, g.Qy = d->x.y;
-  g.tz = d->kz, g.tx = d->kx, g.ty = d->ky;
-  g.sz = g.sx = g.sy = 1;
-  g.W = dw, g.out_mode = 0;
+  conv_wgrad_problem(d, x, dy, dw, &g);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
     rc = e2_launch_conv_c1_wgrad_line(h, g, s);
   else if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
     rc = e2_launch_conv_c1_wgrad(h, g, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_wgrad_halo_tc_ok(h, g))
-    rc = e2_launch_wgrad_halo_tc(h, g, s);
+    rc = e2_launch_wgrad_halo_tc(h, g, ws, ws_bytes, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))
     rc = e2_launch_reduce_gemm_tc(h, g, s);
   else

@@ -60,4 +60,5 @@ bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
 // halo-reuse wgrad (e2_wgrad_halo_tc.cu): x tile loaded once, taps are shifted descriptor views
 bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g);
-int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t e2_wgrad_halo_workspace_bytes(int sm_count, const ReduceGemm& g);

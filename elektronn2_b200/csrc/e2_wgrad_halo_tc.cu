@@ -43,8 +43,10 @@ struct WhParams {
   int tmem_cols;
   int tiles_total, tiles_per_split;
   float* W;
+  float* ws;   // partial-sum workspace [cta][acc][col/4][lane][4]; NULL: fp32 atomics straight into W
   int out_mode;
   uint32_t idesc;
+  int dbg;   // bit 0: skip the TMA loads, bit 1: skip the MMAs (E2_WGRAD_DBG, bottleneck experiments only)
 };
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
@@ -57,6 +59,8 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// KX_ / KG_: compile-time x-tap count and y-tap groups (0: run-time values from the parameters)
+template <int KX_, int KG_>
 __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_constant__ CUtensorMap tmP,
                                                               const __grid_constant__ CUtensorMap tmQ,
                                                               const WhParams p) {
@@ -112,6 +116,11 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
         const int in_ = t / p.ntz;
         const int z0 = itz * p.TZ, x0 = itx * p.TX, y0 = ity * TY;
         tc::mbar_wait(&empty[s], par);
+        if (p.dbg & 1) {
+          tc::mbar_arrive(&full[s]);
+          if (++s == p.stages) s = 0, par ^= 1u;
+          continue;
+        }
         tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(p.dy_bytes + p.x_bytes));
         uint8_t* st = smem + s * p.stage_bytes;
         tc::tma_load_5d(st, &tmQ, &full[s], s0, y0 + p.oy, x0 + p.ox, z0 + i3 + p.oz, in_);
@@ -122,40 +131,49 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    // whole warp runs the loop with uniform values; one elected lane issues
+    // whole warp walks the tile ring; per tile ONE elected lane issues all MMAs from an unrolled body whose
+    // descriptors advance by constants (uniform registers only, ~3 instructions per MMA)
+    const int KX = KX_ ? KX_ : p.kx, KG = KX_ ? KG_ : p.kgroups;
     const uint64_t a_tmpl = tc::make_smem_desc(0, 128, 512, 1);
     const uint64_t b_tmpl = tc::make_smem_desc(0, (uint32_t)p.dy_chunk_bytes, 512, 1);
     const uint32_t smem_enc = tc::smem_u32(smem) >> 4;
     const uint32_t stage_enc = (uint32_t)p.stage_bytes >> 4, xs_enc = (uint32_t)p.x_stride >> 4;
     const uint32_t yp_enc = (uint32_t)p.YP * 8;   // one halo x-line = YP rows of 128 B, >> 4
+    const uint32_t zskip_enc = (uint32_t)(p.kx - 1) * yp_enc;   // from the last line of a z-plane to the next plane
+    const uint32_t ncols = (uint32_t)p.n_cols;
+    const uint32_t idesc = p.idesc;
     int s = 0;
     uint32_t par = 0;
+    uint32_t accf = 0u;
     for (int ti = 0; ti < ntiles; ++ti) {
       wait_bar(&full[s], par);
       tc::tc_fence_after();
-      const uint32_t a0 = smem_enc + (uint32_t)s * stage_enc;
-      uint32_t bd_enc = a0 + xs_enc;
-      for (int z = 0; z < p.TZ; ++z) {
-        uint32_t line_enc = a0 + (uint32_t)(z * p.XP) * yp_enc;
-        for (int x = 0; x < p.TX; ++x) {
-          const uint64_t bd = b_tmpl + (uint64_t)bd_enc;
-          const uint32_t accf = (ti > 0 || z > 0 || x > 0) ? 1u : 0u;
-          uint32_t acc = tmem_base;
-          uint32_t aj = line_enc;
-          for (int j = 0; j < p.kx; ++j) {
-            for (int kg = 0; kg < p.kgroups; ++kg) {
-              const uint64_t ad = a_tmpl + (uint64_t)(aj + (uint32_t)kg * 32u);   // 4 rows = 512 B
-              if (tc::elect_one()) tc::mma_tf32_ss(acc, ad, bd, p.idesc, accf);
-              acc += (uint32_t)p.n_cols;
+      if (!(p.dbg & 2) && tc::elect_one()) {
+        const uint32_t a0 = smem_enc + (uint32_t)s * stage_enc;
+        uint64_t bd = b_tmpl + (uint64_t)(a0 + xs_enc);
+        uint64_t ad0 = a_tmpl + (uint64_t)a0;
+        for (int z = 0; z < p.TZ; ++z) {
+          for (int x = 0; x < p.TX; ++x) {
+            uint32_t acc = tmem_base;
+            uint64_t adj = ad0;
+#pragma unroll
+            for (int j = 0; j < KX; ++j) {
+#pragma unroll
+              for (int kg = 0; kg < KG; ++kg) {
+                tc::mma_tf32_ss(acc, adj + (uint64_t)(kg * 32), bd, idesc, accf);   // y-tap group: 4 rows = 512 B
+                acc += ncols;
+              }
+              adj += yp_enc;
             }
-            aj += yp_enc;
+            accf = 1u;
+            bd += 64;          // next dy line: 8 rows = 1024 B
+            ad0 += yp_enc;
           }
-          __syncwarp();
-          bd_enc += 64;          // next dy line: 8 rows = 1024 B
-          line_enc += yp_enc;
+          ad0 += zskip_enc;
         }
+        tc::mma_commit(&empty[s]);
       }
-      if (tc::elect_one()) tc::mma_commit(&empty[s]);
+      accf = 1u;
       __syncwarp();
       if (++s == p.stages) s = 0, par ^= 1u;
     }
@@ -168,7 +186,27 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
     const int s = s0 + lane;                        // TMEM lane = (chunk q = y-tap within group, s)
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
-    if (ntiles > 0) {
+    if (p.ws) {
+      // partial sums of this CTA -> workspace, one coalesced float4 per lane and 4 columns
+      float4* dst = reinterpret_cast<float4*>(p.ws) +
+                    (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * p.n_acc * (p.n_cols / 4) * 128 + q * 32 + lane;
+      for (int a = 0; a < p.n_acc; ++a) {
+        for (int c0 = 0; c0 < p.n_cols; c0 += 16) {
+          uint32_t v[16];
+          tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_cols + c0), v);
+          tc::tmem_ld_wait();
+          if (ntiles == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[(size_t)(a * (p.n_cols / 4) + c0 / 4 + j) * 128] =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    } else if (ntiles > 0) {
       for (int a = 0; a < p.n_acc; ++a) {
         const int j3 = a / p.kgroups, kg = a % p.kgroups;
         const int k3 = kg * 4 + q;
@@ -197,6 +235,53 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// Sum the per-CTA partial tiles over the position splits and scatter into the reference weight layout.
+// One thread per (unit, accumulator, 4 columns, lane); reads are coalesced float4, every dw element is
+// written exactly once (no memset, no atomics, deterministic).
+__global__ void __launch_bounds__(128) k_wgrad_halo_reduce(const WhParams p, int units, int splits) {
+  const int lane = threadIdx.x;                       // TMEM lane: (y-tap within group, s)
+  int b = blockIdx.x;
+  const int c4 = b % (p.n_cols / 4);
+  b /= (p.n_cols / 4);
+  const int a = b % p.n_acc;
+  const int unit = b / p.n_acc;
+  int u = unit;
+  const int i3 = u % p.kz;
+  u /= p.kz;
+  const int sc = u % p.n_sc;
+  const int rc = u / p.n_sc;
+  const int j3 = a / p.kgroups, kg = a % p.kgroups;
+  const int k3 = kg * 4 + (lane >> 5);
+  const int s = sc * 32 + (lane & 31);
+  if (k3 >= p.ky || s >= p.S) return;
+  const size_t per_cta = (size_t)p.n_acc * (p.n_cols / 4) * 128;
+  const float4* src = reinterpret_cast<const float4*>(p.ws) + (size_t)unit * per_cta + (size_t)(a * (p.n_cols / 4) + c4) * 128 + lane;
+  const size_t stride = (size_t)units * per_cta;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    const float4 v0 = __ldcg(src + (size_t)sp * stride), v1 = __ldcg(src + (size_t)(sp + 1) * stride);
+    const float4 v2 = __ldcg(src + (size_t)(sp + 2) * stride), v3 = __ldcg(src + (size_t)(sp + 3) * stride);
+    acc.x += (v0.x + v1.x) + (v2.x + v3.x), acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+    acc.z += (v0.z + v1.z) + (v2.z + v3.z), acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+  }
+  for (; sp < splits; ++sp) {
+    const float4 v = __ldcg(src + (size_t)sp * stride);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  const int T = p.kz * p.kx * p.ky;
+  const int tq = (i3 * p.kx + j3) * p.ky + k3;
+  const int tflip = ((p.kz - 1 - i3) * p.kx + (p.kx - 1 - j3)) * p.ky + (p.ky - 1 - k3);
+  const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = rc * p.n_cols + c4 * 4 + e;
+    if (r >= p.R) continue;
+    const int64_t ofs = (p.out_mode == 0) ? ((int64_t)r * p.S + s) * T + tflip : ((int64_t)s * p.R + r) * T + tq;
+    p.W[ofs] = v[e];
   }
 }
 
@@ -263,24 +348,44 @@ bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g) {
   return plan_halo(h, g, &p);
 }
 
-int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) {
+// grid plan shared by the launcher and the workspace query
+static bool plan_grid(int sm_count, WhParams* p, int* units_out, int* splits_out) {
+  // two CTAs per SM when TMEM and shared memory allow (one CTA's epilogue overlaps the other's main loop)
+  const int ctas_per_sm = (p->tmem_cols <= 256 && 3 * p->stage_bytes + 2048 <= 112 * 1024) ? 2 : 1;
+  const int budget = (ctas_per_sm == 2 ? 112 : 226) * 1024 - 2048;
+  p->stages = std::min(MAX_STAGES, budget / p->stage_bytes);
+  if (p->stages < 2) return false;
+  const int units = p->n_rc * p->n_sc * p->kz;
+  int splits = (ctas_per_sm * sm_count) / units;   // floor: never spill one CTA into a second wave
+  if (splits > p->tiles_total) splits = p->tiles_total;
+  if (splits < 1) splits = 1;
+  p->tiles_per_split = (p->tiles_total + splits - 1) / splits;
+  splits = (p->tiles_total + p->tiles_per_split - 1) / p->tiles_per_split;
+  *units_out = units, *splits_out = splits;
+  return true;
+}
+
+size_t e2_wgrad_halo_workspace_bytes(int sm_count, const ReduceGemm& g) {
+  WhParams p;
+  int units, splits;
+  if (!plan_halo(nullptr, g, &p) || !plan_grid(sm_count, &p, &units, &splits)) return 0;
+  return (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float);
+}
+
+int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s) {
   EncodeTiledFn enc = e2_get_tmap_encode();
   if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
   WhParams p;
   if (!plan_halo(h, g, &p)) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_halo_tc: problem does not qualify");
   const int T = g.tz * g.tx * g.ty;
-  // two CTAs per SM when TMEM and shared memory allow (one CTA's epilogue overlaps the other's main loop)
-  const int ctas_per_sm = (p.tmem_cols <= 256 && 3 * p.stage_bytes + 2048 <= 112 * 1024) ? 2 : 1;
-  const int budget = (ctas_per_sm == 2 ? 112 : 226) * 1024 - 2048;
-  p.stages = std::min(MAX_STAGES, budget / p.stage_bytes);
-  if (p.stages < 2) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_halo_tc: shared memory budget");
-  const int units = p.n_rc * p.n_sc * p.kz;
-  int splits = (ctas_per_sm * h->sm_count) / units;   // floor: never spill one CTA into a second wave
-  if (splits > p.tiles_total) splits = p.tiles_total;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
-  splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  int units, splits;
+  if (!plan_grid(h->sm_count, &p, &units, &splits)) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_halo_tc: shared memory budget");
+  const size_t ws_need = (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float);
+  // with a workspace: per-CTA partial tiles + a reduce kernel (deterministic); without: fp32 atomics
+  p.ws = (ws && ws_bytes >= ws_need && !(reinterpret_cast<uintptr_t>(ws) & 15) && env_int("E2_WGRAD_ATOMIC", 0) == 0)
+             ? static_cast<float*>(ws) : nullptr;
   p.W = g.W, p.out_mode = g.out_mode;
+  p.dbg = env_int("E2_WGRAD_DBG", 0);
   p.idesc = tc::make_idesc(2 /*TF32*/, 1, 1, 128, (uint32_t)p.n_cols);
 
   CUtensorMap tmP, tmQ;
@@ -306,17 +411,36 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) {
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(Q) failed: %d", (int)r);
   }
-  cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
+  if (!p.ws) cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
   const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + (2 * MAX_STAGES + 1) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k_wgrad_halo_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
-      return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
-    configured = true;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const WhParams);
+  KernelFn fn = k_wgrad_halo_tc<0, 0>;
+  if (p.kgroups == 1) {
+    switch (p.kx) {
+      case 1: fn = k_wgrad_halo_tc<1, 1>; break;
+      case 2: fn = k_wgrad_halo_tc<2, 1>; break;
+      case 3: fn = k_wgrad_halo_tc<3, 1>; break;
+      case 4: fn = k_wgrad_halo_tc<4, 1>; break;
+      default: break;
+    }
+  } else if (p.kgroups == 2) {
+    switch (p.kx) {
+      case 1: fn = k_wgrad_halo_tc<1, 2>; break;
+      case 5: fn = k_wgrad_halo_tc<5, 2>; break;
+      case 6: fn = k_wgrad_halo_tc<6, 2>; break;
+      default: break;
+    }
   }
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
+    return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
   dim3 grid((unsigned)units, (unsigned)splits);
-  k_wgrad_halo_tc<<<grid, WH_THREADS, smem, s>>>(tmP, tmQ, p);
+  fn<<<grid, WH_THREADS, smem, s>>>(tmP, tmQ, p);
   h->launches++;
   E2_CUDA_CHECK(h, "wgrad_halo_tc");
+  if (p.ws) {
+    k_wgrad_halo_reduce<<<(unsigned)(units * p.n_acc * (p.n_cols / 4)), 128, 0, s>>>(p, units, splits);
+    h->launches++;
+    E2_CUDA_CHECK(h, "wgrad_halo_reduce");
+  }
   return E2_OK;
 }

@@ -31,6 +31,9 @@ class ConvOp(object):
         _lib.lib.e2_conv3d_packed_floats(C.byref(self.d), C.byref(f), C.byref(g))
         self.wf = _dev_f32(f.value, x.buf.device)
         self.wd = _dev_f32(g.value, x.buf.device)
+        ws = C.c_size_t()
+        _lib.lib.e2_conv3d_workspace_size(C.byref(self.d), C.byref(ws))
+        h.reserve_workspace(ws.value)
 
     def _desc(self, x=None, y=None, accumulate=0, act=None, has_bias=None):
         d = _lib.ConvDesc()
@@ -64,7 +67,8 @@ class ConvOp(object):
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
-        self.h.call('e2_conv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), None, 0,
+        ws, ws_bytes = self.h.workspace()
+        self.h.call('e2_conv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), ws, ws_bytes,
                     self.h.stream())
 
 
