@@ -196,19 +196,25 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
           const uint32_t row_enc = (uint32_t)((j * p.YP + k) * 8);      // (rows * 128 B) >> 4
           const bool first_stage = (cb == 0 && jk == 0);
           const bool last_stage = (jk == T9 - 1);
-          int s = pslot;
-          uint32_t par = ppar;
-          for (int q = 0; q < p.NP; ++q) {
-            if (jk == 0) {
-              wait_bar(&pl_full[s], par);
-              tc::tc_fence_after();
-            }
-            const int zl_hi = min(q, p.TZ - 1), zl_lo = max(0, q - kz1);
-            const int i_lo = q - zl_hi, nblk = zl_hi - zl_lo + 1;
-            const uint64_t ad = a_tmpl + (uint64_t)(smP_enc + (uint32_t)s * pstride_enc + row_enc);
-            const uint64_t bd = bd0 + (uint64_t)((uint32_t)i_lo * wblk_enc);
-            const uint32_t dcol = acc0 + (uint32_t)((p.TZ - 1 - zl_hi) * p.BN);
-            if (tc::elect_one()) {
+          // ring position after this stage (all lanes keep it; only the elected lane walks the planes)
+          int s_next = pslot + p.NP;
+          uint32_t par_next = ppar;
+          if (s_next >= p.nslot) s_next -= p.nslot, par_next ^= 1u;
+          if (tc::elect_one()) {
+            // ONE elected lane issues every MMA of the stage: a branch-free body per plane, descriptors
+            // advance by uniform adds
+            int s = pslot;
+            uint32_t par = ppar;
+            for (int q = 0; q < p.NP; ++q) {
+              if (jk == 0) {
+                wait_bar(&pl_full[s], par);
+                tc::tc_fence_after();
+              }
+              const int zl_hi = min(q, p.TZ - 1), zl_lo = max(0, q - kz1);
+              const int i_lo = q - zl_hi, nblk = zl_hi - zl_lo + 1;
+              const uint64_t ad = a_tmpl + (uint64_t)(smP_enc + (uint32_t)s * pstride_enc + row_enc);
+              const uint64_t bd = bd0 + (uint64_t)((uint32_t)i_lo * wblk_enc);
+              const uint32_t dcol = acc0 + (uint32_t)((p.TZ - 1 - zl_hi) * p.BN);
               if (first_stage && q < p.TZ) {
                 // output plane q is touched for the first time (z-tap 0 = block i_lo = 0): overwrite
                 mma4(dcol, ad, bd, p.idesc0 + p.idesc_step, 0u);
@@ -217,13 +223,12 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                 mma4(dcol, ad, bd, p.idesc0 + (uint32_t)nblk * p.idesc_step, 1u);
               }
               if (last_stage) tc::mma_commit(&pl_empty[s]);   // plane slot free once these MMAs have read it
+              if (++s == p.nslot) s = 0, par ^= 1u;
             }
-            __syncwarp();
-            if (++s == p.nslot) s = 0, par ^= 1u;
+            tc::mma_commit(&w_empty[ws]);
           }
-          s_end = s, par_end = par;
-          if (tc::elect_one()) tc::mma_commit(&w_empty[ws]);
           __syncwarp();
+          s_end = s_next, par_end = par_next;
           if (++ws == p.wslot) ws = 0, wpar ^= 1u;
           if (++k == p.ky) k = 0, ++j;
         }

@@ -176,6 +176,50 @@ __global__ void __launch_bounds__(256) k_maxpool_bwd(PoolP p, const float* __res
   }
 }
 
+// Gather form for E2_TIE_FIRST: one thread per INPUT position x V channels, so the two big streams (dx
+// write, ReLU-gate read) are fully coalesced; the pooled dy / argmax values are re-read by the prod(p)
+// threads of a window and come from L1/L2.
+template <int V>
+__global__ void __launch_bounds__(256) k_maxpool_bwd_gather(PoolP p, const float* __restrict__ dy,
+                                                            const int* __restrict__ amax, float* __restrict__ dx,
+                                                            const float* __restrict__ gate) {
+  const int cv = p.C / V;
+  const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * V;
+    const int64_t pos = i / cv;
+    const int yy = (int)(pos % p.Y);
+    int64_t t = pos / p.Y;
+    const int xx = (int)(t % p.X);
+    t /= p.X;
+    const int zz = (int)(t % p.Z);
+    const int n = (int)(t / p.Z);
+    const int lin = (zz * p.X + xx) * p.Y + yy;
+    const int64_t opos = (((int64_t)n * p.Zo + zz / p.pz) * p.Xo + xx / p.px) * p.Yo + yy / p.py;
+    Vec<V> g, o;
+    IVec<V> am;
+    g.load(dy + opos * p.yp + c);
+    am.load(amax + opos * p.yp + c);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.v[j] = (am.v[j] == lin) ? g.v[j] : 0.f;
+    const int64_t ofs = pos * p.xp + c;
+    if (gate) {
+      Vec<V> gt;
+      gt.load(gate + ofs);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(gt.v[j] > 0.f)) o.v[j] = 0.f;
+    }
+    if (p.accumulate) {
+      Vec<V> old;
+      old.load(dx + ofs);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o.v[j] += old.v[j];
+    }
+    o.store(dx + ofs);
+  }
+}
+
 static int fill_pool(e2_handle* h, const e2_pool_desc* d, PoolP* p) {
   E2_REQUIRE(h, d && e2_tensor_ok(&d->x) && e2_tensor_ok(&d->y), "maxpool3d: bad descriptor");
   E2_REQUIRE(h, d->pz >= 1 && d->px >= 1 && d->py >= 1, "maxpool3d: pool factors must be >= 1");
@@ -220,7 +264,13 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
   E2_REQUIRE(h, d->tie_mode == E2_TIE_FIRST ? argmax != nullptr : x != nullptr,
              "maxpool3d_bwd: tie_mode FIRST needs argmax, tie_mode ALL needs x");
   int64_t work = e2_positions(&d->y) * d->y.c;
-  if (vec4_ok({dy, dx, argmax, x}, {p.C, p.xp, p.yp})) {
+  if (p.tie == E2_TIE_FIRST) {
+    const int64_t iwork = e2_positions(&d->x) * d->x.c;
+    if (vec4_ok({dy, dx, argmax, relu_gate}, {p.C, p.xp, p.yp}))
+      k_maxpool_bwd_gather<4><<<e2_grid_1d(iwork / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx, relu_gate);
+    else
+      k_maxpool_bwd_gather<1><<<e2_grid_1d(iwork, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx, relu_gate);
+  } else if (vec4_ok({dy, dx, argmax, x}, {p.C, p.xp, p.yp})) {
     k_maxpool_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx,
                                                                                                relu_gate);
   } else {
@@ -486,6 +536,35 @@ template <int V>
 __global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restrict__ ddst, float* __restrict__ dsrc,
                                                   const float* __restrict__ gate) {
   const int cv = p.C / V;
+  if (p.accumulate) {
+    // only the cropped region changes: walk the (small) gradient of the crop, not the whole source
+    const int64_t total = (int64_t)p.n * p.Zd * p.Xd * p.Yd * cv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int c = (int)(i % cv) * V;
+      int64_t dpos = i / cv;
+      int yd = (int)(dpos % p.Yd);
+      int64_t t = dpos / p.Yd;
+      int xd = (int)(t % p.Xd);
+      t /= p.Xd;
+      int zd = (int)(t % p.Zd);
+      int n = (int)(t / p.Zd);
+      int64_t pos = (((int64_t)n * p.Z + zd + p.oz) * p.X + xd + p.ox) * p.Y + yd + p.oy;
+      Vec<V> v, old;
+      v.load(ddst + dpos * p.dp + p.c0 + c);
+      if (gate) {
+        Vec<V> gt;
+        gt.load(gate + pos * p.sp + c);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (!(gt.v[j] > 0.f)) v.v[j] = 0.f;
+      }
+      old.load(dsrc + pos * p.sp + c);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v.v[j] += old.v[j];
+      v.store(dsrc + pos * p.sp + c);
+    }
+    return;
+  }
   const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % cv) * V;
@@ -509,18 +588,11 @@ __global__ void __launch_bounds__(256) k_crop_bwd(CropP p, const float* __restri
         for (int j = 0; j < V; ++j)
           if (!(gt.v[j] > 0.f)) v.v[j] = 0.f;
       }
-      if (p.accumulate) {
-        Vec<V> old;
-        old.load(dsrc + pos * p.sp + c);
-#pragma unroll
-        for (int j = 0; j < V; ++j) v.v[j] += old.v[j];
-      }
-      v.store(dsrc + pos * p.sp + c);
-    } else if (!p.accumulate) {
+    } else {
 #pragma unroll
       for (int j = 0; j < V; ++j) v.v[j] = 0.f;
-      v.store(dsrc + pos * p.sp + c);
     }
+    v.store(dsrc + pos * p.sp + c);
   }
 }
 
@@ -558,7 +630,7 @@ extern "C" int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const flo
   int rc = fill_crop(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, ddst && dsrc, "crop_concat_bwd: null pointer");
-  int64_t work = e2_positions(&d->src) * d->src.c;
+  int64_t work = (d->accumulate ? e2_positions(&d->dst) : e2_positions(&d->src)) * d->src.c;
   if (vec4_ok({ddst, dsrc}, {p.C, p.sp, p.dp, p.c0}))
     k_crop_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc, relu_gate);
   else

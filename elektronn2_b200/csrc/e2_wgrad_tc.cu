@@ -35,6 +35,7 @@ struct WgParams {
   int tz, tx, ty;          // position tile box (product KP)
   int ntz, ntx, nty;
   int kz, kx, ky, oz, ox, oy;
+  int sz, sx, sy;          // position stride of the Q gather (upconv wgrad: pool factors)
   int R, S;
   int sw;                  // s-channels per tap inside one MMA group: 32, 64 or 128
   int tpm;                 // taps per MMA group = 128 / sw
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
             // taps past the end of the filter: any in-range box, its rows are never stored
             const int tap = min(tap0 + tl, T - 1);
             const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
-            tc::tma_load_5d(smA + as * A_BYTES + ci * CHUNK_BYTES, &tmQ, &a_full[as], s0 + sb * 32, y0 + k3 + p.oy,
-                            x0 + j3 + p.ox, z0 + i3 + p.oz, in_);
+            tc::tma_load_5d(smA + as * A_BYTES + ci * CHUNK_BYTES, &tmQ, &a_full[as], s0 + sb * 32,
+                            y0 * p.sy + k3 + p.oy, x0 * p.sx + j3 + p.ox, z0 * p.sz + i3 + p.oz, in_);
           }
         }
       }
@@ -201,13 +202,14 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
   }
 }
 
-bool pick_tile64(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
+bool pick_tile64(int Oz, int Ox, int Oy, int sz, int sx, int sy, int* tz, int* tx, int* ty) {
   static const int opts[][3] = {{1, 8, 8},  {2, 4, 8}, {1, 4, 16}, {4, 4, 4},  {1, 2, 32}, {2, 2, 16}, {1, 16, 4},
                                 {1, 1, 64}, {2, 8, 4}, {4, 2, 8},  {2, 1, 32}, {4, 1, 16}, {8, 2, 4},  {8, 1, 8},
                                 {1, 32, 2}, {2, 16, 2}, {4, 8, 2}, {8, 4, 2},  {16, 2, 2}, {1, 64, 1}, {2, 32, 1},
                                 {4, 16, 1}, {8, 8, 1}, {16, 4, 1}, {16, 1, 4}, {32, 1, 2}, {32, 2, 1}, {64, 1, 1}};
   int64_t best = -1;
   for (auto& o : opts) {
+    if (o[0] * sz > 256 || o[1] * sx > 256 || o[2] * sy > 256) continue;   // TMA box extent limit (strided gather)
     int64_t v = (int64_t)((Oz + o[0] - 1) / o[0]) * o[0] * ((Ox + o[1] - 1) / o[1]) * o[1] * ((Oy + o[2] - 1) / o[2]) * o[2];
     if (best < 0 || v < best) best = v, *tz = o[0], *tx = o[1], *ty = o[2];
   }
@@ -218,7 +220,7 @@ bool pick_tile64(int Oz, int Ox, int Oy, int* tz, int* tx, int* ty) {
 
 bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g) {
   if (!e2_get_tmap_encode()) return false;
-  if (g.sz != 1 || g.sx != 1 || g.sy != 1) return false;  // strided (upconv) wgrad stays on CUDA cores
+  if (g.sz < 1 || g.sx < 1 || g.sy < 1 || g.sz > 8 || g.sx > 8 || g.sy > 8) return false;   // TMA element-stride limit
   if (g.R < 8 || g.S < 8) return false;
   if (g.p_pitch % 4 || g.q_pitch % 4) return false;
   if ((reinterpret_cast<uintptr_t>(g.P) & 15) || (reinterpret_cast<uintptr_t>(g.Q) & 15)) return false;
@@ -231,7 +233,9 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.Mn = g.Mn, p.Mz = g.Mz, p.Mx = g.Mx, p.My = g.My;
-  pick_tile64(g.Mz, g.Mx, g.My, &p.tz, &p.tx, &p.ty);
+  if (!pick_tile64(g.Mz, g.Mx, g.My, g.sz, g.sx, g.sy, &p.tz, &p.tx, &p.ty))
+    return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: no position tile fits the TMA extent limit");
+  p.sz = g.sz, p.sx = g.sx, p.sy = g.sy;
   p.ntz = (g.Mz + p.tz - 1) / p.tz, p.ntx = (g.Mx + p.tx - 1) / p.tx, p.nty = (g.My + p.ty - 1) / p.ty;
   p.kz = g.tz, p.kx = g.tx, p.ky = g.ty, p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
   p.R = g.R, p.S = g.S;
@@ -281,8 +285,9 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
     cuuint64_t dims[5] = {(cuuint64_t)g.S, (cuuint64_t)g.Qy, (cuuint64_t)g.Qx, (cuuint64_t)g.Qz, (cuuint64_t)g.Qn};
     cuuint64_t pitch = (cuuint64_t)g.q_pitch * 4;
     cuuint64_t strides[4] = {pitch, pitch * g.Qy, pitch * g.Qy * g.Qx, pitch * g.Qy * g.Qx * g.Qz};
-    cuuint32_t box[5] = {32, (cuuint32_t)p.ty, (cuuint32_t)p.tx, (cuuint32_t)p.tz, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    // strided gather (upconv): traverse ty*sy elements, keep every sy-th -> ty rows
+    cuuint32_t box[5] = {32, (cuuint32_t)(p.ty * g.sy), (cuuint32_t)(p.tx * g.sx), (cuuint32_t)(p.tz * g.sz), 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)g.sy, (cuuint32_t)g.sx, (cuuint32_t)g.sz, 1};
     CUresult r = enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.Q), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -308,7 +308,20 @@ class Plan(object):
         self._b('softmax_nll_bwd', lambda: self.loss_op.bwd(self.grad[lg], self.grad_scale), 0,
                 4 * 3 * _nel(self.grad[lg]))
         written.add(lg)
+        # A Crop contributes to only part of its parent's gradient.  Emitted first it would have to
+        # zero-fill the whole buffer and every later contribution would read-modify-write it; so crop
+        # contributions wait until a full-coverage writer (pool / conv dgrad) has gone, then touch only
+        # their own region.  They are flushed at the latest when the parent itself comes up.
+        deferred = {}
+
+        def flush(par):
+            for emit in deferred.pop(par, []):
+                emit(par in written)
+                written.add(par)
+
+        self._flush_deferred = flush
         for n in reversed(self.nodes):
+            flush(n)
             if n not in written and n not in self.crop_into:
                 continue
             if isinstance(n, UpConv):
@@ -347,6 +360,7 @@ class Plan(object):
                         op.bwd(dy, dx, acc, relu_gate=gate), 0,
                         4 * (2 * _nel(self.grad[n]) + _nel(self.grad[par])))
                 written.add(par)
+                flush(par)
             elif isinstance(n, Crop):
                 par = n.parent
                 if isinstance(par, Input):
@@ -358,13 +372,17 @@ class Plan(object):
                     ddst = self.grad[cat]
                 else:
                     ddst = self.grad[n]
-                acc = par in written
                 gate = self._gate_for(par)
-                self._b('crop_concat_bwd:' + n.name,
-                        lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc, gate=gate:
-                        op.bwd(ddst, dx, acc, relu_gate=gate), 0,
-                        4 * (_nel(self.val[n]) + (2 if acc else 1) * _nel(self.grad[par])))
-                written.add(par)
+
+                def emit(acc, n=n, par=par, ddst=ddst, gate=gate):
+                    self._b('crop_concat_bwd:' + n.name,
+                            lambda op=self.aux[n], ddst=ddst, dx=self.grad[par], acc=acc, gate=gate:
+                            op.bwd(ddst, dx, acc, relu_gate=gate), 0,
+                            4 * (3 * _nel(self.val[n]) if acc else _nel(self.val[n]) + _nel(self.grad[par])))
+                if par in written:
+                    emit(True)
+                else:
+                    deferred.setdefault(par, []).append(emit)
             elif isinstance(n, Concat):
                 for p in n.parents:
                     if p in self.alias_of:
@@ -423,6 +441,7 @@ class Plan(object):
         self._b(label, lambda op=op, dy=dy, dx=self.grad[parent], acc=acc, gate=gate:
                 op.dgrad(dy, dx, acc, relu_gate=gate), flops, 4 * (_nel(dy) + _nel(self.grad[parent])), kind)
         written.add(parent)
+        self._flush_deferred(parent)
 
     # ---------------------------------------------------------------- execution
     def pack(self, need_dgrad=None):

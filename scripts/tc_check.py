@@ -100,11 +100,15 @@ def check_upconv(h, n, ci, sp, co, p):
         dy = dev_rand(n, co, osp, 3, signed=True)
         dx = DevTensor(n, sp[0], sp[1], sp[2], ci)
         op.dgrad(dy, dx)
+        dw = torch.zeros_like(w)
+        op.wgrad(dy, dw, None)
         torch.cuda.synchronize()
-        outs[comp] = (view(y).clone(), view(dx).clone())
+        outs[comp] = (view(y).clone(), view(dx).clone(), dw.clone())
+        if comp == 'tf32':
+            ms = [time_ms(f) for f in (op.fwd, lambda: op.dgrad(dy, dx), lambda: op.wgrad(dy, dw, None))]
     e = [rel(a, b_) for a, b_ in zip(outs['tf32'], outs['f32'])]
-    print('upconv n=%d ci=%d sp=%s co=%d p=%s : fwd %.2e dgrad %.2e %s' % (n, ci, sp, co, p, e[0], e[1],
-                                                                        'OK' if max(e) < 1e-3 else 'FAIL'), flush=True)
+    print('upconv n=%d ci=%d sp=%s co=%d p=%s : fwd %.2e dgrad %.2e wgrad %.2e %s  [fwd %.3f dgrad %.3f wgrad %.3f ms]' % (
+        n, ci, sp, co, p, e[0], e[1], e[2], 'OK' if max(e) < 1e-3 else 'FAIL', ms[0], ms[1], ms[2]), flush=True)
     return max(e) < 1e-3
 
 
@@ -121,7 +125,8 @@ def main():
               (1, 32, (9, 34, 34), 64, (3, 3, 3))]
     for c in cases:
         ok &= check_conv(h, *c)
-    for c in [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (1, 64, (3, 4, 5), 64, (2, 2, 2)), (1, 512, (7, 9, 9), 512, (2, 2, 2))]:
+    for c in [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (1, 64, (3, 4, 5), 64, (2, 2, 2)), (1, 512, (7, 9, 9), 512, (2, 2, 2)),
+              (1, 256, (10, 14, 14), 256, (2, 2, 2)), (1, 128, (16, 24, 24), 128, (2, 2, 2))]:
         ok &= check_upconv(h, *c)
     if '--big' in sys.argv:
         for c in [(1, 32, (114, 130, 130), 64, (3, 3, 3)), (1, 64, (56, 64, 64), 64, (3, 3, 3)),
