@@ -33,8 +33,9 @@
 namespace {
 
 constexpr int TX = 16, TY = 8;   // tile x/y extent (16 groups of 8 rows = 128 MMA rows)
-constexpr int ZS_THREADS = 256;
-constexpr int MAX_PSLOTS = 12;
+constexpr int EPI_WARPS = 8;      // two epilogue warps per TMEM lane quadrant, alternating over the chunks of a tile
+constexpr int ZS_THREADS = (4 + EPI_WARPS) * 32;
+constexpr int MAX_PSLOTS = 24;   // NP <= 11 planes per unit, single or double buffered
 constexpr int MAX_WSLOTS = 4;
 
 struct ZsParams {
@@ -54,6 +55,8 @@ struct ZsParams {
   int act, accumulate, round_tf32;
   uint32_t idesc0, idesc_step;   // idesc for N = nblk*BN is idesc0 + nblk*idesc_step
   int epi_off;                   // byte offset of the epilogue staging area (1024-aligned)
+  long long* trace;              // E2_ZS_TRACE: per-role cycle counters of CTA 0 (debug)
+  int dbg;                       // E2_ZS_DBG bottleneck experiments: 1 no plane TMA, 2 no weight TMA, 4 no MMA, 8 no stores
 };
 
 // lean bounded wait for the issuing warp (all lanes poll; try_wait suspends in hardware)
@@ -74,6 +77,41 @@ __device__ __forceinline__ void mma4(uint32_t acc, uint64_t ad, uint64_t bd, uin
   tc::mma_tf32_ss(acc, ad + 6, bd + 6, idesc, 1u);
 }
 
+// One stage = one (channel block, in-plane tap): every input plane of the unit times the stacked weights.
+// TZ / KZ are compile-time so the plane loop unrolls into straight-line code whose per-plane constants
+// (accumulator column, first weight block, MMA width) fold away; the elected lane issues ~6 uniform
+// instructions per MMA instead of ~19 (the run-time loop was issue-bound: 122 cycles per MMA).
+template <int TZ, int KZ, bool WAIT>
+__device__ __forceinline__ void zs_issue_stage(uint64_t a_desc0, uint32_t pstride_enc, uint64_t bd0, uint32_t wblk_enc,
+                                               uint32_t acc0, uint32_t bn, uint32_t idesc0, uint32_t idesc_step,
+                                               bool first_stage, bool last_stage, uint64_t* pl_full, uint64_t* pl_empty,
+                                               uint32_t par_full) {
+  constexpr int NP = TZ + KZ - 1;
+  uint64_t ad = a_desc0;
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const int zl_hi = q < TZ - 1 ? q : TZ - 1;
+    const int zl_lo = q - (KZ - 1) > 0 ? q - (KZ - 1) : 0;
+    const int i_lo = q - zl_hi, nblk = zl_hi - zl_lo + 1;
+    if (WAIT) {
+      wait_bar(&pl_full[q], par_full);
+      tc::tc_fence_after();
+    }
+    const uint64_t bd = bd0 + (uint64_t)((uint32_t)i_lo * wblk_enc);
+    const uint32_t dcol = acc0 + (uint32_t)(TZ - 1 - zl_hi) * bn;
+    if (q < TZ && first_stage) {
+      // output plane q is touched for the first time (z-tap 0 = block i_lo = 0): overwrite
+      mma4(dcol, ad, bd, idesc0 + idesc_step, 0u);
+      if (nblk > 1) mma4(dcol + bn, ad, bd + wblk_enc, idesc0 + (uint32_t)(nblk - 1) * idesc_step, 1u);
+    } else {
+      mma4(dcol, ad, bd, idesc0 + (uint32_t)nblk * idesc_step, 1u);
+    }
+    if (last_stage) tc::mma_commit(&pl_empty[q]);   // plane slot free once these MMAs have read it
+    ad += pstride_enc;
+  }
+}
+
+template <int TZ_, int KZ_>
 __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmC,
@@ -83,16 +121,16 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smP = smem;                                   // plane slots
   uint8_t* smW = smem + p.nslot * p.plane_stride;        // weight ring
-  uint8_t* smE = smem + p.epi_off;                       // epilogue: per warp 4 KB staging + 4 KB aux, then bias
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + 4 * 8192 + 4 * p.BN * 4);
+  uint8_t* smE = smem + p.epi_off;                       // epilogue: per warp one 4 KB staging/aux tile, then bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4);
   uint64_t* pl_full = bars;
   uint64_t* pl_empty = pl_full + MAX_PSLOTS;
   uint64_t* w_full = pl_empty + MAX_PSLOTS;
   uint64_t* w_empty = w_full + MAX_WSLOTS;
   uint64_t* acc_full = w_empty + MAX_WSLOTS;             // [2]
   uint64_t* acc_empty = acc_full + 2;                    // [2]
-  uint64_t* aux_bar = acc_empty + 2;                     // [4] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
+  uint64_t* aux_bar = acc_empty + 2;                     // [EPI_WARPS] one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + EPI_WARPS);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -103,8 +141,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
     if (p.gate) tc::prefetch_tmap(&tmG);
     for (int i = 0; i < p.nslot; ++i) tc::mbar_init(&pl_full[i], 1), tc::mbar_init(&pl_empty[i], 1);
     for (int i = 0; i < p.wslot; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 4);
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], EPI_WARPS);
+    for (int i = 0; i < EPI_WARPS; ++i) tc::mbar_init(&aux_bar[i], 1);
     tc::fence_barrier_init();
   }
   if (warp == 2) {
@@ -131,20 +169,29 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
 
   if (warp == 0) {
     // ----------------------------------------------------------- plane producer
+    // A unit (tile, channel block) owns NP consecutive slots: group 0, or groups 0/1 alternately when the
+    // ring is double buffered (nslot == 2*NP).
     if (lane == 0) {
-      int s = 0;
-      uint32_t par = 1;   // parity to wait for on pl_empty (first round passes)
+      const int dbl = (p.nslot >= 2 * p.NP) ? 1 : 0;
+      int ucount = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         int in_, z0, x0, y0, n0;
         tile_coords(t, in_, z0, x0, y0, n0);
-        for (int cb = 0; cb < p.CB; ++cb)
+        for (int cb = 0; cb < p.CB; ++cb, ++ucount) {
+          const int s0 = dbl ? (ucount & 1) * p.NP : 0;
+          const uint32_t par = (((uint32_t)(dbl ? (ucount >> 1) : ucount)) & 1u) ^ 1u;
           for (int pl = 0; pl < p.NP; ++pl) {
+            const int s = s0 + pl;
             tc::mbar_wait(&pl_empty[s], par);
-            tc::mbar_arrive_expect_tx(&pl_full[s], (uint32_t)p.plane_bytes);
-            tc::tma_load_5d(smP + s * p.plane_stride, &tmA, &pl_full[s], cb * 32, y0 + p.oy, x0 + p.ox,
-                            z0 + p.oz + pl, in_);
-            if (++s == p.nslot) s = 0, par ^= 1u;
+            if (p.dbg & 1) {
+              tc::mbar_arrive(&pl_full[s]);
+            } else {
+              tc::mbar_arrive_expect_tx(&pl_full[s], (uint32_t)p.plane_bytes);
+              tc::tma_load_5d(smP + s * p.plane_stride, &tmA, &pl_full[s], cb * 32, y0 + p.oy, x0 + p.ox,
+                              z0 + p.oz + pl, in_);
+            }
           }
+        }
       }
     }
   } else if (warp == 2) {
@@ -158,99 +205,98 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
         for (int cb = 0; cb < p.CB; ++cb)
           for (int jk = 0; jk < T9; ++jk) {
             tc::mbar_wait(&w_empty[s], par);
-            tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)p.w_bytes);
-            for (int i = 0; i < p.kz; ++i)
-              tc::tma_load_3d(smW + s * p.w_bytes + i * p.wblk_bytes, &tmB, &w_full[s], cb * 32, i * T9 + jk, n0);
+            if (p.dbg & 2) {
+              tc::mbar_arrive(&w_full[s]);
+            } else {
+              tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)p.w_bytes);
+              for (int i = 0; i < p.kz; ++i)
+                tc::tma_load_3d(smW + s * p.w_bytes + i * p.wblk_bytes, &tmB, &w_full[s], cb * 32, i * T9 + jk, n0);
+            }
             if (++s == p.wslot) s = 0, par ^= 1u;
           }
       }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
-    // Executed by all 32 lanes with warp-uniform values; only the tcgen05 instructions are predicated
-    // on the elected lane.  Ring indices / parities are kept incrementally (no division in the loop).
+    // The warp walks tiles / channel blocks / in-plane taps with warp-uniform values; per stage ONE elected
+    // lane issues the unrolled plane sequence (zs_issue_stage).
     const uint32_t smP_enc = tc::smem_u32(smP) >> 4, smW_enc = tc::smem_u32(smW) >> 4;
     const uint32_t pstride_enc = (uint32_t)p.plane_stride >> 4, w_enc = (uint32_t)p.w_bytes >> 4;
     const uint32_t wblk_enc = (uint32_t)p.wblk_bytes >> 4;
     const uint64_t a_tmpl = tc::make_smem_desc(0, 16, (uint32_t)(p.YP * 128), 2);
     const uint64_t b_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
-    const int kz1 = p.kz - 1;
-    int pslot = 0;
-    uint32_t ppar = 0;
+    const uint32_t bn = (uint32_t)p.BN, idesc0 = p.idesc0, idesc_step = p.idesc_step;
+    const int dbl = (p.nslot >= 2 * p.NP) ? 1 : 0;
+    int ucount = 0;
     int ws = 0;
     uint32_t wpar = 0;
     int buf = 0;
     uint32_t bpar = 1;
+    long long tr_acc = 0, tr_w = 0, tr_issue = 0, tr_t0 = clock64();
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      long long c0 = clock64();
       wait_bar(&acc_empty[buf], bpar);
+      tr_acc += clock64() - c0;
       tc::tc_fence_after();
-      const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.TZ * p.BN);
-      for (int cb = 0; cb < p.CB; ++cb) {
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * TZ_) * bn;
+      for (int cb = 0; cb < p.CB; ++cb, ++ucount) {
+        const int s0 = dbl ? (ucount & 1) * p.NP : 0;
+        const uint32_t par_full = ((uint32_t)(dbl ? (ucount >> 1) : ucount)) & 1u;
+        const uint32_t unit_enc = smP_enc + (uint32_t)s0 * pstride_enc;
         int j = 0, k = 0;
-        int s_end = pslot;
-        uint32_t par_end = ppar;
         for (int jk = 0; jk < T9; ++jk) {
+          long long c1 = clock64();
           wait_bar(&w_full[ws], wpar);
+          long long c2 = clock64();
+          tr_w += c2 - c1;
           tc::tc_fence_after();
-          const uint64_t bd0 = b_tmpl + (uint64_t)(smW_enc + (uint32_t)ws * w_enc);
-          const uint32_t row_enc = (uint32_t)((j * p.YP + k) * 8);      // (rows * 128 B) >> 4
-          const bool first_stage = (cb == 0 && jk == 0);
-          const bool last_stage = (jk == T9 - 1);
-          // ring position after this stage (all lanes keep it; only the elected lane walks the planes)
-          int s_next = pslot + p.NP;
-          uint32_t par_next = ppar;
-          if (s_next >= p.nslot) s_next -= p.nslot, par_next ^= 1u;
           if (tc::elect_one()) {
-            // ONE elected lane issues every MMA of the stage: a branch-free body per plane, descriptors
-            // advance by uniform adds
-            int s = pslot;
-            uint32_t par = ppar;
-            for (int q = 0; q < p.NP; ++q) {
-              if (jk == 0) {
-                wait_bar(&pl_full[s], par);
-                tc::tc_fence_after();
-              }
-              const int zl_hi = min(q, p.TZ - 1), zl_lo = max(0, q - kz1);
-              const int i_lo = q - zl_hi, nblk = zl_hi - zl_lo + 1;
-              const uint64_t ad = a_tmpl + (uint64_t)(smP_enc + (uint32_t)s * pstride_enc + row_enc);
-              const uint64_t bd = bd0 + (uint64_t)((uint32_t)i_lo * wblk_enc);
-              const uint32_t dcol = acc0 + (uint32_t)((p.TZ - 1 - zl_hi) * p.BN);
-              if (first_stage && q < p.TZ) {
-                // output plane q is touched for the first time (z-tap 0 = block i_lo = 0): overwrite
-                mma4(dcol, ad, bd, p.idesc0 + p.idesc_step, 0u);
-                if (nblk > 1) mma4(dcol + (uint32_t)p.BN, ad, bd + wblk_enc, p.idesc0 + (uint32_t)(nblk - 1) * p.idesc_step, 1u);
-              } else {
-                mma4(dcol, ad, bd, p.idesc0 + (uint32_t)nblk * p.idesc_step, 1u);
-              }
-              if (last_stage) tc::mma_commit(&pl_empty[s]);   // plane slot free once these MMAs have read it
-              if (++s == p.nslot) s = 0, par ^= 1u;
+            const uint64_t bd0 = b_tmpl + (uint64_t)(smW_enc + (uint32_t)ws * w_enc);
+            const uint64_t ad0 = a_tmpl + (uint64_t)(unit_enc + (uint32_t)((j * p.YP + k) * 8));   // (rows * 128 B) >> 4
+            const bool last_stage = (jk == T9 - 1);
+            if (p.dbg & 4) {
+              if (jk == 0)
+                for (int q = 0; q < p.NP; ++q) wait_bar(&pl_full[s0 + q], par_full);
+              if (last_stage)
+                for (int q = 0; q < p.NP; ++q) tc::mma_commit(&pl_empty[s0 + q]);
+            } else if (jk == 0) {
+              zs_issue_stage<TZ_, KZ_, true>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, cb == 0,
+                                             last_stage, pl_full + s0, pl_empty + s0, par_full);
+            } else {
+              zs_issue_stage<TZ_, KZ_, false>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, false,
+                                              last_stage, pl_full + s0, pl_empty + s0, par_full);
             }
             tc::mma_commit(&w_empty[ws]);
           }
           __syncwarp();
-          s_end = s_next, par_end = par_next;
+          tr_issue += clock64() - c2;
           if (++ws == p.wslot) ws = 0, wpar ^= 1u;
           if (++k == p.ky) k = 0, ++j;
         }
-        pslot = s_end, ppar = par_end;
       }
       if (tc::elect_one()) tc::mma_commit(&acc_full[buf]);
       __syncwarp();
       if (++buf == p.acc_bufs) buf = 0, bpar ^= 1u;
     }
+    if (p.trace && blockIdx.x == 0 && lane == 0) {
+      p.trace[0] = clock64() - tr_t0, p.trace[1] = tr_acc, p.trace[2] = tr_w, p.trace[3] = tr_issue;
+    }
   } else if (warp >= 4) {
     // ----------------------------------------------------------------- epilogue
-    // Warp q owns TMEM lanes 32q..32q+31 = x-lines 4q..4q+3 of the tile.  Per output plane and 32-column
-    // chunk: tcgen05.ld -> +bias -> act -> (gate / accumulate from a TMA-loaded aux tile) -> tf32 round ->
-    // swizzled st.shared -> ONE TMA store of the [32 ch x 8 y x 4 x] box.  No per-thread global stores:
-    // with ~220 KB of shared memory in use the L1 is gone and scattered 16-byte STGs ran at ~300 GB/s.
-    const int q = warp & 3;
-    uint8_t* stage = smE + q * 8192;
-    uint8_t* aux = stage + 4096;
-    float* bias_w = reinterpret_cast<float*>(smE + 4 * 8192) + q * p.BN;
-    uint64_t* abar = &aux_bar[q];
+    // Warps q and q+4 own TMEM lanes 32q..32q+31 = x-lines 4q..4q+3 of the tile and alternate over its
+    // (plane, 32-column chunk) list.  Per chunk: tcgen05.ld -> +bias -> act -> (gate / accumulate from a
+    // TMA-loaded tile) -> tf32 round -> swizzled st.shared -> ONE TMA store of the [32 ch x 8 y x 4 x] box.
+    // The 4 KB buffer serves as aux tile first and as store staging afterwards.  No per-thread global
+    // stores: with ~220 KB of shared memory in use the L1 is gone and scattered 16-byte STGs ran at ~300 GB/s.
+    const int ew = warp - 4;
+    const int q = warp & 3, half = ew >> 2;
+    uint8_t* stage = smE + ew * 4096;
+    float* bias_w = reinterpret_cast<float*>(smE + EPI_WARPS * 4096) + ew * p.BN;
+    uint64_t* abar = &aux_bar[ew];
     uint32_t apar = 0;
     const int r8 = lane & 7;
+    const bool has_aux = p.gate || p.accumulate;
+    long long tr_full = 0, tr_work = 0, tr_e0 = clock64();
     int buf = 0;
     uint32_t fpar = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -258,18 +304,27 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       tile_coords(t, in_, z0, x0, y0, n0);
       for (int i = lane; i < p.BN; i += 32) bias_w[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       __syncwarp();
+      long long e0 = clock64();
       tc::mbar_wait(&acc_full[buf], fpar);
+      long long e1 = clock64();
+      tr_full += e1 - e0;
       tc::tc_fence_after();
+      int ci = 0;
       for (int zl = 0; zl < p.TZ; ++zl) {
         const uint32_t acc = tmem_base + (uint32_t)((buf * p.TZ + (p.TZ - 1 - zl)) * p.BN) + ((uint32_t)(q * 32) << 16);
         if (z0 + zl >= p.Oz) break;                       // uniform: whole plane outside the tensor
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           if (n0 + c0 >= p.N) break;                      // uniform: chunk entirely past the last channel
-          const bool has_aux = p.gate || p.accumulate;
-          if (has_aux && lane == 0) {
-            tc::mbar_arrive_expect_tx(abar, 4096u);
-            tc::tma_load_5d(aux, p.gate ? &tmG : &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+          if ((ci++ & 1) != half) continue;               // the sibling warp's chunk
+          // the previous TMA store must have finished reading the buffer
+          if (lane == 0) {
+            tc::bulk_wait_read0();
+            if (has_aux) {
+              tc::mbar_arrive_expect_tx(abar, 4096u);
+              tc::tma_load_5d(stage, p.gate ? &tmG : &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+            }
           }
+          __syncwarp();
           uint32_t r[32];
           if (p.BN - c0 >= 32) {
             tc::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
@@ -294,7 +349,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           } else if (p.act != E2_ACT_LIN) {
-#pragma unroll 4
+            // fully unrolled on purpose: a partially unrolled loop indexes v[] dynamically, which puts the
+            // whole array in local memory (L1 is carved out for shared memory here -> every access goes to L2)
+#pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = e2_apply_act(v[j], p.act);
           }
           if (has_aux) {
@@ -303,7 +360,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
             if (p.gate) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 g4 = *reinterpret_cast<const float4*>(aux + lane * 128 + ((j ^ r8) << 4));
+                const float4 g4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
                 if (!(g4.x > 0.f)) v[4 * j + 0] = 0.f;
                 if (!(g4.y > 0.f)) v[4 * j + 1] = 0.f;
                 if (!(g4.z > 0.f)) v[4 * j + 2] = 0.f;
@@ -314,7 +371,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                 __syncwarp();
                 if (lane == 0) {
                   tc::mbar_arrive_expect_tx(abar, 4096u);
-                  tc::tma_load_5d(aux, &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+                  tc::tma_load_5d(stage, &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
                 }
                 tc::mbar_wait(abar, apar);
                 apar ^= 1u;
@@ -323,7 +380,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
             if (p.accumulate) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 c4 = *reinterpret_cast<const float4*>(aux + lane * 128 + ((j ^ r8) << 4));
+                const float4 c4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
                 v[4 * j + 0] += c4.x, v[4 * j + 1] += c4.y, v[4 * j + 2] += c4.z, v[4 * j + 3] += c4.w;
               }
             }
@@ -332,16 +389,14 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
           }
-          // the previous TMA store must have finished reading the staging buffer
-          if (lane == 0) tc::bulk_wait_read0();
-          __syncwarp();
+          // each lane reads and writes only its own 128-byte row of the buffer: no cross-lane hazard
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ r8) << 4)) =
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           tc::fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 8)) {
             tc::tma_store_5d(&tmC, stage, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
             tc::bulk_commit();
           }
@@ -351,9 +406,14 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+      tr_work += clock64() - e1;
       if (++buf == p.acc_bufs) buf = 0, fpar ^= 1u;
     }
     if (lane == 0) tc::bulk_wait0();
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 4)) {
+      long long* tr = p.trace + 8 + (ew >> 2) * 4;
+      tr[0] = clock64() - tr_e0, tr[1] = tr_full, tr[2] = tr_work;
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -392,8 +452,8 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   p->wblk_bytes = bn * 128;
   p->w_bytes = S * bn * 128;
   if (g.c_pitch % 4 || (reinterpret_cast<uintptr_t>(g.C) & 15) || (reinterpret_cast<uintptr_t>(g.gate) & 15)) return false;
-  const int epi_bytes = 4 * 8192 + 4 * bn * 4;  // per epilogue warp: 4 KB staging + 4 KB aux; bias copies
-  const int budget = 227 * 1024 - 1024 - 512 - epi_bytes;   // alignment slack + barriers + epilogue
+  const int epi_bytes = EPI_WARPS * 4096 + EPI_WARPS * bn * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
+  const int budget = 227 * 1024 - 1024 - 1024 - epi_bytes;   // alignment slack + barriers + epilogue
   // TZ: as many output planes as TMEM (double-buffered) and shared memory allow; among those, the one
   // with the least z-quantisation / wave-quantisation waste
   const int ntx = (g.Ox + TX - 1) / TX, nty = (g.Oy + TY - 1) / TY;
@@ -402,7 +462,7 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   for (int tz = 8; tz >= 1; --tz) {
     if (2 * tz * bn > 512) continue;
     const int np = tz + S - 1;
-    if (np > MAX_PSLOTS) continue;
+    if (np > 11) continue;
     if (np * p->plane_stride + 2 * p->w_bytes > budget) continue;
     const int ntz = (g.Oz + tz - 1) / tz;
     const int64_t tiles = (int64_t)g.On * ntz * ntx * nty * ntn;
@@ -422,10 +482,12 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   int rest = budget - p->NP * p->plane_stride - 2 * p->w_bytes;
   p->nslot = p->NP;
   p->wslot = 2;
-  // spare memory: one extra plane slot first (prefetch across unit boundaries), then weight slots, then planes
-  if (p->nslot < MAX_PSLOTS && rest >= p->plane_stride) p->nslot++, rest -= p->plane_stride;
+  // spare memory: a third weight slot first (a stage's MMAs are about as long as one TMA round trip), then
+  // full double buffering of the unit's planes (the next unit loads while this one computes), then more
+  // weight slots
   if (rest >= p->w_bytes) p->wslot++, rest -= p->w_bytes;
-  while (p->nslot < MAX_PSLOTS && p->nslot < 2 * p->NP && rest >= p->plane_stride) p->nslot++, rest -= p->plane_stride;
+  if (rest >= p->NP * p->plane_stride) p->nslot = 2 * p->NP, rest -= p->NP * p->plane_stride;
+  while (p->wslot < MAX_WSLOTS && rest >= p->w_bytes) p->wslot++, rest -= p->w_bytes;
   p->acc_bufs = 2;
   int cols = 32;
   while (cols < p->acc_bufs * p->TZ * bn) cols *= 2;
@@ -456,6 +518,11 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   p.C = g.C, p.c_pitch = g.c_pitch, p.bias = g.bias, p.gate = g.gate;
   p.act = g.act, p.accumulate = g.accumulate, p.round_tf32 = g.round_tf32;
   p.idesc0 = tc::make_idesc(2 /*TF32*/, 0, 0, 128, 0);
+  {
+    const char* e = getenv("E2_ZS_DBG");
+    p.dbg = e ? atoi(e) : 0;
+    if (getenv("E2_ZS_INFO")) fprintf(stderr, "zstack: TZ %d NP %d nslot %d wslot %d BN %d CB %d tiles %d smem plane %d w %d\n", p.TZ, p.NP, p.nslot, p.wslot, p.BN, p.CB, p.num_tiles, p.plane_stride, p.w_bytes);
+  }
   p.idesc_step = (uint32_t)(p.BN >> 3) << 17;
   CUtensorMap tmA, tmB;
   {
@@ -498,17 +565,32 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + (size_t)p.epi_off + 4 * 8192 + 4 * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 8) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k_conv_zstack_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) !=
-        cudaSuccess)
-      return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
-    configured = true;
-  }
+  const size_t smem = 1024 + (size_t)p.epi_off + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 4 + EPI_WARPS) * 8 + 16;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ZsParams);
+#define ZS_ROW(KZ)                                                                                               \
+  {k_conv_zstack_tc<1, KZ>, k_conv_zstack_tc<2, KZ>, k_conv_zstack_tc<3, KZ>, k_conv_zstack_tc<4, KZ>,             \
+   k_conv_zstack_tc<5, KZ>, k_conv_zstack_tc<6, KZ>, k_conv_zstack_tc<7, KZ>, k_conv_zstack_tc<8, KZ>}
+  static const KernelFn table[4][8] = {ZS_ROW(1), ZS_ROW(2), ZS_ROW(3), ZS_ROW(4)};
+#undef ZS_ROW
+  if (p.kz < 1 || p.kz > 4 || p.TZ < 1 || p.TZ > 8) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: no kernel for TZ %d kz %d", p.TZ, p.kz);
+  KernelFn fn = table[p.kz - 1][p.TZ - 1];
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
+    return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
   if (smem > 227 * 1024) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: shared memory plan exceeds 227 KB");
   const int grid = std::min(p.num_tiles, h->sm_count);
-  k_conv_zstack_tc<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, tmC, tmG, p);
+  if (getenv("E2_ZS_TRACE")) {
+    cudaMalloc(&p.trace, 32 * sizeof(long long));
+    cudaMemset(p.trace, 0, 32 * sizeof(long long));
+  }
+  fn<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, tmC, tmG, p);
+  if (p.trace) {
+    long long tr[32];
+    cudaMemcpy(tr, p.trace, sizeof(tr), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    const int tiles0 = (p.num_tiles + grid - 1) / grid;
+    fprintf(stderr, "zstack trace (CTA 0, %d tiles): mma warp total %lld  wait acc_empty %lld  wait w_full %lld  issue %lld | epi0 total %lld wait acc_full %lld work %lld | epi4 total %lld wait %lld work %lld\n",
+            tiles0, tr[0], tr[1], tr[2], tr[3], tr[8], tr[9], tr[10], tr[12], tr[13], tr[14]);
+  }
   h->launches++;
   E2_CUDA_CHECK(h, "conv_zstack_tc");
   return E2_OK;
