@@ -641,19 +641,20 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   E2_REQUIRE(h, x && dy && dw, "conv3d_wgrad: null pointer");
   ReduceGemm g;
   conv_wgrad_problem(d, x, dy, dw, &g);
+  bool db_done = false;
   cudaStream_t s = (cudaStream_t)stream;
   if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
     rc = e2_launch_conv_c1_wgrad_line(h, g, s);
   else if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
     rc = e2_launch_conv_c1_wgrad(h, g, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_wgrad_halo_tc_ok(h, g))
-    rc = e2_launch_wgrad_halo_tc(h, g, ws, ws_bytes, s);
+    rc = e2_launch_wgrad_halo_tc(h, g, ws, ws_bytes, db, &db_done, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))
     rc = e2_launch_reduce_gemm_tc(h, g, s);
   else
     rc = e2_launch_reduce_gemm_ffma(h, g, s);
   if (rc) return rc;
-  if (db) return e2_launch_bias_grad(h, dy, e2_positions(&d->y), d->y.c, d->y.c_pitch, db, s);
+  if (db && !db_done) return e2_launch_bias_grad(h, dy, e2_positions(&d->y), d->y.c, d->y.c_pitch, db, s);
   return E2_OK;
 }
 

@@ -60,5 +60,7 @@ bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
 // halo-reuse wgrad (e2_wgrad_halo_tc.cu): x tile loaded once, taps are shifted descriptor views
 bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g);
-int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s);
+// db (nullable): bias gradient = column sums of P; *db_done tells the caller whether the kernel produced it
+int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
+                            cudaStream_t s);
 size_t e2_wgrad_halo_workspace_bytes(int sm_count, const ReduceGemm& g);

@@ -43,6 +43,8 @@ struct WhParams {
   int tmem_cols;
   int tiles_total, tiles_per_split;
   float* W;
+  float* db_ws;   // fused bias gradient: per-(split, r chunk) column sums of dy [splits][n_rc][n_cols], NULL: off
+  float* db;      // final bias gradient (reduce kernel)
   float* ws;   // partial-sum workspace [cta][acc][col/4][lane][4]; NULL: fp32 atomics straight into W
   int out_mode;
   uint32_t idesc;
@@ -88,7 +90,9 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmP);
     tc::prefetch_tmap(&tmQ);
-    for (int i = 0; i < p.stages; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    // CTAs that also sum dy for the bias gradient have a second consumer of each stage (the epilogue warps)
+    const uint32_t consumers = (p.db_ws && i3 == 0 && sc == 0) ? 2u : 1u;
+    for (int i = 0; i < p.stages; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], consumers);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
@@ -184,6 +188,38 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
     const int q = warp & 3;
     const int T = p.kz * p.kx * p.ky;
     const int s = s0 + lane;                        // TMEM lane = (chunk q = y-tap within group, s)
+    if (p.db_ws && i3 == 0 && sc == 0) {
+      // fused bias gradient: while the MMAs run, the epilogue warps sum the dy tile of every stage over its
+      // 64 positions (thread = channel; the 32B-atom swizzle keeps a warp's 32 channels on distinct banks)
+      const int et = (int)threadIdx.x - 64;         // 0..127
+      float sum0 = 0.f, sum1 = 0.f;
+      const int c0 = et, c1 = et + 128;
+      const uint32_t off0 = (uint32_t)(c0 >> 5) * (uint32_t)p.dy_chunk_bytes, off1 = (uint32_t)(c1 >> 5) * (uint32_t)p.dy_chunk_bytes;
+      const uint32_t a0 = (uint32_t)((c0 >> 3) & 3), a1 = (uint32_t)((c1 >> 3) & 3), w0 = (uint32_t)(c0 & 7) * 4u, w1 = (uint32_t)(c1 & 7) * 4u;
+      const int rows = p.TZ * p.TX * TY;
+      int st = 0;
+      uint32_t par = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        wait_bar(&full[st], par);
+        const uint8_t* dyb = smem + st * p.stage_bytes + p.x_stride;
+        if (c0 < p.n_cols) {
+#pragma unroll 8
+          for (int r = 0; r < rows; ++r)
+            sum0 += *reinterpret_cast<const float*>(dyb + off0 + r * 128 + ((a0 ^ (uint32_t)(r & 3)) << 5) + w0);
+        }
+        if (c1 < p.n_cols) {
+#pragma unroll 8
+          for (int r = 0; r < rows; ++r)
+            sum1 += *reinterpret_cast<const float*>(dyb + off1 + r * 128 + ((a1 ^ (uint32_t)(r & 3)) << 5) + w1);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // all four epilogue warps are done with the stage
+        if (et == 0) tc::mbar_arrive(&empty[st]);
+        if (++st == p.stages) st = 0, par ^= 1u;
+      }
+      float* dst = p.db_ws + ((size_t)blockIdx.y * p.n_rc + rc) * p.n_cols;
+      if (c0 < p.n_cols) dst[c0] = sum0;
+      if (c1 < p.n_cols) dst[c1] = sum1;
+    }
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
     if (p.ws) {
@@ -241,7 +277,19 @@ __global__ void __launch_bounds__(WH_THREADS) k_wgrad_halo_tc(const __grid_const
 // Sum the per-CTA partial tiles over the position splits and scatter into the reference weight layout.
 // One thread per (unit, accumulator, 4 columns, lane); reads are coalesced float4, every dw element is
 // written exactly once (no memset, no atomics, deterministic).
-__global__ void __launch_bounds__(128) k_wgrad_halo_reduce(const WhParams p, int units, int splits) {
+__global__ void __launch_bounds__(128) k_wgrad_halo_reduce(const WhParams p, int units, int splits, int w_blocks) {
+  if ((int)blockIdx.x >= w_blocks) {
+    // bias gradient: sum the per-split column sums
+    const int i = ((int)blockIdx.x - w_blocks) * 128 + (int)threadIdx.x;
+    if (i >= p.n_rc * p.n_cols) return;
+    const int rc = i / p.n_cols, c = i % p.n_cols;
+    const int r = rc * p.n_cols + c;
+    if (r >= p.R) return;
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += __ldcg(p.db_ws + ((size_t)sp * p.n_rc + rc) * p.n_cols + c);
+    p.db[r] = acc;
+    return;
+  }
   const int lane = threadIdx.x;                       // TMEM lane: (y-tap within group, s)
   int b = blockIdx.x;
   const int c4 = b % (p.n_cols / 4);
@@ -369,10 +417,12 @@ size_t e2_wgrad_halo_workspace_bytes(int sm_count, const ReduceGemm& g) {
   WhParams p;
   int units, splits;
   if (!plan_halo(nullptr, g, &p) || !plan_grid(sm_count, &p, &units, &splits)) return 0;
-  return (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float);
+  return (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float) + (size_t)splits * p.n_rc * p.n_cols * sizeof(float);
 }
 
-int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s) {
+int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
+                            cudaStream_t s) {
+  if (db_done) *db_done = false;
   EncodeTiledFn enc = e2_get_tmap_encode();
   if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
   WhParams p;
@@ -380,11 +430,18 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t 
   const int T = g.tz * g.tx * g.ty;
   int units, splits;
   if (!plan_grid(h->sm_count, &p, &units, &splits)) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_halo_tc: shared memory budget");
-  const size_t ws_need = (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float);
+  const size_t w_part = (size_t)units * splits * p.n_acc * p.n_cols * 128 * sizeof(float);
+  const size_t ws_need = w_part + (size_t)splits * p.n_rc * p.n_cols * sizeof(float);
   // with a workspace: per-CTA partial tiles + a reduce kernel (deterministic); without: fp32 atomics
   p.ws = (ws && ws_bytes >= ws_need && !(reinterpret_cast<uintptr_t>(ws) & 15) && env_int("E2_WGRAD_ATOMIC", 0) == 0)
              ? static_cast<float*>(ws) : nullptr;
   p.W = g.W, p.out_mode = g.out_mode;
+  // fused bias gradient (sum of P = dy over all positions): only with the workspace path, conv layout
+  if (p.ws && db && g.out_mode == 0 && env_int("E2_WGRAD_FUSE_DB", 1)) {
+    p.db_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + w_part);
+    p.db = db;
+    if (db_done) *db_done = true;
+  }
   p.dbg = env_int("E2_WGRAD_DBG", 0);
   p.idesc = tc::make_idesc(2 /*TF32*/, 1, 1, 128, (uint32_t)p.n_cols);
 
@@ -438,7 +495,9 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t 
   h->launches++;
   E2_CUDA_CHECK(h, "wgrad_halo_tc");
   if (p.ws) {
-    k_wgrad_halo_reduce<<<(unsigned)(units * p.n_acc * (p.n_cols / 4)), 128, 0, s>>>(p, units, splits);
+    const int w_blocks = units * p.n_acc * (p.n_cols / 4);
+    const int db_blocks = p.db_ws ? (p.n_rc * p.n_cols + 127) / 128 : 0;
+    k_wgrad_halo_reduce<<<(unsigned)(w_blocks + db_blocks), 128, 0, s>>>(p, units, splits, w_blocks);
     h->launches++;
     E2_CUDA_CHECK(h, "wgrad_halo_reduce");
   }

@@ -63,7 +63,8 @@ def check_conv(h, n, ci, sp, co, k, bench=False):
         dx = DevTensor(n, sp[0], sp[1], sp[2], ci)
         op.dgrad(dy, dx)
         dw = torch.zeros_like(w)
-        op.wgrad(dy, dw, None)
+        db = torch.zeros_like(b)
+        op.wgrad(dy, dw, db)
         # fused ReLU-backward gate + accumulate into a pre-filled gradient
         gate = dev_rand(n, ci, sp, 5, signed=True)
         dx2 = dev_rand(n, ci, sp, 6, signed=True)
@@ -73,15 +74,16 @@ def check_conv(h, n, ci, sp, co, k, bench=False):
         dx4 = DevTensor(n, sp[0], sp[1], sp[2], ci)
         op.dgrad(dy, dx4, relu_gate=gate)
         torch.cuda.synchronize()
-        outs[comp] = (view(y).clone(), view(dx).clone(), dw.clone(), view(dx2).clone(), view(dx3).clone(), view(dx4).clone())
+        outs[comp] = (view(y).clone(), view(dx).clone(), dw.clone(), view(dx2).clone(), view(dx3).clone(), view(dx4).clone(),
+                      db.clone())
         if bench:
             fl = 2.0 * n * np.prod(osp) * co * ci * np.prod(k)
             for name, fn in (('fwd', op.fwd), ('dgrad', lambda: op.dgrad(dy, dx)), ('wgrad', lambda: op.wgrad(dy, dw, None))):
                 ms = time_ms(fn)
                 res['%s_%s' % (comp, name)] = '%.3f ms %.1f TF/s' % (ms, fl / ms / 1e9)
     e = [rel(a, b_) for a, b_ in zip(outs['tf32'], outs['f32'])]
-    print('conv n=%d ci=%d sp=%s co=%d k=%s : fwd %.2e dgrad %.2e wgrad %.2e gate+acc %.2e acc %.2e gate %.2e %s %s' % (
-        n, ci, sp, co, k, e[0], e[1], e[2], e[3], e[4], e[5], 'OK' if max(e) < 1e-3 else 'FAIL', res), flush=True)
+    print('conv n=%d ci=%d sp=%s co=%d k=%s : fwd %.2e dgrad %.2e wgrad %.2e gate+acc %.2e acc %.2e gate %.2e db %.1e %s %s' % (
+        n, ci, sp, co, k, e[0], e[1], e[2], e[3], e[4], e[5], e[6], 'OK' if max(e) < 1e-3 else 'FAIL', res), flush=True)
     return max(e) < 1e-3
 
 

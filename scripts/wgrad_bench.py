@@ -34,7 +34,8 @@ def main():
         op.pack()
         dy = t.dev_rand(1, co, osp, 3, signed=True)
         dw = torch.zeros_like(w)
-        ms = t.time_ms(lambda: op.wgrad(dy, dw, None), 10)
+        db = torch.zeros(co, device='cuda')
+        ms = t.time_ms(lambda: op.wgrad(dy, dw, db), 10)
         fl = 2.0 * np.prod(osp) * co * ci * 27
         tot += ms
         print('%-7s %4d->%4d %-14s wgrad %.3f ms  %.1f TF/s' % (name, ci, co, osp, ms, fl / ms / 1e9), flush=True)
