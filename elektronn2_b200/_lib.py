@@ -69,7 +69,7 @@ class UpConvDesc(C.Structure):
 
 class PoolDesc(C.Structure):
     _fields_ = [('x', Tensor), ('y', Tensor), ('pz', i32), ('px', i32), ('py', i32), ('act', i32),
-                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32), ('round_tf32', i32)]
+                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32), ('round_tf32', i32), ('gate_pooled', i32)]
 
 
 class MfpDesc(C.Structure):
@@ -107,6 +107,7 @@ SIGNATURES = {
     'e2_conv3d_dgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_wgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_packed_floats': (C.c_int, [P(UpConvDesc), P(sz), P(sz)]),
+    'e2_upconv3d_workspace_size': (C.c_int, [P(UpConvDesc), P(sz)]),
     'e2_upconv3d_pack_weights': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp]),
     'e2_upconv3d_fwd': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_dgrad': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, sz, vp]),

@@ -11,6 +11,7 @@
 //   reduce-GEMM   W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]
 //                 conv wgrad (P=dy,Q=x), upconv wgrad (P=x,Q=dy,st=p)
 #include <stdlib.h>
+#include <algorithm>
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
 
@@ -568,6 +569,33 @@ static void conv_fwd_problem(const e2_conv_desc* d, const float* x, const float*
   g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
 }
 
+static int current_sm_count() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sm_count = 148;
+  }
+  return sm_count;
+}
+
+static void conv_dgrad_problem(const e2_conv_desc* d, const float* dy, const float* wd, float* dx, const float* relu_gate,
+                               GatherGemm* g) {
+  memset(g, 0, sizeof(*g));
+  g->gate = relu_gate;
+  int T = d->kz * d->kx * d->ky, op = round_up(d->y.c, 4);
+  g->A = dy, g->a_pitch = d->y.c_pitch, g->K = d->y.c;
+  g->An = d->y.n, g->Az = d->y.z, g->Ax = d->y.x, g->Ay = d->y.y;
+  g->B = wd, g->b_row = (int64_t)T * op, g->b_tap = op;
+  g->C = dx, g->c_pitch = d->x.c_pitch, g->N = d->x.c;
+  g->On = d->x.n, g->Oz = d->x.z, g->Ox = d->x.x, g->Oy = d->x.y;
+  g->tz = d->kz, g->tx = d->kx, g->ty = d->ky;
+  g->oz = -(d->kz - 1), g->ox = -(d->kx - 1), g->oy = -(d->ky - 1);
+  g->sz = g->sx = g->sy = 1;
+  g->accumulate = d->accumulate;
+  g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
+}
+
 static void conv_wgrad_problem(const e2_conv_desc* d, const float* x, const float* dy, float* dw, ReduceGemm* gp) {
   ReduceGemm& g = *gp;
   memset(&g, 0, sizeof(g));
@@ -585,16 +613,21 @@ extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
   *bytes = 0;
   // only the tcgen05 wgrad uses a workspace (per-CTA partial weight tiles, summed by a second kernel)
   if (d->compute == E2_COMPUTE_TF32 && d->x.c > 1) {
-    static int sm_count = 0;
-    if (!sm_count) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        sm_count = 148;
-    }
+    const int sm_count = current_sm_count();
     ReduceGemm g;
     alignas(16) static float dummy[4];
+    e2_handle fake;
+    memset(&fake, 0, sizeof(fake));
+    fake.sm_count = sm_count;
     conv_wgrad_problem(d, dummy, dummy, dummy, &g);
-    if (e2_wgrad_halo_tc_ok(nullptr, g)) *bytes = e2_wgrad_halo_workspace_bytes(sm_count, g);
+    if (e2_wgrad_halo_tc_ok(&fake, g)) *bytes = e2_wgrad_halo_workspace_bytes(sm_count, g);
+    // forward / dgrad on the tap kernel: split-K partial tiles for layers with few output positions
+    GatherGemm f, b;
+    conv_fwd_problem(d, dummy, dummy, nullptr, dummy, &f);
+    conv_dgrad_problem(d, dummy, dummy, dummy, nullptr, &b);
+    for (const GatherGemm* q : {&f, &b})
+      if (e2_gather_gemm_tc_ok(&fake, *q) && !e2_conv_zstack_tc_ok(&fake, *q) && !e2_conv_plane_tc_ok(&fake, *q))
+        *bytes = std::max(*bytes, e2_gather_gemm_tc_workspace_bytes(sm_count, *q));
   }
   return E2_OK;
 }
@@ -606,6 +639,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   E2_REQUIRE(h, x && wf && y && (!d->has_bias || bias), "conv3d_fwd: null pointer");
   GatherGemm g;
   conv_fwd_problem(d, x, wf, bias, y, &g);
+  g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
   if (d->x.c == 1) return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
@@ -617,19 +651,8 @@ extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float*
   if (rc) return rc;
   E2_REQUIRE(h, dy && wd && dx, "conv3d_dgrad: null pointer");
   GatherGemm g;
-  memset(&g, 0, sizeof(g));
-  g.gate = relu_gate;
-  int T = d->kz * d->kx * d->ky, op = round_up(d->y.c, 4);
-  g.A = dy, g.a_pitch = d->y.c_pitch, g.K = d->y.c;
-  g.An = d->y.n, g.Az = d->y.z, g.Ax = d->y.x, g.Ay = d->y.y;
-  g.B = wd, g.b_row = (int64_t)T * op, g.b_tap = op;
-  g.C = dx, g.c_pitch = d->x.c_pitch, g.N = d->x.c;
-  g.On = d->x.n, g.Oz = d->x.z, g.Ox = d->x.x, g.Oy = d->x.y;
-  g.tz = d->kz, g.tx = d->kx, g.ty = d->ky;
-  g.oz = -(d->kz - 1), g.ox = -(d->kx - 1), g.oy = -(d->ky - 1);
-  g.sz = g.sx = g.sy = 1;
-  g.accumulate = d->accumulate;
-  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
+  conv_dgrad_problem(d, dy, wd, dx, relu_gate, &g);
+  g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
@@ -658,25 +681,64 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   return E2_OK;
 }
 
+static void upconv_fwd_problem(const e2_upconv_desc* d, const float* x, const float* wf, const float* bias, float* y,
+                               GatherGemm* g) {
+  memset(g, 0, sizeof(*g));
+  int T = d->pz * d->px * d->py, cp = round_up(d->x.c, 4);
+  g->A = x, g->a_pitch = d->x.c_pitch, g->K = d->x.c;
+  g->An = d->x.n, g->Az = d->x.z, g->Ax = d->x.x, g->Ay = d->x.y;
+  g->B = wf, g->b_row = cp, g->b_tap = 0;
+  g->C = y, g->c_pitch = d->y.c_pitch, g->N = T * d->y.c;
+  g->On = d->x.n, g->Oz = d->x.z, g->Ox = d->x.x, g->Oy = d->x.y;
+  g->tz = g->tx = g->ty = 1;
+  g->sz = g->sx = g->sy = 1;
+  g->bias = d->has_bias ? bias : nullptr;
+  g->act = d->act;
+  g->shuffle = 1, g->pz = d->pz, g->px = d->px, g->py = d->py, g->Fo = d->y.c;
+  g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
+}
+
+static void upconv_dgrad_problem(const e2_upconv_desc* d, const float* dy, const float* wd, float* dx,
+                                 const float* relu_gate, GatherGemm* g) {
+  memset(g, 0, sizeof(*g));
+  g->gate = relu_gate;
+  int T = d->pz * d->px * d->py, np = round_up(T * d->y.c, 4);
+  g->A = dy, g->a_pitch = d->y.c_pitch, g->K = d->y.c;
+  g->An = d->y.n, g->Az = d->y.z, g->Ax = d->y.x, g->Ay = d->y.y;
+  g->B = wd, g->b_row = np, g->b_tap = d->y.c;
+  g->C = dx, g->c_pitch = d->x.c_pitch, g->N = d->x.c;
+  g->On = d->x.n, g->Oz = d->x.z, g->Ox = d->x.x, g->Oy = d->x.y;
+  g->tz = d->pz, g->tx = d->px, g->ty = d->py;
+  g->sz = d->pz, g->sx = d->px, g->sy = d->py;
+  g->accumulate = d->accumulate;
+  g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
+}
+
+extern "C" int e2_upconv3d_workspace_size(const e2_upconv_desc* d, size_t* bytes) {
+  if (!d || !bytes) return E2_ERR_INVALID;
+  *bytes = 0;
+  if (d->compute != E2_COMPUTE_TF32) return E2_OK;
+  const int sm_count = current_sm_count();
+  alignas(16) static float dummy[4];
+  e2_handle fake;
+  memset(&fake, 0, sizeof(fake));
+  fake.sm_count = sm_count;
+  GatherGemm f, b;
+  upconv_fwd_problem(d, dummy, dummy, nullptr, dummy, &f);
+  upconv_dgrad_problem(d, dummy, dummy, dummy, nullptr, &b);
+  for (const GatherGemm* q : {&f, &b})
+    if (e2_gather_gemm_tc_ok(&fake, *q)) *bytes = std::max(*bytes, e2_gather_gemm_tc_workspace_bytes(sm_count, *q));
+  return E2_OK;
+}
+
 extern "C" int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* wf,
                                const float* bias, float* y, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_upconv(h, d);
   if (rc) return rc;
   E2_REQUIRE(h, x && wf && y && (!d->has_bias || bias), "upconv3d_fwd: null pointer");
   GatherGemm g;
-  memset(&g, 0, sizeof(g));
-  int T = d->pz * d->px * d->py, cp = round_up(d->x.c, 4);
-  g.A = x, g.a_pitch = d->x.c_pitch, g.K = d->x.c;
-  g.An = d->x.n, g.Az = d->x.z, g.Ax = d->x.x, g.Ay = d->x.y;
-  g.B = wf, g.b_row = cp, g.b_tap = 0;
-  g.C = y, g.c_pitch = d->y.c_pitch, g.N = T * d->y.c;
-  g.On = d->x.n, g.Oz = d->x.z, g.Ox = d->x.x, g.Oy = d->x.y;
-  g.tz = g.tx = g.ty = 1;
-  g.sz = g.sx = g.sy = 1;
-  g.bias = d->has_bias ? bias : nullptr;
-  g.act = d->act;
-  g.shuffle = 1, g.pz = d->pz, g.px = d->px, g.py = d->py, g.Fo = d->y.c;
-  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
+  upconv_fwd_problem(d, x, wf, bias, y, &g);
+  g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
@@ -688,18 +750,8 @@ extern "C" int e2_upconv3d_dgrad(e2_handle* h, const e2_upconv_desc* d, const fl
   E2_REQUIRE(h, dy && wd && dx, "upconv3d_dgrad: null pointer");
   // dx[m][c] = sum_{tap,o} dy[m*p + tap][o] * w[o][c][tap]  -- a strided gather-GEMM
   GatherGemm g;
-  memset(&g, 0, sizeof(g));
-  g.gate = relu_gate;
-  int T = d->pz * d->px * d->py, np = round_up(T * d->y.c, 4);
-  g.A = dy, g.a_pitch = d->y.c_pitch, g.K = d->y.c;
-  g.An = d->y.n, g.Az = d->y.z, g.Ax = d->y.x, g.Ay = d->y.y;
-  g.B = wd, g.b_row = np, g.b_tap = d->y.c;
-  g.C = dx, g.c_pitch = d->x.c_pitch, g.N = d->x.c;
-  g.On = d->x.n, g.Oz = d->x.z, g.Ox = d->x.x, g.Oy = d->x.y;
-  g.tz = d->pz, g.tx = d->px, g.ty = d->py;
-  g.sz = d->pz, g.sx = d->px, g.sy = d->py;
-  g.accumulate = d->accumulate;
-  g.round_tf32 = (d->compute == E2_COMPUTE_TF32);
+  upconv_dgrad_problem(d, dy, wd, dx, relu_gate, &g);
+  g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }

@@ -19,6 +19,8 @@ struct GatherGemm {
   int act, accumulate, round_tf32;
   int shuffle, pz, px, py, Fo;  // pixel-shuffle epilogue (upconv fwd)
   const float* gate;            // fused ReLU backward: zero the result where gate <= 0 (same layout as C)
+  void* ws;                     // optional caller-owned scratch (split-K partial tiles)
+  size_t ws_bytes;
 };
 
 // W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]
@@ -48,6 +50,8 @@ int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pit
 // tcgen05 path (e2_conv_tc.cu)
 bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+// scratch bytes the tap kernel wants for its split-K path (0: it will not split)
+size_t e2_gather_gemm_tc_workspace_bytes(int sm_count, const GatherGemm& g);
 // halo-reuse variant of the gather-GEMM (e2_conv_plane_tc.cu); preferred when it qualifies
 bool e2_conv_plane_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_conv_plane_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);

@@ -42,6 +42,8 @@ struct TcParams {
   int sz, sx, sy;            // position stride of the gather (upconv dgrad: pool factors)
   const float* gate;         // fused ReLU backward
   uint32_t idesc;
+  int its_per_split;         // K iterations (tap x channel block) per blockIdx.z
+  float* part;               // split-K: raw partial tiles [z][n tile][m tile][col/4][row][4]; NULL: fused epilogue
 };
 
 __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_constant__ CUtensorMap tmA,
@@ -94,23 +96,23 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
 
   const int kblocks = (p.K + BK - 1) / BK;
   const int T = p.kz * p.kx * p.ky;
-  const int total = T * kblocks;
+  const int it_begin = blockIdx.z * p.its_per_split;
+  const int it_end = min(T * kblocks, it_begin + p.its_per_split);
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < T; ++tap) {
+      for (int it = it_begin; it < it_end; ++it) {
+        const int tap = it / kblocks, kb = it - tap * kblocks;
         const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(&empty[s], ph ^ 1u);
-          tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
-          tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 * p.sy + k3 + p.oy,
-                          x0 * p.sx + j3 + p.ox, z0 * p.sz + i3 + p.oz, in_);
-          tc::tma_load_3d(smB + s * b_stage_bytes, &tmB, &full[s], kb * BK, tap, n0);
-        }
+        const int li = it - it_begin;
+        const int s = li % p.stages;
+        const uint32_t ph = (uint32_t)(li / p.stages) & 1u;
+        tc::mbar_wait(&empty[s], ph ^ 1u);
+        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+        tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 * p.sy + k3 + p.oy,
+                        x0 * p.sx + j3 + p.ox, z0 * p.sz + i3 + p.oz, in_);
+        tc::tma_load_3d(smB + s * b_stage_bytes, &tmB, &full[s], kb * BK, tap, n0);
       }
     }
   } else if (warp == 1) {
@@ -118,9 +120,9 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
     if (lane == 0) {
       const uint64_t desc_tmpl = tc::make_smem_desc(0, 16, 1024, 2);
       const uint32_t smA_addr = tc::smem_u32(smA), smB_addr = tc::smem_u32(smB);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      for (int li = 0; li < it_end - it_begin; ++li) {
+        const int s = li % p.stages;
+        const uint32_t ph = (uint32_t)(li / p.stages) & 1u;
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
         // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart; advancing K by
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
         // descriptor's 16-byte start-address field)
         const uint64_t ad = desc_tmpl + (uint64_t)((smA_addr + (uint32_t)(s * A_STAGE_BYTES)) >> 4);
         const uint64_t bd = desc_tmpl + (uint64_t)((smB_addr + (uint32_t)(s * b_stage_bytes)) >> 4);
-        tc::mma_tf32_ss(tmem_base, ad, bd, p.idesc, it > 0 ? 1u : 0u);
+        tc::mma_tf32_ss(tmem_base, ad, bd, p.idesc, li > 0 ? 1u : 0u);
         tc::mma_tf32_ss(tmem_base, ad + 2, bd + 2, p.idesc, 1u);
         tc::mma_tf32_ss(tmem_base, ad + 4, bd + 4, p.idesc, 1u);
         tc::mma_tf32_ss(tmem_base, ad + 6, bd + 6, p.idesc, 1u);
@@ -156,6 +158,18 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
         for (int j = 16; j < 32; ++j) r[j] = 0u;
       }
       tc::tmem_ld_wait();
+      if (p.part) {
+        // split-K: raw accumulators, one coalesced float4 per row and 4 columns; the reduce kernel sums
+        // the splits and applies the epilogue
+        float4* dst = reinterpret_cast<float4*>(p.part) +
+                      ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (p.BN / 4) * BM + row;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4)
+          if (c0 + j4 < p.BN)
+            dst[(size_t)((c0 + j4) / 4) * BM] = make_float4(__uint_as_float(r[j4]), __uint_as_float(r[j4 + 1]),
+                                                           __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
+        continue;
+      }
       if (!row_ok) continue;
       if (!p.shuffle) {
         float* out = p.C + pos * p.c_pitch + n0 + c0;
@@ -243,6 +257,61 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
 // ------------------------------------------------------------------ host side
 EncodeTiledFn get_encode() { return e2_get_tmap_encode(); }
 
+// Split-K second pass: sum the partial tiles over the K splits and apply the epilogue of the fused path
+// (+bias -> act -> ReLU gate -> accumulate -> tf32 round; pixel shuffle for upconv forward).
+// One thread per (tile, 4 columns, row): the partial reads are coalesced float4.
+__global__ void __launch_bounds__(BM) k_gather_gemm_reduce(const TcParams p, int ksplit, int tiles_m, int tiles_n) {
+  const int row = threadIdx.x;
+  int b = blockIdx.x;
+  const int c4 = b % (p.BN / 4);
+  b /= (p.BN / 4);
+  const int tm = b % tiles_m;
+  const int tn = b / tiles_m;
+  const size_t tile_f4 = (size_t)(p.BN / 4) * BM;
+  const float4* src = reinterpret_cast<const float4*>(p.part) + ((size_t)tn * tiles_m + tm) * tile_f4 + (size_t)c4 * BM + row;
+  const size_t zstride = (size_t)tiles_n * tiles_m * tile_f4;
+  float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < ksplit; ++z) {
+    const float4 v = __ldcg(src + (size_t)z * zstride);
+    a4.x += v.x, a4.y += v.y, a4.z += v.z, a4.w += v.w;
+  }
+  int tile = tm;
+  const int ity = tile % p.nty;
+  tile /= p.nty;
+  const int itx = tile % p.ntx;
+  tile /= p.ntx;
+  const int itz = tile % p.ntz;
+  const int in_ = tile / p.ntz;
+  const int ly = row % p.ty, lx = (row / p.ty) % p.tx, lz = row / (p.ty * p.tx);
+  const int oz = itz * p.tz + lz, ox = itx * p.tx + lx, oy = ity * p.ty + ly;
+  if (oz >= p.Oz || ox >= p.Ox || oy >= p.Oy) return;
+  const int64_t pos = (((int64_t)in_ * p.Oz + oz) * p.Ox + ox) * p.Oy + oy;
+  const float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int n = tn * p.BN + c4 * 4 + e;
+    if (n >= p.N) continue;
+    float a = v[e];
+    int64_t ofs;
+    int ch = n;
+    if (p.shuffle) {
+      const int tp = n / p.Fo;
+      ch = n - tp * p.Fo;
+      const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+      ofs = ((((int64_t)in_ * (p.Oz * p.pz) + oz * p.pz + i3) * (p.Ox * p.px) + ox * p.px + j3) * (p.Oy * p.py) +
+             oy * p.py + k3) * p.c_pitch + ch;
+    } else {
+      ofs = pos * p.c_pitch + n;
+    }
+    if (p.bias) a += __ldg(p.bias + ch);
+    a = e2_apply_act(a, p.act);
+    if (p.gate && !(__ldg(p.gate + ofs) > 0.f)) a = 0.f;
+    if (p.accumulate) a += p.C[ofs];
+    if (p.round_tf32) a = e2_round_tf32(a);
+    p.C[ofs] = a;
+  }
+}
+
 }  // namespace
 
 EncodeTiledFn e2_get_tmap_encode() {
@@ -291,22 +360,62 @@ bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g) {
   return true;
 }
 
+// N tile and K split.  Layers with few output positions give few CTAs (conv7 of unet3d: 5 M tiles), so the
+// N tile shrinks and the (tap x channel block) loop is split over blockIdx.z when scratch is available.
+static void plan_tc(int sm_count, const GatherGemm& g, int tiles_m, bool may_split, int* bn_out, int* ksplit_out,
+                    int* its_out) {
+  int bn = (g.N + 15) / 16 * 16;
+  if (bn > 256) bn = 256;
+  // the shuffle epilogue wants whole 32-channel runs; keep multiples of 32 when N allows
+  while (bn > 64 && (int64_t)tiles_m * ((g.N + bn - 1) / bn) < sm_count) bn = (bn / 2 + 31) / 32 * 32;
+  const int tiles_n = (g.N + bn - 1) / bn;
+  const int total = g.tz * g.tx * g.ty * ((g.K + BK - 1) / BK);
+  int ksplit = 1;
+  if (may_split) {
+    const int64_t ctas = (int64_t)tiles_m * tiles_n;
+    ksplit = (int)((2 * (int64_t)sm_count) / ctas);
+    if (ksplit > total / 6) ksplit = total / 6;      // at least 6 K iterations (24 MMAs) per CTA
+    if (ksplit < 1) ksplit = 1;
+  }
+  int its = (total + ksplit - 1) / ksplit;
+  ksplit = (total + its - 1) / its;
+  *bn_out = bn, *ksplit_out = ksplit, *its_out = its;
+}
+
+static int tc_tiles_m(const GatherGemm& g, int* tz, int* tx, int* ty) {
+  pick_tile(g.Oz, g.Ox, g.Oy, g.sz, g.sx, g.sy, tz, tx, ty);
+  return g.On * ((g.Oz + *tz - 1) / *tz) * ((g.Ox + *tx - 1) / *tx) * ((g.Oy + *ty - 1) / *ty);
+}
+
+size_t e2_gather_gemm_tc_workspace_bytes(int sm_count, const GatherGemm& g) {
+  int tz, tx, ty, bn, ksplit, its;
+  const int tiles_m = tc_tiles_m(g, &tz, &tx, &ty);
+  plan_tc(sm_count, g, tiles_m, true, &bn, &ksplit, &its);
+  if (ksplit <= 1) return 0;
+  return (size_t)ksplit * tiles_m * ((g.N + bn - 1) / bn) * BM * bn * sizeof(float);
+}
+
 int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.On = g.On, p.Oz = g.Oz, p.Ox = g.Ox, p.Oy = g.Oy;
-  pick_tile(g.Oz, g.Ox, g.Oy, g.sz, g.sx, g.sy, &p.tz, &p.tx, &p.ty);
+  const int tiles_m = tc_tiles_m(g, &p.tz, &p.tx, &p.ty);
   p.sz = g.sz, p.sx = g.sx, p.sy = g.sy;
   p.gate = g.gate;
   p.ntz = (g.Oz + p.tz - 1) / p.tz, p.ntx = (g.Ox + p.tx - 1) / p.tx, p.nty = (g.Oy + p.ty - 1) / p.ty;
   p.kz = g.tz, p.kx = g.tx, p.ky = g.ty;
   p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
   p.K = g.K, p.N = g.N;
-  int bn = (g.N + 15) / 16 * 16;
-  if (bn > 256) bn = 256;
+  int bn, ksplit, its;
+  const bool have_ws = g.ws && !(reinterpret_cast<uintptr_t>(g.ws) & 15) && !getenv("E2_NO_SPLITK");
+  plan_tc(h->sm_count, g, tiles_m, have_ws, &bn, &ksplit, &its);
+  if (ksplit > 1 && (size_t)ksplit * tiles_m * ((g.N + bn - 1) / bn) * BM * bn * sizeof(float) > g.ws_bytes)
+    plan_tc(h->sm_count, g, tiles_m, false, &bn, &ksplit, &its);
   p.BN = bn;
+  p.its_per_split = its;
+  p.part = ksplit > 1 ? static_cast<float*>(g.ws) : nullptr;
   const int b_stage = bn * BK * 4;
   p.stages = (bn <= 64) ? 4 : (bn <= 128 ? 3 : 4);
   int cols = 32;
@@ -352,10 +461,16 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
       return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
     configured = 227 * 1024;
   }
-  dim3 grid((unsigned)(p.On * p.ntz * p.ntx * p.nty), (unsigned)((g.N + bn - 1) / bn));
+  const int tiles_n = (g.N + bn - 1) / bn;
+  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   k_gather_gemm_tc<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
   h->launches++;
   E2_CUDA_CHECK(h, "gather_gemm_tc");
+  if (p.part) {
+    k_gather_gemm_reduce<<<(unsigned)(tiles_m * tiles_n * (bn / 4)), BM, 0, s>>>(p, ksplit, tiles_m, tiles_n);
+    h->launches++;
+    E2_CUDA_CHECK(h, "gather_gemm_reduce");
+  }
   return E2_OK;
 }
 

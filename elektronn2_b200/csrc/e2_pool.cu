@@ -54,7 +54,7 @@ struct PoolP {
   int n, Z, X, Y, C, xp;  // input dims, input pitch
   int Zo, Xo, Yo, yp;     // output dims, output pitch
   int pz, px, py;
-  int act, has_bias, tie, accumulate, round_tf32;
+  int act, has_bias, tie, accumulate, round_tf32, gate_pooled;
 };
 
 // ------------------------------------------------------------------ max-pool forward
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_maxpool_bwd_gather(PoolP p, const float
     const int64_t ofs = pos * p.xp + c;
     if (gate) {
       Vec<V> gt;
-      gt.load(gate + ofs);
+      gt.load(p.gate_pooled ? gate + opos * p.yp + c : gate + ofs);
 #pragma unroll
       for (int j = 0; j < V; ++j)
         if (!(gt.v[j] > 0.f)) o.v[j] = 0.f;
@@ -234,7 +234,7 @@ static int fill_pool(e2_handle* h, const e2_pool_desc* d, PoolP* p) {
   p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
   p->pz = d->pz, p->px = d->px, p->py = d->py;
   p->act = d->act, p->has_bias = d->has_bias, p->tie = d->tie_mode, p->accumulate = d->accumulate;
-  p->round_tf32 = d->round_tf32;
+  p->round_tf32 = d->round_tf32, p->gate_pooled = d->gate_pooled;
   return E2_OK;
 }
 
@@ -263,6 +263,8 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
   E2_REQUIRE(h, dy && dx, "maxpool3d_bwd: null pointer");
   E2_REQUIRE(h, d->tie_mode == E2_TIE_FIRST ? argmax != nullptr : x != nullptr,
              "maxpool3d_bwd: tie_mode FIRST needs argmax, tie_mode ALL needs x");
+  E2_REQUIRE(h, !d->gate_pooled || (d->tie_mode == E2_TIE_FIRST && !d->has_bias && d->act == E2_ACT_LIN),
+             "maxpool3d_bwd: gate_pooled needs tie_mode FIRST and a pool without bias/activation");
   int64_t work = e2_positions(&d->y) * d->y.c;
   if (p.tie == E2_TIE_FIRST) {
     const int64_t iwork = e2_positions(&d->x) * d->x.c;
@@ -402,7 +404,7 @@ static int fill_mfp(e2_handle* h, const e2_mfp_desc* d, PoolP* p) {
   p->Zo = d->y.z, p->Xo = d->y.x, p->Yo = d->y.y, p->yp = d->y.c_pitch;
   p->pz = d->pz, p->px = d->px, p->py = d->py;
   p->act = d->act, p->has_bias = d->has_bias, p->tie = 0, p->accumulate = 0;
-  p->round_tf32 = d->round_tf32;
+  p->round_tf32 = d->round_tf32, p->gate_pooled = 0;
   return E2_OK;
 }
 

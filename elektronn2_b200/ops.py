@@ -56,14 +56,16 @@ class ConvOp(object):
     def fwd(self, act=None, has_bias=None, y=None):
         d = self.d if (act is None and has_bias is None and y is None) else self._desc(act=act, has_bias=has_bias, y=y)
         yy = y if y is not None else self.y
+        ws, ws_bytes = self.h.workspace()
         self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
-                    _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), None, 0, self.h.stream())
+                    _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), ws, ws_bytes, self.h.stream())
 
     def dgrad(self, dy, dx, accumulate=False, relu_gate=None):
         """relu_gate: post-ReLU output of the layer that produced x (fused ReLU backward)."""
         d = self._desc(x=dx, y=dy, accumulate=accumulate)
+        ws, ws_bytes = self.h.workspace()
         self.h.call('e2_conv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(),
-                    relu_gate.ptr() if relu_gate is not None else None, None, 0, self.h.stream())
+                    relu_gate.ptr() if relu_gate is not None else None, ws, ws_bytes, self.h.stream())
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
@@ -84,6 +86,9 @@ class UpConvOp(object):
         _lib.lib.e2_upconv3d_packed_floats(C.byref(self.d), C.byref(f), C.byref(g))
         self.wf = _dev_f32(f.value, x.buf.device)
         self.wd = _dev_f32(g.value, x.buf.device)
+        ws = C.c_size_t()
+        _lib.lib.e2_upconv3d_workspace_size(C.byref(self.d), C.byref(ws))
+        h.reserve_workspace(ws.value)
 
     def _desc(self, x=None, y=None, accumulate=0):
         d = _lib.UpConvDesc()
@@ -100,13 +105,15 @@ class UpConvOp(object):
                     _lib.ptr(self.wd) if need_dgrad else None, self.h.stream())
 
     def fwd(self):
+        ws, ws_bytes = self.h.workspace()
         self.h.call('e2_upconv3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.wf),
-                    _lib.ptr(self.b) if self.d.has_bias else None, self.y.ptr(), None, 0, self.h.stream())
+                    _lib.ptr(self.b) if self.d.has_bias else None, self.y.ptr(), ws, ws_bytes, self.h.stream())
 
     def dgrad(self, dy, dx, accumulate=False, relu_gate=None):
         d = self._desc(x=dx, y=dy, accumulate=accumulate)
+        ws, ws_bytes = self.h.workspace()
         self.h.call('e2_upconv3d_dgrad', C.byref(d), dy.ptr(), _lib.ptr(self.wd), dx.ptr(),
-                    relu_gate.ptr() if relu_gate is not None else None, None, 0, self.h.stream())
+                    relu_gate.ptr() if relu_gate is not None else None, ws, ws_bytes, self.h.stream())
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
@@ -133,8 +140,13 @@ class PoolOp(object):
         d = _lib.PoolDesc()
         C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
         d.x, d.y, d.accumulate = dx.desc, dy.desc, int(accumulate)
+        gate = relu_gate
+        if (relu_gate is self.x and self.argmax is not None and not d.has_bias and d.act == ACT['lin']
+                and d.tie_mode == TIE['first']):
+            # the gate is this pool's own (post-ReLU) input: gate[argmax] == pooled value, read y instead of x
+            gate, d.gate_pooled = self.y, 1
         self.h.call('e2_maxpool3d_bwd', C.byref(d), dy.ptr(), self.argmax.ptr() if self.argmax is not None else None,
-                    self.x.ptr(), dx.ptr(), relu_gate.ptr() if relu_gate is not None else None, self.h.stream())
+                    self.x.ptr(), dx.ptr(), gate.ptr() if gate is not None else None, self.h.stream())
 
 
 class MfpOp(object):

@@ -127,6 +127,8 @@ typedef struct {
 } e2_upconv_desc;
 
 int e2_upconv3d_packed_floats(const e2_upconv_desc* d, size_t* fwd_floats, size_t* dgrad_floats);
+/* scratch bytes the fwd / dgrad / wgrad entry points can use (split-K partial tiles); 0 is always accepted */
+int e2_upconv3d_workspace_size(const e2_upconv_desc* d, size_t* bytes);
 int e2_upconv3d_pack_weights(e2_handle* h, const e2_upconv_desc* d, const float* w, float* wf, float* wd, void* stream);
 int e2_upconv3d_fwd(e2_handle* h, const e2_upconv_desc* d, const float* x, const float* wf, const float* bias,
                     float* y, void* ws, size_t ws_bytes, void* stream);
@@ -155,6 +157,10 @@ typedef struct {
   int32_t tie_mode;      /* e2_tie_mode, bwd only                    */
   int32_t accumulate;    /* bwd only: dx += instead of dx =          */
   int32_t round_tf32;    /* fwd only: round the output to tf32 (it feeds a kind::tf32 MMA) */
+  int32_t gate_pooled;   /* bwd only: relu_gate has the geometry of y (the pooled tensor) instead of x.  Valid
+                          * for a pool without bias/activation whose input is a post-ReLU tensor: the only
+                          * element of a window that receives gradient is the argmax, whose value IS the
+                          * pooled value, so gate(x)[argmax] == y -- one eighth of the gate traffic */
 } e2_pool_desc;
 
 int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,

@@ -40,7 +40,7 @@ def test_descriptor_structs_match_header_sizes():
     from elektronn2_b200 import _lib
     assert ctypes.sizeof(_lib.Tensor) == 24
     assert ctypes.sizeof(_lib.ConvDesc) == 48 + 7 * 4
-    assert ctypes.sizeof(_lib.PoolDesc) == 48 + 8 * 4
+    assert ctypes.sizeof(_lib.PoolDesc) == 48 + 9 * 4
     assert ctypes.sizeof(_lib.MfpDesc) == 48 + 6 * 4
     assert ctypes.sizeof(_lib.F2DDesc) == 48 + 3 * 4
     assert ctypes.sizeof(_lib.CropDesc) == 48 + 5 * 4
