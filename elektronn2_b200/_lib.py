@@ -97,6 +97,7 @@ SIGNATURES = {
     'e2_last_error': (C.c_char_p, [vp]),
     'e2_launch_count': (C.c_int64, [vp]),
     'e2_ncdhw_to_ndhwc': (C.c_int, [vp, P(Tensor), vp, vp, vp]),
+    'e2_repitch': (C.c_int, [vp, P(Tensor), vp, P(Tensor), vp, i32, vp]),
     'e2_ndhwc_to_ncdhw': (C.c_int, [vp, P(Tensor), vp, vp, vp]),
     'e2_u8_to_f32': (C.c_int, [vp, vp, vp, C.c_int64, C.c_float, vp]),
     'e2_f32_to_u8': (C.c_int, [vp, vp, vp, C.c_int64, C.c_float, vp]),

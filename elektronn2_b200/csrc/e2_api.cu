@@ -97,6 +97,34 @@ extern "C" int e2_ndhwc_to_ncdhw(e2_handle* h, const e2_tensor* t, const float* 
   return layout_launch<false>(h, t, ndhwc, ncdhw, stream);
 }
 
+// ------------------------------------------------------------- channel re-pitch
+// Copies (n,z,x,y,c) between two channel pitches, optionally rounding to tf32.  Used to hand a dense
+// single-channel input to the tcgen05 path (TMA needs 16-byte rows): pad lanes are written as zero.
+__global__ void __launch_bounds__(256) k_repitch(const float* __restrict__ src, float* __restrict__ dst, int64_t P, int C,
+                                                 int sp, int dp, int round_tf32) {
+  const int64_t total = P * dp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = i / dp;
+    const int c = (int)(i - pos * dp);
+    float v = c < C ? src[pos * sp + c] : 0.f;
+    if (round_tf32) v = e2_round_tf32(v);
+    dst[i] = v;
+  }
+}
+
+extern "C" int e2_repitch(e2_handle* h, const e2_tensor* src_t, const float* src, const e2_tensor* dst_t, float* dst,
+                          int32_t round_tf32, void* stream) {
+  E2_REQUIRE(h, e2_tensor_ok(src_t) && e2_tensor_ok(dst_t) && src && dst, "repitch: bad tensor descriptor or null pointer");
+  E2_REQUIRE(h, src_t->n == dst_t->n && src_t->z == dst_t->z && src_t->x == dst_t->x && src_t->y == dst_t->y &&
+                    src_t->c == dst_t->c, "repitch: geometry mismatch");
+  const int64_t P = e2_positions(src_t);
+  k_repitch<<<e2_grid_1d(P * dst_t->c_pitch, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, P, src_t->c, src_t->c_pitch, dst_t->c_pitch, round_tf32);
+  h->launches++;
+  E2_CUDA_CHECK(h, "repitch");
+  return E2_OK;
+}
+
 // ------------------------------------------------------------- uint8 <-> float32
 __global__ void __launch_bounds__(256) k_u8_to_f32(const uint8_t* __restrict__ s, float* __restrict__ d, int64_t n,
                                                    float scale) {

@@ -641,7 +641,18 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   conv_fwd_problem(d, x, wf, bias, y, &g);
   g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->x.c == 1) return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
+  if (d->x.c == 1) {
+    // a single input channel is HBM-bound either way; with 16-byte rows (pitch % 4 == 0) the halo-plane
+    // tcgen05 kernel takes it (one K = 8 MMA per tap and plane, TMA zero-fills the 7 missing channels) and
+    // its TMA-store epilogue writes the output at full speed
+    // (measured: TMA walks every 16-byte chunk of a box, valid or zero-filled, so the 1-of-32-channel boxes
+    // load at 1/8 speed and the path is slower than the CUDA-core kernel -- opt-in via E2_C1_TC=1)
+    static const bool tc1 = getenv("E2_C1_TC") != nullptr;
+    if (tc1 && d->compute == E2_COMPUTE_TF32 && d->x.c_pitch % 4 == 0 && d->y.c >= 8 &&
+        !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(wf) & 15) && e2_conv_zstack_tc_ok(h, g))
+      return e2_launch_conv_zstack_tc(h, g, s);
+    return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
+  }
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 

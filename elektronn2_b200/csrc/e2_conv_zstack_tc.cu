@@ -36,7 +36,7 @@ constexpr int TX = 16, TY = 8;   // tile x/y extent (16 groups of 8 rows = 128 M
 constexpr int EPI_WARPS = 8;      // two epilogue warps per TMEM lane quadrant, alternating over the chunks of a tile
 constexpr int ZS_THREADS = (4 + EPI_WARPS) * 32;
 constexpr int MAX_PSLOTS = 24;   // NP <= 11 planes per unit, single or double buffered
-constexpr int MAX_WSLOTS = 4;
+constexpr int MAX_WSLOTS = 8;
 
 struct ZsParams {
   int On, Oz, Ox, Oy;
@@ -70,11 +70,12 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void mma4(uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t first_acc) {
+// one 128-byte K block = up to 4 MMAs of K = 8; nk < 4 when the channel count ends inside the block
+__device__ __forceinline__ void mma4(uint32_t acc, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t first_acc, int nk) {
   tc::mma_tf32_ss(acc, ad, bd, idesc, first_acc);
-  tc::mma_tf32_ss(acc, ad + 2, bd + 2, idesc, 1u);
-  tc::mma_tf32_ss(acc, ad + 4, bd + 4, idesc, 1u);
-  tc::mma_tf32_ss(acc, ad + 6, bd + 6, idesc, 1u);
+  if (nk > 1) tc::mma_tf32_ss(acc, ad + 2, bd + 2, idesc, 1u);
+  if (nk > 2) tc::mma_tf32_ss(acc, ad + 4, bd + 4, idesc, 1u);
+  if (nk > 3) tc::mma_tf32_ss(acc, ad + 6, bd + 6, idesc, 1u);
 }
 
 // One stage = one (channel block, in-plane tap): every input plane of the unit times the stacked weights.
@@ -85,7 +86,7 @@ template <int TZ, int KZ, bool WAIT>
 __device__ __forceinline__ void zs_issue_stage(uint64_t a_desc0, uint32_t pstride_enc, uint64_t bd0, uint32_t wblk_enc,
                                                uint32_t acc0, uint32_t bn, uint32_t idesc0, uint32_t idesc_step,
                                                bool first_stage, bool last_stage, uint64_t* pl_full, uint64_t* pl_empty,
-                                               uint32_t par_full) {
+                                               uint32_t par_full, int nk) {
   constexpr int NP = TZ + KZ - 1;
   uint64_t ad = a_desc0;
 #pragma unroll
@@ -101,10 +102,10 @@ __device__ __forceinline__ void zs_issue_stage(uint64_t a_desc0, uint32_t pstrid
     const uint32_t dcol = acc0 + (uint32_t)(TZ - 1 - zl_hi) * bn;
     if (q < TZ && first_stage) {
       // output plane q is touched for the first time (z-tap 0 = block i_lo = 0): overwrite
-      mma4(dcol, ad, bd, idesc0 + idesc_step, 0u);
-      if (nblk > 1) mma4(dcol + bn, ad, bd + wblk_enc, idesc0 + (uint32_t)(nblk - 1) * idesc_step, 1u);
+      mma4(dcol, ad, bd, idesc0 + idesc_step, 0u, nk);
+      if (nblk > 1) mma4(dcol + bn, ad, bd + wblk_enc, idesc0 + (uint32_t)(nblk - 1) * idesc_step, 1u, nk);
     } else {
-      mma4(dcol, ad, bd, idesc0 + (uint32_t)nblk * idesc_step, 1u);
+      mma4(dcol, ad, bd, idesc0 + (uint32_t)nblk * idesc_step, 1u, nk);
     }
     if (last_stage) tc::mma_commit(&pl_empty[q]);   // plane slot free once these MMAs have read it
     ad += pstride_enc;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
         const int s0 = dbl ? (ucount & 1) * p.NP : 0;
         const uint32_t par_full = ((uint32_t)(dbl ? (ucount >> 1) : ucount)) & 1u;
         const uint32_t unit_enc = smP_enc + (uint32_t)s0 * pstride_enc;
+        const int nk = min(4, (p.K - cb * 32 + 7) >> 3);
         int j = 0, k = 0;
         for (int jk = 0; jk < T9; ++jk) {
           long long c1 = clock64();
@@ -261,10 +263,10 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                 for (int q = 0; q < p.NP; ++q) tc::mma_commit(&pl_empty[s0 + q]);
             } else if (jk == 0) {
               zs_issue_stage<TZ_, KZ_, true>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, cb == 0,
-                                             last_stage, pl_full + s0, pl_empty + s0, par_full);
+                                             last_stage, pl_full + s0, pl_empty + s0, par_full, nk);
             } else {
               zs_issue_stage<TZ_, KZ_, false>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, false,
-                                              last_stage, pl_full + s0, pl_empty + s0, par_full);
+                                              last_stage, pl_full + s0, pl_empty + s0, par_full, nk);
             }
             tc::mma_commit(&w_empty[ws]);
           }
@@ -457,37 +459,45 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   // TZ: as many output planes as TMEM (double-buffered) and shared memory allow; among those, the one
   // with the least z-quantisation / wave-quantisation waste
   const int ntx = (g.Ox + TX - 1) / TX, nty = (g.Oy + TY - 1) / TY;
-  int best_tz = 0;
+  // Cost model per tile: CB * T9 stages, each max(MMA cycles, TMA round trip / weight-ring depth), plus one
+  // round trip when the unit's planes are single-buffered.  Layers with few MMAs per stage (K <= 8: one K
+  // slice per plane) are latency-bound unless the weight ring is deep, so TZ may shrink to make room.
+  const double kLatency = 1200.0;
+  const int T9 = g.tx * g.ty, CBn = (g.K + 31) / 32;
+  const double nk_avg = (double)((g.K + 7) / 8) / CBn;   // K = 8 slices per 32-channel block
+  int best_tz = 0, best_w = 0, best_dbl = 0;
   double best_cost = 0;
   for (int tz = 8; tz >= 1; --tz) {
     if (2 * tz * bn > 512) continue;
     const int np = tz + S - 1;
     if (np > 11) continue;
     if (np * p->plane_stride + 2 * p->w_bytes > budget) continue;
+    int rest = budget - np * p->plane_stride;
+    int wsl = std::min(MAX_WSLOTS, rest / p->w_bytes);
+    int dbl = 0;
+    // double buffering the planes is worth more than weight slots beyond the third
+    if (wsl >= 3 && rest - 3 * p->w_bytes >= np * p->plane_stride) {
+      dbl = 1;
+      wsl = std::min(MAX_WSLOTS, (rest - np * p->plane_stride) / p->w_bytes);
+    }
     const int ntz = (g.Oz + tz - 1) / tz;
     const int64_t tiles = (int64_t)g.On * ntz * ntx * nty * ntn;
     const int64_t waves = (tiles + h->sm_count - 1) / h->sm_count;
-    // per-tile time ~ MMA cycles of the planes (np groups; edge groups are narrower) + fixed overhead
     double mma = 0;
     for (int q = 0; q < np; ++q) {
       const int nblk = std::min(q, tz - 1) - std::max(0, q - (S - 1)) + 1;
-      mma += std::max(50.0, nblk * bn / 2.0);
+      const double n = nblk * bn;
+      mma += std::max(std::max(48.0, 32.0 + n / 4.0), n / 2.0);   // operand fetch (128 B/clk) or math bound
     }
-    const double cost = (double)waves * (mma + 30.0);
-    if (best_tz == 0 || cost < best_cost * 0.97) best_tz = tz, best_cost = cost;
+    const double stage = std::max(mma * nk_avg, kLatency / (wsl - 1));
+    const double cost = (double)waves * (CBn * T9 * stage + (dbl ? 0.0 : kLatency) + 200.0);
+    if (best_tz == 0 || cost < best_cost * 0.97) best_tz = tz, best_cost = cost, best_w = wsl, best_dbl = dbl;
   }
   if (best_tz == 0) return false;
   p->TZ = best_tz;
   p->NP = best_tz + S - 1;
-  int rest = budget - p->NP * p->plane_stride - 2 * p->w_bytes;
-  p->nslot = p->NP;
-  p->wslot = 2;
-  // spare memory: a third weight slot first (a stage's MMAs are about as long as one TMA round trip), then
-  // full double buffering of the unit's planes (the next unit loads while this one computes), then more
-  // weight slots
-  if (rest >= p->w_bytes) p->wslot++, rest -= p->w_bytes;
-  if (rest >= p->NP * p->plane_stride) p->nslot = 2 * p->NP, rest -= p->NP * p->plane_stride;
-  while (p->wslot < MAX_WSLOTS && rest >= p->w_bytes) p->wslot++, rest -= p->w_bytes;
+  p->nslot = best_dbl ? 2 * p->NP : p->NP;
+  p->wslot = best_w;
   p->acc_bufs = 2;
   int cols = 32;
   while (cols < p->acc_bufs * p->TZ * bn) cols *= 2;

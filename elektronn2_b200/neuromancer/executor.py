@@ -17,6 +17,7 @@ Data layout in HBM:
                             front to back (bucketed all-reduce overlaps with wgrad)
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -242,6 +243,19 @@ class Plan(object):
     def _plan_conv(self, n):
         h = self.h
         x = self.val[n.parent]
+        if (x.desc.c == 1 and x.desc.c_pitch == 1 and self.compute == 'tf32' and n.n_f >= 8
+                and os.environ.get('E2_C1_TC')):
+            # dense single-channel input -> 16-byte rows (tf32-rounded) so the first layer runs on the
+            # TMA / tcgen05 path; the copy is ~1 % of the layer's output traffic
+            key = ('repitch', n.parent)
+            if key not in self.aux:
+                d = x.desc
+                x4 = DevTensor(d.n, d.z, d.x, d.y, 1, c_pitch=4, device=self.device)
+                self.aux[key] = x4
+                self._f('repitch:' + n.parent.name,
+                        lambda x=x, x4=x4: h.call('e2_repitch', C.byref(x.desc), x.ptr(), C.byref(x4.desc), x4.ptr(), 1,
+                                                  h.stream()), 0, 20 * _nel(x))
+            x = self.aux[key]
         y = self.val[n] if n in self.val else self._new(n)
         self.val[n] = y
         pooled = any(p > 1 for p in n.pool_shape)

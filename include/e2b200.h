@@ -74,6 +74,10 @@ int64_t e2_launch_count(const e2_handle* h);
  * here they are converted once at the edge.  ncdhw is dense C-contiguous. */
 int e2_ncdhw_to_ndhwc(e2_handle* h, const e2_tensor* t, const float* ncdhw, float* ndhwc, void* stream);
 int e2_ndhwc_to_ncdhw(e2_handle* h, const e2_tensor* t, const float* ndhwc, float* ncdhw, void* stream);
+/* same tensor, different channel pitch (pad lanes zero); round_tf32 != 0 rounds the values to tf32.
+ * Hands the dense single-channel raw input to the TMA/tcgen05 path, which needs 16-byte rows. */
+int e2_repitch(e2_handle* h, const e2_tensor* src_t, const float* src, const e2_tensor* dst_t, float* dst,
+               int32_t round_tf32, void* stream);
 /* predict_dense input scaling, node_basic.py:904-910: uint8 -> float32 / 255 (count elements) */
 int e2_u8_to_f32(e2_handle* h, const uint8_t* src, float* dst, int64_t count, float scale, void* stream);
 /* predict_dense as_uint8 output, node_basic.py:990-996: trunc(p*255) */
