@@ -651,6 +651,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
     if (tc1 && d->compute == E2_COMPUTE_TF32 && d->x.c_pitch % 4 == 0 && d->y.c >= 8 &&
         !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(wf) & 15) && e2_conv_zstack_tc_ok(h, g))
       return e2_launch_conv_zstack_tc(h, g, s);
+    if (e2_conv_c1_fwd_reg_ok(g)) return e2_launch_conv_c1_fwd_reg(h, g, s);
     return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
   }
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
@@ -677,7 +678,9 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   conv_wgrad_problem(d, x, dy, dw, &g);
   bool db_done = false;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
+  if (d->x.c == 1 && e2_conv_c1_wgrad_reg_ok(g))
+    rc = e2_launch_conv_c1_wgrad_reg(h, g, db, s), db_done = (db != nullptr);
+  else if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
     rc = e2_launch_conv_c1_wgrad_line(h, g, s);
   else if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
     rc = e2_launch_conv_c1_wgrad(h, g, s);

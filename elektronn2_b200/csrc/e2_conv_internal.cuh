@@ -45,6 +45,11 @@ bool e2_conv_c1_fwd_line_ok(const GatherGemm& g);
 int e2_launch_conv_c1_fwd_line(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 bool e2_conv_c1_wgrad_line_ok(const ReduceGemm& g);
 int e2_launch_conv_c1_wgrad_line(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+// register-tiled first-layer kernels (compile-time taps); wgrad fuses the bias gradient
+bool e2_conv_c1_fwd_reg_ok(const GatherGemm& g);
+int e2_launch_conv_c1_fwd_reg(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+bool e2_conv_c1_wgrad_reg_ok(const ReduceGemm& g);
+int e2_launch_conv_c1_wgrad_reg(e2_handle* h, const ReduceGemm& g, float* db, cudaStream_t s);
 int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pitch, float* db, cudaStream_t s);
 
 // tcgen05 path (e2_conv_tc.cu)

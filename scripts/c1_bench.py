@@ -36,5 +36,6 @@ for pitch in (1, 4):
     f = t.time_ms(op.fwd, 10)
     wg = t.time_ms(lambda: op.wgrad(dy, dw, db), 10)
     print('pitch %d: fwd %.3f ms (%.0f GB/s out)  wgrad %.3f ms' % (pitch, f, yd.desc.floats * 4 / f / 1e6, wg), flush=True)
+print('checksums: y %.6e  dw %.6e  db %.6e  |y| %.6e' % (float(res[1][0].double().sum()), float(res[1][1].double().sum()), float(res[1][2].double().sum()), float(res[1][0].double().abs().sum())))
 print('fwd rel diff pitch4 vs pitch1: %.2e   wgrad %.2e  db %.2e' % (t.rel(res[4][0], res[1][0]), t.rel(res[4][1], res[1][1]),
                                                                     t.rel(res[4][2], res[1][2])))
