@@ -333,6 +333,68 @@ __global__ void __launch_bounds__(128) k_wgrad_halo_reduce(const WhParams p, int
   }
 }
 
+// Same reduction for the conv layout (out_mode 0), staged through shared memory so that the global writes are
+// contiguous: a block owns 4 r-channels x one 32-channel s block and ALL taps, i.e. for each r one run of
+// 32*T consecutive floats of dw.  blockDim = 128 * kz (thread = TMEM lane x z-tap).
+__global__ void __launch_bounds__(512) k_wgrad_halo_reduce_rows(const WhParams p, int units, int splits, int w_blocks) {
+  extern __shared__ float outs[];                    // [4][32][T]
+  if ((int)blockIdx.x >= w_blocks) {
+    // bias gradient: sum the per-split column sums
+    const int i = ((int)blockIdx.x - w_blocks) * (int)blockDim.x + (int)threadIdx.x;
+    if (i >= p.n_rc * p.n_cols) return;
+    const int rc = i / p.n_cols, c = i % p.n_cols;
+    const int r = rc * p.n_cols + c;
+    if (r >= p.R) return;
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += __ldcg(p.db_ws + ((size_t)sp * p.n_rc + rc) * p.n_cols + c);
+    p.db[r] = acc;
+    return;
+  }
+  const int T = p.kz * p.kx * p.ky;
+  const int lane = threadIdx.x & 127, i3 = threadIdx.x >> 7;
+  int b = blockIdx.x;
+  const int c4 = b % (p.n_cols / 4);
+  b /= (p.n_cols / 4);
+  const int sc = b % p.n_sc;
+  const int rc = b / p.n_sc;
+  const int unit = (rc * p.n_sc + sc) * p.kz + i3;
+  const size_t per_cta = (size_t)p.n_acc * (p.n_cols / 4) * 128;
+  const size_t stride = (size_t)units * per_cta;
+  const int sl = lane & 31;
+  for (int a = 0; a < p.n_acc; ++a) {
+    const int j3 = a / p.kgroups, kg = a % p.kgroups;
+    const int k3 = kg * 4 + (lane >> 5);
+    if (k3 >= p.ky) continue;
+    const float4* src = reinterpret_cast<const float4*>(p.ws) + (size_t)unit * per_cta + (size_t)(a * (p.n_cols / 4) + c4) * 128 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      const float4 v0 = __ldcg(src + (size_t)sp * stride), v1 = __ldcg(src + (size_t)(sp + 1) * stride);
+      const float4 v2 = __ldcg(src + (size_t)(sp + 2) * stride), v3 = __ldcg(src + (size_t)(sp + 3) * stride);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x), acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z), acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; sp < splits; ++sp) {
+      const float4 v = __ldcg(src + (size_t)sp * stride);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    const int tflip = ((p.kz - 1 - i3) * p.kx + (p.kx - 1 - j3)) * p.ky + (p.ky - 1 - k3);
+    outs[(0 * 32 + sl) * T + tflip] = acc.x;
+    outs[(1 * 32 + sl) * T + tflip] = acc.y;
+    outs[(2 * 32 + sl) * T + tflip] = acc.z;
+    outs[(3 * 32 + sl) * T + tflip] = acc.w;
+  }
+  __syncthreads();
+  const int s0 = sc * 32;
+  const int ns = min(32, p.S - s0);
+  for (int e = 0; e < 4; ++e) {
+    const int r = rc * p.n_cols + c4 * 4 + e;
+    if (r >= p.R) break;
+    float* dst = p.W + ((int64_t)r * p.S + s0) * T;
+    for (int i = threadIdx.x; i < ns * T; i += blockDim.x) dst[i] = outs[e * 32 * T + i];
+  }
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -495,11 +557,23 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t 
   h->launches++;
   E2_CUDA_CHECK(h, "wgrad_halo_tc");
   if (p.ws) {
-    const int w_blocks = units * p.n_acc * (p.n_cols / 4);
     const int db_blocks = p.db_ws ? (p.n_rc * p.n_cols + 127) / 128 : 0;
-    k_wgrad_halo_reduce<<<(unsigned)(w_blocks + db_blocks), 128, 0, s>>>(p, units, splits, w_blocks);
-    h->launches++;
-    E2_CUDA_CHECK(h, "wgrad_halo_reduce");
+    // few splits: the scattered 4-byte stores dominate -> row-staged variant; many splits (small dw, long
+    // sums): keep the variant with one block per (unit, accumulator, 4 columns)
+    if (p.out_mode == 0 && p.kz <= 4 && splits <= 8 && (size_t)4 * 32 * T * sizeof(float) <= 48 * 1024 &&
+        env_int("E2_WGRAD_REDUCE_ROWS", 1)) {
+      const int w_blocks = p.n_rc * p.n_sc * (p.n_cols / 4);
+      const int dbb = p.db_ws ? (p.n_rc * p.n_cols + 128 * p.kz - 1) / (128 * p.kz) : 0;
+      k_wgrad_halo_reduce_rows<<<(unsigned)(w_blocks + dbb), 128 * p.kz, (size_t)4 * 32 * T * sizeof(float), s>>>(
+          p, units, splits, w_blocks);
+      h->launches++;
+      E2_CUDA_CHECK(h, "wgrad_halo_reduce_rows");
+    } else {
+      const int w_blocks = units * p.n_acc * (p.n_cols / 4);
+      k_wgrad_halo_reduce<<<(unsigned)(w_blocks + db_blocks), 128, 0, s>>>(p, units, splits, w_blocks);
+      h->launches++;
+      E2_CUDA_CHECK(h, "wgrad_halo_reduce");
+    }
   }
   return E2_OK;
 }
