@@ -170,6 +170,80 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
                                                            __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
         continue;
       }
+      const bool fast_shuffle = p.shuffle && (p.Fo & 31) == 0 && n0 + c0 < p.N;
+      if ((!p.shuffle || fast_shuffle) && (p.c_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+          (!p.gate || (reinterpret_cast<uintptr_t>(p.gate) & 15) == 0)) {
+        // Coalesced path.  A lane owns one ROW of the tile (32 channels = 128 B); storing it directly makes a
+        // warp instruction touch 32 different lines with 16 B each (~300-400 GB/s).  The chunk is transposed
+        // through the (now idle) operand ring so that 8 lanes cover one row: every store / gate / accumulate
+        // access is then a full 128-byte line, and bias / activation run in the transposed domain.
+        uint8_t* st = smA + (warp - 2) * 4096;
+        const int r8 = lane & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ r8) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        const int pc = lane & 7;
+        const int nb = n0 + c0 + pc * 4;                 // first of this lane's 4 columns
+        int ch = nb, k3 = 0, j3 = 0, i3 = 0;
+        if (p.shuffle) {
+          const int tp = (n0 + c0) / p.Fo;
+          ch = nb - tp * p.Fo;
+          k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+        }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          const int nlim = p.shuffle ? p.Fo : p.N;
+          b4.x = ch + 0 < nlim ? __ldg(p.bias + ch + 0) : 0.f, b4.y = ch + 1 < nlim ? __ldg(p.bias + ch + 1) : 0.f;
+          b4.z = ch + 2 < nlim ? __ldg(p.bias + ch + 2) : 0.f, b4.w = ch + 3 < nlim ? __ldg(p.bias + ch + 3) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + (lane >> 3);           // row inside this warp's 32
+          const int rr = q * 32 + rl;
+          const int ry = rr % p.ty, rx = (rr / p.ty) % p.tx, rz = rr / (p.ty * p.tx);
+          const int pz_ = z0 + rz, px_ = x0 + rx, py_ = y0 + ry;
+          if (pz_ >= p.Oz || px_ >= p.Ox || py_ >= p.Oy || nb >= p.N) continue;
+          int64_t ofs;
+          if (p.shuffle)
+            ofs = ((((int64_t)in_ * (p.Oz * p.pz) + pz_ * p.pz + i3) * (p.Ox * p.px) + px_ * p.px + j3) * (p.Oy * p.py) +
+                   py_ * p.py + k3) * p.c_pitch + ch;
+          else
+            ofs = ((((int64_t)in_ * p.Oz + pz_) * p.Ox + px_) * p.Oy + py_) * p.c_pitch + nb;
+          const float4 raw = *reinterpret_cast<const float4*>(st + rl * 128 + ((pc ^ (rl & 7)) << 4));
+          float v[4] = {raw.x + b4.x, raw.y + b4.y, raw.z + b4.z, raw.w + b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = e2_apply_act(v[e], p.act);
+          const bool full = nb + 3 < p.N;
+          if (full) {
+            if (p.gate) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + ofs));
+              if (!(g4.x > 0.f)) v[0] = 0.f;
+              if (!(g4.y > 0.f)) v[1] = 0.f;
+              if (!(g4.z > 0.f)) v[2] = 0.f;
+              if (!(g4.w > 0.f)) v[3] = 0.f;
+            }
+            if (p.accumulate) {
+              const float4 c4 = *reinterpret_cast<const float4*>(p.C + ofs);
+              v[0] += c4.x, v[1] += c4.y, v[2] += c4.z, v[3] += c4.w;
+            }
+            if (p.round_tf32) v[0] = e2_round_tf32(v[0]), v[1] = e2_round_tf32(v[1]), v[2] = e2_round_tf32(v[2]), v[3] = e2_round_tf32(v[3]);
+            *reinterpret_cast<float4*>(p.C + ofs) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (nb + e >= p.N) continue;
+              float a = v[e];
+              if (p.gate && !(__ldg(p.gate + ofs + e) > 0.f)) a = 0.f;
+              if (p.accumulate) a += p.C[ofs + e];
+              if (p.round_tf32) a = e2_round_tf32(a);
+              p.C[ofs + e] = a;
+            }
+          }
+        }
+        __syncwarp();     // the staging tile is rewritten by the next chunk
+        continue;
+      }
       if (!row_ok) continue;
       if (!p.shuffle) {
         float* out = p.C + pos * p.c_pitch + n0 + c0;

@@ -261,9 +261,22 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
   p.a_slots = a_slots;
   p.tiles_total = g.Mn * p.ntz * p.ntx * p.nty;
   const int units = p.n_rc * p.n_sc * p.n_gs;
-  int splits = (2 * h->sm_count + units - 1) / units;
-  if (splits > p.tiles_total) splits = p.tiles_total;
-  if (splits < 1) splits = 1;
+  // Position splits: more CTAs shorten the MMA phase but every split adds |dw| fp32 atomics (measured
+  // ~32 per clock chip-wide for this scattered pattern).  Small layers with large dw (the upconvs) were
+  // spending 90 % of their time in atomics at 2 CTAs per SM; pick the split count that minimises the sum.
+  int splits = 1;
+  {
+    const double per_tile = groups_max * (KP / 8) * 70.0;                       // MMA cycles per position tile
+    const double atom_per_split = (double)units * groups_max * 128.0 * ncols / 32.0;
+    double best = -1;
+    const int smax = std::max(1, std::min(p.tiles_total, (2 * h->sm_count + units - 1) / units));
+    for (int sp = 1; sp <= smax; ++sp) {
+      const int tps = (p.tiles_total + sp - 1) / sp;
+      const int waves = (units * sp + h->sm_count - 1) / h->sm_count;
+      const double t = waves * (tps * per_tile + 3000.0) + sp * atom_per_split;
+      if (best < 0 || t < best) best = t, splits = sp;
+    }
+  }
   p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
   p.W = g.W, p.out_mode = g.out_mode;
