@@ -50,14 +50,33 @@ static inline int e2_grid_1d(int64_t work, int threads, int sm_count, int max_wa
   return (int)g;
 }
 
-__device__ __forceinline__ float e2_apply_act(float v, int act) {
+// Division of a small index (< 2^20) by a launch-constant divisor (< 4096) as one multiply-high; m == 0 selects
+// the plain division (divisor 1 or out of the exact range).
+struct E2FastDiv {
+  uint32_t m, d;
+  __device__ __forceinline__ uint32_t div(uint32_t t) const { return m ? __umulhi(t, m) : t / d; }
+};
+static inline E2FastDiv e2_fastdiv(uint32_t d, uint64_t max_t) {
+  E2FastDiv f;
+  f.d = d;
+  f.m = (d > 1 && d < 4096 && max_t < (1u << 20)) ? (uint32_t)(((1ull << 32) + d - 1) / d) : 0u;
+  return f;
+}
+
+// lin / relu (every BASELINE config) stay inline; the transcendental activations live behind a call so that
+// unrolled epilogues do not carry a copy of tanhf / expf per element (instruction-cache footprint).
+static __device__ __noinline__ float e2_apply_act_slow(float v, int act) {
   switch (act) {
-    case E2_ACT_RELU: return v > 0.f ? v : 0.f;
     case E2_ACT_TANH: return tanhf(v);
     case E2_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
     case E2_ACT_ABS: return fabsf(v);
     default: return v;
   }
+}
+__device__ __forceinline__ float e2_apply_act(float v, int act) {
+  if (act == E2_ACT_LIN) return v;
+  if (act == E2_ACT_RELU) return v > 0.f ? v : 0.f;
+  return e2_apply_act_slow(v, act);
 }
 
 // round-to-nearest fp32 -> tf32 (kept in an fp32 container)

@@ -678,6 +678,7 @@ extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
     fake.sm_count = sm_count;
     conv_wgrad_problem(d, dummy, dummy, dummy, &g);
     if (e2_wgrad_halo_tc_ok(&fake, g)) *bytes = e2_wgrad_halo_workspace_bytes(sm_count, g);
+    else if (e2_reduce_gemm_tc_ok(&fake, g)) *bytes = e2_reduce_gemm_tc_workspace_bytes(sm_count, g);
     // forward / dgrad on the tap kernel: split-K partial tiles for layers with few output positions
     GatherGemm f, b;
     conv_fwd_problem(d, dummy, dummy, nullptr, dummy, &f);
@@ -744,7 +745,7 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   else if (d->compute == E2_COMPUTE_TF32 && e2_wgrad_halo_tc_ok(h, g))
     rc = e2_launch_wgrad_halo_tc(h, g, ws, ws_bytes, db, &db_done, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))
-    rc = e2_launch_reduce_gemm_tc(h, g, s);
+    rc = e2_launch_reduce_gemm_tc(h, g, ws, ws_bytes, s);
   else
     rc = e2_launch_reduce_gemm_ffma(h, g, s);
   if (rc) return rc;
@@ -785,6 +786,19 @@ static void upconv_dgrad_problem(const e2_upconv_desc* d, const float* dy, const
   g->round_tf32 = (d->compute == E2_COMPUTE_TF32);
 }
 
+// dw[o][c][tap] = sum_m x[m][c] * dy[m*p + tap][o]
+static void upconv_wgrad_problem(const e2_upconv_desc* d, const float* x, const float* dy, float* dw, ReduceGemm* gp) {
+  ReduceGemm& g = *gp;
+  memset(&g, 0, sizeof(g));
+  g.P = x, g.p_pitch = d->x.c_pitch, g.R = d->x.c;
+  g.Mn = d->x.n, g.Mz = d->x.z, g.Mx = d->x.x, g.My = d->x.y;
+  g.Q = dy, g.q_pitch = d->y.c_pitch, g.S = d->y.c;
+  g.Qn = d->y.n, g.Qz = d->y.z, g.Qx = d->y.x, g.Qy = d->y.y;
+  g.tz = d->pz, g.tx = d->px, g.ty = d->py;
+  g.sz = d->pz, g.sx = d->px, g.sy = d->py;
+  g.W = dw, g.out_mode = 1;
+}
+
 extern "C" int e2_upconv3d_workspace_size(const e2_upconv_desc* d, size_t* bytes) {
   if (!d || !bytes) return E2_ERR_INVALID;
   *bytes = 0;
@@ -799,6 +813,9 @@ extern "C" int e2_upconv3d_workspace_size(const e2_upconv_desc* d, size_t* bytes
   upconv_dgrad_problem(d, dummy, dummy, dummy, nullptr, &b);
   for (const GatherGemm* q : {&f, &b})
     if (e2_gather_gemm_tc_ok(&fake, *q)) *bytes = std::max(*bytes, e2_gather_gemm_tc_workspace_bytes(sm_count, *q));
+  ReduceGemm w;
+  upconv_wgrad_problem(d, dummy, dummy, dummy, &w);
+  if (e2_reduce_gemm_tc_ok(&fake, w)) *bytes = std::max(*bytes, e2_reduce_gemm_tc_workspace_bytes(sm_count, w));
   return E2_OK;
 }
 
@@ -832,19 +849,11 @@ extern "C" int e2_upconv3d_wgrad(e2_handle* h, const e2_upconv_desc* d, const fl
   int rc = check_upconv(h, d);
   if (rc) return rc;
   E2_REQUIRE(h, x && dy && dw, "upconv3d_wgrad: null pointer");
-  // dw[o][c][tap] = sum_m x[m][c] * dy[m*p + tap][o]
   ReduceGemm g;
-  memset(&g, 0, sizeof(g));
-  g.P = x, g.p_pitch = d->x.c_pitch, g.R = d->x.c;
-  g.Mn = d->x.n, g.Mz = d->x.z, g.Mx = d->x.x, g.My = d->x.y;
-  g.Q = dy, g.q_pitch = d->y.c_pitch, g.S = d->y.c;
-  g.Qn = d->y.n, g.Qz = d->y.z, g.Qx = d->y.x, g.Qy = d->y.y;
-  g.tz = d->pz, g.tx = d->px, g.ty = d->py;
-  g.sz = d->pz, g.sx = d->px, g.sy = d->py;
-  g.W = dw, g.out_mode = 1;
+  upconv_wgrad_problem(d, x, dy, dw, &g);
   cudaStream_t s = (cudaStream_t)stream;
   if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))
-    rc = e2_launch_reduce_gemm_tc(h, g, s);
+    rc = e2_launch_reduce_gemm_tc(h, g, ws, ws_bytes, s);
   else
     rc = e2_launch_reduce_gemm_ffma(h, g, s);
   if (rc) return rc;

@@ -66,7 +66,9 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // picks zstack / plane kernel / tap kernel / CUDA cores for a TF32 request
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s);
 bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
-int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s);
+// ws (nullable): per-CTA partial tiles + deterministic reduce kernel; without it fp32 atomics
+int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t e2_reduce_gemm_tc_workspace_bytes(int sm_count, const ReduceGemm& g);
 // halo-reuse wgrad (e2_wgrad_halo_tc.cu): x tile loaded once, taps are shifted descriptor views
 bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g);
 // db (nullable): bias gradient = column sums of P; *db_done tells the caller whether the kernel produced it

@@ -140,14 +140,33 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
     }
   } else {
     // ----------------------------------------------------------------- epilogue
+    // A lane of tcgen05.ld owns one ROW of the tile (32 channels = 128 B); storing that directly makes a warp
+    // instruction touch 32 different lines.  Every chunk is therefore transposed through the (now idle) operand
+    // ring so that 8 lanes cover one row: each store / gate / accumulate access is a full 128-byte line, and bias /
+    // activation run in the transposed domain.  Row offsets are decoded once per tile; the chunk loop is kept
+    // rolled -- an unrolled version of this epilogue was 17 k instructions and instruction-fetch bound.
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;          // row of the tile == position inside the box
-    const int ly = row % p.ty, lx = (row / p.ty) % p.tx, lz = row / (p.ty * p.tx);
-    const int oz = z0 + lz, ox = x0 + lx, oy = y0 + ly;
-    const bool row_ok = oz < p.Oz && ox < p.Ox && oy < p.Oy;
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
-    const int64_t pos = (((int64_t)in_ * p.Oz + oz) * p.Ox + ox) * p.Oy + oy;
+    uint8_t* st = smA + (warp - 2) * 4096;
+    const int r8 = lane & 7, pc = lane & 7, rsub = lane >> 3;
+    const bool vec_ok = (p.N & 3) == 0 && (p.c_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!p.gate || (reinterpret_cast<uintptr_t>(p.gate) & 15) == 0) && (!p.shuffle || (p.Fo & 3) == 0);
+    // vector path: this lane serves rows rsub, rsub+4, ... of the warp's 32; scalar path: its own row `lane`
+    int64_t rowofs[8];
+    uint32_t rowmask = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = q * 32 + (vec_ok ? it * 4 + rsub : lane);
+      const int ry = rr % p.ty, rx = (rr / p.ty) % p.tx, rz = rr / (p.ty * p.tx);
+      const int pz_ = z0 + rz, px_ = x0 + rx, py_ = y0 + ry;
+      if (pz_ < p.Oz && px_ < p.Ox && py_ < p.Oy) rowmask |= 1u << it;
+      rowofs[it] = p.shuffle ? ((((int64_t)in_ * (p.Oz * p.pz) + pz_ * p.pz) * (p.Ox * p.px) + px_ * p.px) * (p.Oy * p.py) +
+                                py_ * p.py) * p.c_pitch
+                             : ((((int64_t)in_ * p.Oz + pz_) * p.Ox + px_) * p.Oy + py_) * p.c_pitch;
+      if (!vec_ok && it == 0) break;
+    }
+#pragma unroll 1
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       if (p.BN - c0 >= 32) {
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
         // split-K: raw accumulators, one coalesced float4 per row and 4 columns; the reduce kernel sums
         // the splits and applies the epilogue
         float4* dst = reinterpret_cast<float4*>(p.part) +
-                      ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (p.BN / 4) * BM + row;
+                      ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (p.BN / 4) * BM + q * 32 + lane;
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4)
           if (c0 + j4 < p.BN)
@@ -170,154 +189,68 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
                                                            __uint_as_float(r[j4 + 2]), __uint_as_float(r[j4 + 3]));
         continue;
       }
-      const bool fast_shuffle = p.shuffle && (p.Fo & 31) == 0 && n0 + c0 < p.N;
-      if ((!p.shuffle || fast_shuffle) && (p.c_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-          (!p.gate || (reinterpret_cast<uintptr_t>(p.gate) & 15) == 0)) {
-        // Coalesced path.  A lane owns one ROW of the tile (32 channels = 128 B); storing it directly makes a
-        // warp instruction touch 32 different lines with 16 B each (~300-400 GB/s).  The chunk is transposed
-        // through the (now idle) operand ring so that 8 lanes cover one row: every store / gate / accumulate
-        // access is then a full 128-byte line, and bias / activation run in the transposed domain.
-        uint8_t* st = smA + (warp - 2) * 4096;
-        const int r8 = lane & 7;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ r8) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        const int pc = lane & 7;
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(st + lane * 128 + ((j ^ r8) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      if (vec_ok) {
         const int nb = n0 + c0 + pc * 4;                 // first of this lane's 4 columns
-        int ch = nb, k3 = 0, j3 = 0, i3 = 0;
-        if (p.shuffle) {
-          const int tp = (n0 + c0) / p.Fo;
-          ch = nb - tp * p.Fo;
-          k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
-        }
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) {
-          const int nlim = p.shuffle ? p.Fo : p.N;
-          b4.x = ch + 0 < nlim ? __ldg(p.bias + ch + 0) : 0.f, b4.y = ch + 1 < nlim ? __ldg(p.bias + ch + 1) : 0.f;
-          b4.z = ch + 2 < nlim ? __ldg(p.bias + ch + 2) : 0.f, b4.w = ch + 3 < nlim ? __ldg(p.bias + ch + 3) : 0.f;
-        }
+        if (nb < p.N) {
+          int ch = nb;
+          int64_t colofs = nb;
+          if (p.shuffle) {
+            const int tp = nb / p.Fo;
+            ch = nb - tp * p.Fo;
+            const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+            colofs = (((int64_t)i3 * (p.Ox * p.px) + j3) * (p.Oy * p.py) + k3) * p.c_pitch + ch;
+          }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = make_float4(__ldg(p.bias + ch), __ldg(p.bias + ch + 1), __ldg(p.bias + ch + 2), __ldg(p.bias + ch + 3));
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rl = it * 4 + (lane >> 3);           // row inside this warp's 32
-          const int rr = q * 32 + rl;
-          const int ry = rr % p.ty, rx = (rr / p.ty) % p.tx, rz = rr / (p.ty * p.tx);
-          const int pz_ = z0 + rz, px_ = x0 + rx, py_ = y0 + ry;
-          if (pz_ >= p.Oz || px_ >= p.Ox || py_ >= p.Oy || nb >= p.N) continue;
-          int64_t ofs;
-          if (p.shuffle)
-            ofs = ((((int64_t)in_ * (p.Oz * p.pz) + pz_ * p.pz + i3) * (p.Ox * p.px) + px_ * p.px + j3) * (p.Oy * p.py) +
-                   py_ * p.py + k3) * p.c_pitch + ch;
-          else
-            ofs = ((((int64_t)in_ * p.Oz + pz_) * p.Ox + px_) * p.Oy + py_) * p.c_pitch + nb;
-          const float4 raw = *reinterpret_cast<const float4*>(st + rl * 128 + ((pc ^ (rl & 7)) << 4));
-          float v[4] = {raw.x + b4.x, raw.y + b4.y, raw.z + b4.z, raw.w + b4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = e2_apply_act(v[e], p.act);
-          const bool full = nb + 3 < p.N;
-          if (full) {
+          for (int it = 0; it < 8; ++it) {
+            if (!((rowmask >> it) & 1u)) continue;
+            const int rl = it * 4 + rsub;
+            const int64_t ofs = rowofs[it] + colofs;
+            const float4 raw = *reinterpret_cast<const float4*>(st + rl * 128 + ((pc ^ (rl & 7)) << 4));
+            float4 v = make_float4(e2_apply_act(raw.x + b4.x, p.act), e2_apply_act(raw.y + b4.y, p.act),
+                                   e2_apply_act(raw.z + b4.z, p.act), e2_apply_act(raw.w + b4.w, p.act));
             if (p.gate) {
               const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + ofs));
-              if (!(g4.x > 0.f)) v[0] = 0.f;
-              if (!(g4.y > 0.f)) v[1] = 0.f;
-              if (!(g4.z > 0.f)) v[2] = 0.f;
-              if (!(g4.w > 0.f)) v[3] = 0.f;
+              v.x = g4.x > 0.f ? v.x : 0.f, v.y = g4.y > 0.f ? v.y : 0.f;
+              v.z = g4.z > 0.f ? v.z : 0.f, v.w = g4.w > 0.f ? v.w : 0.f;
             }
             if (p.accumulate) {
               const float4 c4 = *reinterpret_cast<const float4*>(p.C + ofs);
-              v[0] += c4.x, v[1] += c4.y, v[2] += c4.z, v[3] += c4.w;
+              v.x += c4.x, v.y += c4.y, v.z += c4.z, v.w += c4.w;
             }
-            if (p.round_tf32) v[0] = e2_round_tf32(v[0]), v[1] = e2_round_tf32(v[1]), v[2] = e2_round_tf32(v[2]), v[3] = e2_round_tf32(v[3]);
-            *reinterpret_cast<float4*>(p.C + ofs) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (nb + e >= p.N) continue;
-              float a = v[e];
-              if (p.gate && !(__ldg(p.gate + ofs + e) > 0.f)) a = 0.f;
-              if (p.accumulate) a += p.C[ofs + e];
-              if (p.round_tf32) a = e2_round_tf32(a);
-              p.C[ofs + e] = a;
-            }
+            if (p.round_tf32) v.x = e2_round_tf32(v.x), v.y = e2_round_tf32(v.y), v.z = e2_round_tf32(v.z), v.w = e2_round_tf32(v.w);
+            *reinterpret_cast<float4*>(p.C + ofs) = v;
           }
         }
-        __syncwarp();     // the staging tile is rewritten by the next chunk
-        continue;
-      }
-      if (!row_ok) continue;
-      if (!p.shuffle) {
-        float* out = p.C + pos * p.c_pitch + n0 + c0;
-        const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n = n0 + c0 + j4 + j;
-            float a = __uint_as_float(r[j4 + j]);
-            if (n < p.N) {
-              if (p.bias) a += __ldg(p.bias + n);
-              a = e2_apply_act(a, p.act);
-              if (p.gate && !(__ldg(p.gate + (out - p.C) + j4 + j) > 0.f)) a = 0.f;
-              if (p.accumulate) a += out[j4 + j];
-              if (p.round_tf32) a = e2_round_tf32(a);
-            }
-            v[j] = a;
-          }
-          if (vec && n0 + c0 + j4 + 3 < p.N) {
-            *reinterpret_cast<float4*>(out + j4) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n0 + c0 + j4 + j < p.N) out[j4 + j] = v[j];
-          }
-        }
-      } else if ((p.Fo & 31) == 0 && (p.c_pitch & 3) == 0 && n0 + c0 < p.N) {
-        // upconv forward, fast path: the 32 columns of this chunk are 32 consecutive channels of ONE
-        // tap -> one contiguous 128-byte run at the shuffled output position
-        const int n = n0 + c0;
-        const int tp = n / p.Fo, ch = n - tp * p.Fo;
-        const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
-        const int64_t ofs = ((((int64_t)in_ * (p.Oz * p.pz) + oz * p.pz + i3) * (p.Ox * p.px) + ox * p.px + j3) *
-                                 (p.Oy * p.py) + oy * p.py + k3) * p.c_pitch + ch;
-        float* out = p.C + ofs;
-        const bool vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = __uint_as_float(r[j4 + j]);
-            if (p.bias) a += __ldg(p.bias + ch + j4 + j);
-            a = e2_apply_act(a, p.act);
-            if (p.round_tf32) a = e2_round_tf32(a);
-            v[j] = a;
-          }
-          if (vec) {
-            *reinterpret_cast<float4*>(out + j4) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[j4 + j] = v[j];
-          }
-        }
-      } else {
-        // upconv forward: column n = tap' * Fo + o  ->  position (pos*p + tap'), channel o
-#pragma unroll
+      } else if (rowmask & 1u) {
+        // scalar path (channel counts / pointers that are not 16-byte friendly): one element at a time
+#pragma unroll 1
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + c0 + j;
-          if (n >= p.N) continue;
-          const int tp = n / p.Fo, ch = n - tp * p.Fo;
-          const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
-          const int64_t ofs = ((((int64_t)in_ * (p.Oz * p.pz) + oz * p.pz + i3) * (p.Ox * p.px) + ox * p.px + j3) *
-                                   (p.Oy * p.py) + oy * p.py + k3) * p.c_pitch + ch;
-          float a = __uint_as_float(r[j]);
+          if (n >= p.N) break;
+          int ch = n;
+          int64_t ofs = rowofs[0] + n;
+          if (p.shuffle) {
+            const int tp = n / p.Fo;
+            ch = n - tp * p.Fo;
+            const int k3 = tp % p.py, j3 = (tp / p.py) % p.px, i3 = tp / (p.py * p.px);
+            ofs = rowofs[0] + (((int64_t)i3 * (p.Ox * p.px) + j3) * (p.Oy * p.py) + k3) * p.c_pitch + ch;
+          }
+          float a = *reinterpret_cast<const float*>(st + lane * 128 + (((j >> 2) ^ r8) << 4) + ((j & 3) << 2));
           if (p.bias) a += __ldg(p.bias + ch);
           a = e2_apply_act(a, p.act);
+          if (p.gate && !(__ldg(p.gate + ofs) > 0.f)) a = 0.f;
           if (p.accumulate) a += p.C[ofs];
           if (p.round_tf32) a = e2_round_tf32(a);
           p.C[ofs] = a;
         }
       }
+      __syncwarp();     // the staging tile is rewritten by the next chunk
     }
   }
   tc::tc_fence_before();

@@ -58,50 +58,57 @@ struct PoolP {
 };
 
 // ------------------------------------------------------------------ max-pool forward
+// One block per OUTPUT row (n, zo, xo): the row's Yo*C outputs and each of its window taps are contiguous in
+// HBM, the block decomposes its row index once, and a thread needs a single multiply-high to split its item
+// into (yo, channel group) -- the 64-bit div/mod chain of a flat index cost more than the memory traffic.
 template <int V>
-__global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, const float* __restrict__ x, const float* __restrict__ bias,
-                                                     float* __restrict__ y, int* __restrict__ amax) {
+__global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, E2FastDiv dcv, const float* __restrict__ x,
+                                                     const float* __restrict__ bias, float* __restrict__ y,
+                                                     int* __restrict__ amax) {
   const int cv = p.C / V;
-  const int64_t total = (int64_t)p.n * p.Zo * p.Xo * p.Yo * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V;
-    int64_t pos = i / cv;
-    int yo = (int)(pos % p.Yo);
-    int64_t t = pos / p.Yo;
-    int xo = (int)(t % p.Xo);
-    t /= p.Xo;
-    int zo = (int)(t % p.Zo);
-    int n = (int)(t / p.Zo);
+  int r = blockIdx.x;
+  const int xo = r % p.Xo;
+  r /= p.Xo;
+  const int zo = r % p.Zo;
+  const int n = r / p.Zo;
+  const int rowlen = p.Yo * cv;
+  const float* xn = x + (int64_t)n * p.Z * p.X * p.Y * p.xp;
+  const int64_t orow = (((int64_t)n * p.Zo + zo) * p.Xo + xo) * p.Yo;
+  for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+    const int yo = (int)dcv.div((uint32_t)t);
+    const int c = (t - yo * cv) * V;
     float best[V];
     int bi[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) best[j] = -INFINITY, bi[j] = 0;
     bool first = true;
     for (int dz = 0; dz < p.pz; ++dz)
-      for (int dx = 0; dx < p.px; ++dx)
+      for (int dx = 0; dx < p.px; ++dx) {
+        const int lin0 = ((zo * p.pz + dz) * p.X + xo * p.px + dx) * p.Y + yo * p.py;
+        const float* src = xn + (int64_t)lin0 * p.xp + c;
+#pragma unroll 2
         for (int dy = 0; dy < p.py; ++dy) {
-          int zz = zo * p.pz + dz, xx = xo * p.px + dx, yy = yo * p.py + dy;
-          int lin = (zz * p.X + xx) * p.Y + yy;
           Vec<V> v;
-          v.load(x + ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c);
+          v.load(src + (int64_t)dy * p.xp);
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             // strict '>' keeps the FIRST maximum in (z,x,y) scan order
-            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin;
+            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin0 + dy;
           }
           first = false;
         }
+      }
     Vec<V> o;
     IVec<V> oi;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float r = best[j];
-      if (p.has_bias) r += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
-      r = e2_apply_act(r, p.act);
-      o.v[j] = p.round_tf32 ? e2_round_tf32(r) : r;
+      float r2 = best[j];
+      if (p.has_bias) r2 += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
+      r2 = e2_apply_act(r2, p.act);
+      o.v[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
       oi.v[j] = bi[j];
     }
-    int64_t oofs = pos * p.yp + c;
+    const int64_t oofs = (orow + yo) * p.yp + c;
     o.store(y + oofs);
     if (amax) oi.store(amax + oofs);
   }
@@ -176,49 +183,64 @@ __global__ void __launch_bounds__(256) k_maxpool_bwd(PoolP p, const float* __res
   }
 }
 
-// Gather form for E2_TIE_FIRST: one thread per INPUT position x V channels, so the two big streams (dx
-// write, ReLU-gate read) are fully coalesced; the pooled dy / argmax values are re-read by the prod(p)
-// threads of a window and come from L1/L2.
+// Gather form for E2_TIE_FIRST: one block per INPUT row (n, z, x); a thread owns one pooled position x V
+// channels of that row and writes the py input positions below it, so the two big streams (dx write, ReLU-gate
+// read) are fully coalesced 16-byte accesses and dy / argmax are read once per window row.
 template <int V>
-__global__ void __launch_bounds__(256) k_maxpool_bwd_gather(PoolP p, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256) k_maxpool_bwd_gather(PoolP p, E2FastDiv dcv, const float* __restrict__ dy,
                                                             const int* __restrict__ amax, float* __restrict__ dx,
                                                             const float* __restrict__ gate) {
   const int cv = p.C / V;
-  const int64_t total = (int64_t)p.n * p.Z * p.X * p.Y * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * V;
-    const int64_t pos = i / cv;
-    const int yy = (int)(pos % p.Y);
-    int64_t t = pos / p.Y;
-    const int xx = (int)(t % p.X);
-    t /= p.X;
-    const int zz = (int)(t % p.Z);
-    const int n = (int)(t / p.Z);
-    const int lin = (zz * p.X + xx) * p.Y + yy;
-    const int64_t opos = (((int64_t)n * p.Zo + zz / p.pz) * p.Xo + xx / p.px) * p.Yo + yy / p.py;
-    Vec<V> g, o;
+  int r = blockIdx.x;
+  const int xx = r % p.X;
+  r /= p.X;
+  const int zz = r % p.Z;
+  const int n = r / p.Z;
+  const int rowlen = p.Yo * cv;
+  const int lin_row = (zz * p.X + xx) * p.Y;
+  const int64_t irow = ((int64_t)n * p.Z * p.X * p.Y + lin_row) * p.xp;
+  const int64_t orow = ((((int64_t)n * p.Zo + zz / p.pz) * p.Xo + xx / p.px) * p.Yo) * p.yp;
+  for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+    const int yo = (int)dcv.div((uint32_t)t);
+    const int c = (t - yo * cv) * V;
+    Vec<V> g;
     IVec<V> am;
-    g.load(dy + opos * p.yp + c);
-    am.load(amax + opos * p.yp + c);
-#pragma unroll
-    for (int j = 0; j < V; ++j) o.v[j] = (am.v[j] == lin) ? g.v[j] : 0.f;
-    const int64_t ofs = pos * p.xp + c;
-    if (gate) {
+    const int64_t oofs = orow + (int64_t)yo * p.yp + c;
+    g.load(dy + oofs);
+    am.load(amax + oofs);
+    if (gate && p.gate_pooled) {
       Vec<V> gt;
-      gt.load(p.gate_pooled ? gate + opos * p.yp + c : gate + ofs);
+      gt.load(gate + oofs);
 #pragma unroll
       for (int j = 0; j < V; ++j)
-        if (!(gt.v[j] > 0.f)) o.v[j] = 0.f;
+        if (!(gt.v[j] > 0.f)) g.v[j] = 0.f;
     }
-    if (p.accumulate) {
-      Vec<V> old;
-      old.load(dx + ofs);
+    for (int k = 0; k < p.py; ++k) {
+      const int yy = yo * p.py + k;
+      const int lin = lin_row + yy;
+      const int64_t ofs = irow + (int64_t)yy * p.xp + c;
+      Vec<V> o;
 #pragma unroll
-      for (int j = 0; j < V; ++j) o.v[j] += old.v[j];
+      for (int j = 0; j < V; ++j) o.v[j] = (am.v[j] == lin) ? g.v[j] : 0.f;
+      if (gate && !p.gate_pooled) {
+        Vec<V> gt;
+        gt.load(gate + ofs);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (!(gt.v[j] > 0.f)) o.v[j] = 0.f;
+      }
+      if (p.accumulate) {
+        Vec<V> old;
+        old.load(dx + ofs);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] += old.v[j];
+      }
+      o.store(dx + ofs);
     }
-    o.store(dx + ofs);
   }
 }
+
+static inline int pool_block(int rowlen) { return rowlen >= 256 ? 256 : ((rowlen + 31) / 32) * 32; }
 
 static int fill_pool(e2_handle* h, const e2_pool_desc* d, PoolP* p) {
   E2_REQUIRE(h, d && e2_tensor_ok(&d->x) && e2_tensor_ok(&d->y), "maxpool3d: bad descriptor");
@@ -244,11 +266,14 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
   int rc = fill_pool(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, x && y && (!d->has_bias || bias), "maxpool3d_fwd: null pointer");
-  int64_t work = e2_positions(&d->y) * d->y.c;
+  const int64_t rows = (int64_t)p.n * p.Zo * p.Xo;
+  E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_fwd: too many rows");
   if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp})) {
-    k_maxpool_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+    const int rowlen = p.Yo * (p.C / 4);
+    k_maxpool_fwd<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C / 4, rowlen), x, bias, y, argmax);
   } else {
-    k_maxpool_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+    const int rowlen = p.Yo * p.C;
+    k_maxpool_fwd<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
   }
   h->launches++;
   E2_CUDA_CHECK(h, "maxpool3d_fwd");
@@ -267,11 +292,15 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
              "maxpool3d_bwd: gate_pooled needs tie_mode FIRST and a pool without bias/activation");
   int64_t work = e2_positions(&d->y) * d->y.c;
   if (p.tie == E2_TIE_FIRST) {
-    const int64_t iwork = e2_positions(&d->x) * d->x.c;
-    if (vec4_ok({dy, dx, argmax, relu_gate}, {p.C, p.xp, p.yp}))
-      k_maxpool_bwd_gather<4><<<e2_grid_1d(iwork / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx, relu_gate);
-    else
-      k_maxpool_bwd_gather<1><<<e2_grid_1d(iwork, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx, relu_gate);
+    const int64_t rows = (int64_t)p.n * p.Z * p.X;
+    E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_bwd: too many rows");
+    if (vec4_ok({dy, dx, argmax, relu_gate}, {p.C, p.xp, p.yp})) {
+      const int rowlen = p.Yo * (p.C / 4);
+      k_maxpool_bwd_gather<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C / 4, rowlen), dy, argmax, dx, relu_gate);
+    } else {
+      const int rowlen = p.Yo * p.C;
+      k_maxpool_bwd_gather<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), dy, argmax, dx, relu_gate);
+    }
   } else if (vec4_ok({dy, dx, argmax, x}, {p.C, p.xp, p.yp})) {
     k_maxpool_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx,
                                                                                                relu_gate);

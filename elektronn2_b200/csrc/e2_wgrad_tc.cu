@@ -48,6 +48,7 @@ struct WgParams {
   float* W;
   int out_mode;
   uint32_t idesc;
+  float* part;             // per-CTA partial tiles [split][unit][group][col/4][row][4]; NULL: fp32 atomics into W
 };
 
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__ CUtensorMap tmP,
@@ -182,6 +183,16 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
           uint32_t v[32];
           tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_cols + c0), v);
           tc::tmem_ld_wait();
+          if (p.part) {
+            // raw accumulators, one float4 per row and 4 columns (coalesced over the rows of a warp)
+            float4* dst = reinterpret_cast<float4*>(p.part) +
+                          (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * p.gpc + g) * (size_t)(p.n_cols / 4) * 128 + row;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4)
+              dst[(size_t)((c0 + j4) / 4) * 128] = make_float4(__uint_as_float(v[j4]), __uint_as_float(v[j4 + 1]),
+                                                              __uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3]));
+            continue;
+          }
           if (!row_ok) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -199,6 +210,45 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// Second pass of the partial-tile mode: sums the position splits and writes dw in the reference layout.  Every
+// valid (r, s, tap) belongs to exactly one (unit, group, row, column), so W needs no memset and the result
+// does not depend on the split order (deterministic).  One thread per (unit, group, 4 columns, row).
+__global__ void __launch_bounds__(128) k_wgrad_tc_reduce(const WgParams p, int splits, int units) {
+  const int row = threadIdx.x;
+  int b = blockIdx.x;
+  const int c4 = b % (p.n_cols / 4);
+  b /= (p.n_cols / 4);
+  const int g = b % p.gpc;
+  int u = b / p.gpc;
+  const int unit = u;
+  const int gs = u % p.n_gs;
+  u /= p.n_gs;
+  const int sc = u % p.n_sc;
+  const int rc = u / p.n_sc;
+  const int T = p.kz * p.kx * p.ky;
+  const int tap = gs * p.gpc * p.tpm + g * p.tpm + row / p.sw;
+  const int s = sc * p.sw + row % p.sw;
+  if (tap >= T || s >= p.S) return;
+  const size_t tile_f4 = (size_t)(p.n_cols / 4) * 128;
+  const float4* src = reinterpret_cast<const float4*>(p.part) + ((size_t)unit * p.gpc + g) * tile_f4 + (size_t)c4 * 128 + row;
+  const size_t zstride = (size_t)units * p.gpc * tile_f4;
+  float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 v = __ldcg(src + (size_t)z * zstride);
+    a4.x += v.x, a4.y += v.y, a4.z += v.z, a4.w += v.w;
+  }
+  const int k3 = tap % p.ky, j3 = (tap / p.ky) % p.kx, i3 = tap / (p.ky * p.kx);
+  const int tflip = ((p.kz - 1 - i3) * p.kx + (p.kx - 1 - j3)) * p.ky + (p.ky - 1 - k3);
+  const float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = rc * p.n_cols + c4 * 4 + e;
+    if (r >= p.R) continue;
+    const int64_t ofs = (p.out_mode == 0) ? ((int64_t)r * p.S + s) * T + tflip : ((int64_t)s * p.R + r) * T + tap;
+    p.W[ofs] = v[e];
   }
 }
 
@@ -227,14 +277,14 @@ bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g) {
   return true;
 }
 
-int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) {
-  EncodeTiledFn enc = e2_get_tmap_encode();
-  if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
-  WgParams p;
+// Geometry shared by the launcher and the workspace query.  `partials`: per-CTA partial tiles + reduce kernel
+// (a split costs |dw| of coalesced traffic) instead of fp32 atomics (~32 per clock chip-wide when scattered).
+static bool plan_wg(int sm_count, const ReduceGemm& g, bool partials, WgParams* pp, int* units_out, int* splits_out,
+                    int* a_slots_out, int* b_bytes_out) {
+  WgParams& p = *pp;
   memset(&p, 0, sizeof(p));
   p.Mn = g.Mn, p.Mz = g.Mz, p.Mx = g.Mx, p.My = g.My;
-  if (!pick_tile64(g.Mz, g.Mx, g.My, g.sz, g.sx, g.sy, &p.tz, &p.tx, &p.ty))
-    return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: no position tile fits the TMA extent limit");
+  if (!pick_tile64(g.Mz, g.Mx, g.My, g.sz, g.sx, g.sy, &p.tz, &p.tx, &p.ty)) return false;
   p.sz = g.sz, p.sx = g.sx, p.sy = g.sy;
   p.ntz = (g.Mz + p.tz - 1) / p.tz, p.ntx = (g.Mx + p.tx - 1) / p.tx, p.nty = (g.My + p.ty - 1) / p.ty;
   p.kz = g.tz, p.kx = g.tx, p.ky = g.ty, p.oz = g.oz, p.ox = g.ox, p.oy = g.oy;
@@ -257,28 +307,54 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
   const int b_bytes = (ncols / 32) * CHUNK_BYTES;
   int a_slots = (int)((208 * 1024 - B_SLOTS * b_bytes) / A_BYTES);
   if (a_slots > 5) a_slots = 5;
-  if (a_slots < 2) return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: shared memory budget");
+  if (a_slots < 2) return false;
   p.a_slots = a_slots;
   p.tiles_total = g.Mn * p.ntz * p.ntx * p.nty;
   const int units = p.n_rc * p.n_sc * p.n_gs;
-  // Position splits: more CTAs shorten the MMA phase but every split adds |dw| fp32 atomics (measured
-  // ~32 per clock chip-wide for this scattered pattern).  Small layers with large dw (the upconvs) were
-  // spending 90 % of their time in atomics at 2 CTAs per SM; pick the split count that minimises the sum.
+  // Position splits: more CTAs shorten the MMA phase, every split adds |dw| of output traffic; pick the
+  // split count that minimises the sum (cycles).
   int splits = 1;
   {
     const double per_tile = groups_max * (KP / 8) * 70.0;                       // MMA cycles per position tile
-    const double atom_per_split = (double)units * groups_max * 128.0 * ncols / 32.0;
+    const double out_per_split = (double)units * groups_max * 128.0 * ncols / (partials ? 350.0 : 32.0);
     double best = -1;
-    const int smax = std::max(1, std::min(p.tiles_total, (2 * h->sm_count + units - 1) / units));
+    const int smax = std::max(1, std::min(p.tiles_total, (2 * sm_count + units - 1) / units));
     for (int sp = 1; sp <= smax; ++sp) {
       const int tps = (p.tiles_total + sp - 1) / sp;
-      const int waves = (units * sp + h->sm_count - 1) / h->sm_count;
-      const double t = waves * (tps * per_tile + 3000.0) + sp * atom_per_split;
+      const int waves = (units * sp + sm_count - 1) / sm_count;
+      const double t = waves * (tps * per_tile + 3000.0) + sp * out_per_split;
       if (best < 0 || t < best) best = t, splits = sp;
     }
   }
   p.tiles_per_split = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_split - 1) / p.tiles_per_split;
+  *units_out = units, *splits_out = splits, *a_slots_out = a_slots, *b_bytes_out = b_bytes;
+  return true;
+}
+
+size_t e2_reduce_gemm_tc_workspace_bytes(int sm_count, const ReduceGemm& g) {
+  WgParams p;
+  int units, splits, a_slots, b_bytes;
+  if (!plan_wg(sm_count, g, true, &p, &units, &splits, &a_slots, &b_bytes)) return 0;
+  return (size_t)splits * units * p.gpc * p.n_cols * 128 * sizeof(float);
+}
+
+int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, cudaStream_t s) {
+  EncodeTiledFn enc = e2_get_tmap_encode();
+  if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
+  WgParams p;
+  int units, splits, a_slots, b_bytes;
+  const int T = g.tz * g.tx * g.ty;
+  bool partials = ws && !(reinterpret_cast<uintptr_t>(ws) & 15) && !getenv("E2_WGRAD_ATOMIC");
+  if (partials) {
+    if (!plan_wg(h->sm_count, g, true, &p, &units, &splits, &a_slots, &b_bytes))
+      return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: no position tile / shared memory budget");
+    if ((size_t)splits * units * p.gpc * p.n_cols * 128 * sizeof(float) > ws_bytes) partials = false;
+  }
+  if (!partials && !plan_wg(h->sm_count, g, false, &p, &units, &splits, &a_slots, &b_bytes))
+    return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_tc: no position tile / shared memory budget");
+  const int ncols = p.n_cols;
+  p.part = partials ? static_cast<float*>(ws) : nullptr;
   p.W = g.W, p.out_mode = g.out_mode;
   p.idesc = tc::make_idesc(2 /*TF32*/, 1, 1, 128, (uint32_t)ncols);
 
@@ -306,7 +382,7 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(Q) failed: %d", (int)r);
   }
-  cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
+  if (!p.part) cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
   const size_t smem = 1024 + (size_t)B_SLOTS * b_bytes + (size_t)a_slots * A_BYTES + (2 * B_SLOTS + 2 * a_slots + 1) * 8 + 16;
   static bool configured = false;
   if (!configured) {
@@ -318,5 +394,10 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, cudaStream_t s) 
   k_wgrad_tc<<<grid, WG_THREADS, smem, s>>>(tmP, tmQ, p);
   h->launches++;
   E2_CUDA_CHECK(h, "wgrad_tc");
+  if (p.part) {
+    k_wgrad_tc_reduce<<<(unsigned)(units * p.gpc * (ncols / 4)), 128, 0, s>>>(p, splits, units);
+    h->launches++;
+    E2_CUDA_CHECK(h, "wgrad_tc_reduce");
+  }
   return E2_OK;
 }

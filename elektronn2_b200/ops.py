@@ -117,7 +117,8 @@ class UpConvOp(object):
 
     def wgrad(self, dy, dw, db=None):
         d = self._desc(y=dy)
-        self.h.call('e2_upconv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), None, 0,
+        ws, ws_bytes = self.h.workspace()
+        self.h.call('e2_upconv3d_wgrad', C.byref(d), self.x.ptr(), dy.ptr(), _lib.ptr(dw), _lib.ptr(db), ws, ws_bytes,
                     self.h.stream())
 
 
