@@ -261,7 +261,7 @@ def main():
                 e2e=dict(value=n_vox * K / (e2e_ms * 1e-3), unit='voxels/s', h2d_bytes_per_step=in_bytes,
                          d2h_bytes_per_step=16, ms_per_step=e2e_ms / K),
                 gpu_launches=launches_per_step * K, clocks=clocks, loss=float(loss),
-                cuda_graph=bool(e2cfg.use_cuda_graph and world == 1))
+                cuda_graph=plan._graph is not None)
     print(json.dumps(line))
     return 0
 

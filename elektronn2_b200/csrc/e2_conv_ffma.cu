@@ -683,9 +683,14 @@ extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
     GatherGemm f, b;
     conv_fwd_problem(d, dummy, dummy, nullptr, dummy, &f);
     conv_dgrad_problem(d, dummy, dummy, dummy, nullptr, &b);
-    for (const GatherGemm* q : {&f, &b})
-      if (e2_gather_gemm_tc_ok(&fake, *q) && !e2_conv_zstack_tc_ok(&fake, *q) && !e2_conv_plane_tc_ok(&fake, *q))
+    for (GatherGemm* q : {&f, &b}) {
+      if (!e2_gather_gemm_tc_ok(&fake, *q)) continue;
+      q->ws = dummy;                      // "a workspace will be supplied": lets the planners consider K splits
+      if (e2_conv_zstack_tc_ok(&fake, *q))
+        *bytes = std::max(*bytes, e2_conv_zstack_workspace_bytes(sm_count, *q));
+      else if (!e2_conv_plane_tc_ok(&fake, *q))
         *bytes = std::max(*bytes, e2_gather_gemm_tc_workspace_bytes(sm_count, *q));
+    }
   }
   return E2_OK;
 }

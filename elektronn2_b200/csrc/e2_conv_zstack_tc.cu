@@ -48,6 +48,7 @@ struct ZsParams {
   int plane_bytes, plane_stride, w_bytes, wblk_bytes;
   int tmem_cols;
   int num_tiles;
+  int ksplit, cb_per;            // K split over channel blocks: unit = (tile, split); raw partial tiles go to a workspace
   float* C;
   int c_pitch;
   const float* bias;
@@ -156,7 +157,12 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const int T9 = p.kx * p.ky;
 
-  auto tile_coords = [&](int t, int& in_, int& z0, int& x0, int& y0, int& n0) {
+  // unit index = (((n, tile z, x, y), N tile), K split) with the split fastest: the CTAs working on one tile's
+  // channel-block ranges run at the same time and write partial tile `ks` of the workspace
+  auto tile_coords = [&](int t, int& in_, int& z0, int& x0, int& y0, int& n0, int& cb_lo, int& cb_hi) {
+    const int ks = t % p.ksplit;
+    t /= p.ksplit;
+    cb_lo = ks * p.cb_per, cb_hi = min(p.CB, cb_lo + p.cb_per);
     const int nt = t % p.ntn;
     t /= p.ntn;
     const int ity = t % p.nty;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
     const int itx = t % p.ntx;
     t /= p.ntx;
     const int itz = t % p.ntz;
-    in_ = t / p.ntz;
+    in_ = t / p.ntz + ks * p.On;     // + split * On: batch coordinate of the partial tensor (only the store uses it)
     z0 = itz * p.TZ, x0 = itx * TX, y0 = ity * TY, n0 = nt * p.BN;
   };
 
@@ -176,9 +182,10 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       const int dbl = (p.nslot >= 2 * p.NP) ? 1 : 0;
       int ucount = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        int in_, z0, x0, y0, n0;
-        tile_coords(t, in_, z0, x0, y0, n0);
-        for (int cb = 0; cb < p.CB; ++cb, ++ucount) {
+        int in_, z0, x0, y0, n0, cb_lo, cb_hi;
+        tile_coords(t, in_, z0, x0, y0, n0, cb_lo, cb_hi);
+        in_ %= p.On;
+        for (int cb = cb_lo; cb < cb_hi; ++cb, ++ucount) {
           const int s0 = dbl ? (ucount & 1) * p.NP : 0;
           const uint32_t par = (((uint32_t)(dbl ? (ucount >> 1) : ucount)) & 1u) ^ 1u;
           for (int pl = 0; pl < p.NP; ++pl) {
@@ -201,9 +208,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       int s = 0;
       uint32_t par = 1;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        int in_, z0, x0, y0, n0;
-        tile_coords(t, in_, z0, x0, y0, n0);
-        for (int cb = 0; cb < p.CB; ++cb)
+        int in_, z0, x0, y0, n0, cb_lo, cb_hi;
+        tile_coords(t, in_, z0, x0, y0, n0, cb_lo, cb_hi);
+        for (int cb = cb_lo; cb < cb_hi; ++cb)
           for (int jk = 0; jk < T9; ++jk) {
             tc::mbar_wait(&w_empty[s], par);
             if (p.dbg & 2) {
@@ -240,7 +247,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       tr_acc += clock64() - c0;
       tc::tc_fence_after();
       const uint32_t acc0 = tmem_base + (uint32_t)(buf * TZ_) * bn;
-      for (int cb = 0; cb < p.CB; ++cb, ++ucount) {
+      const int ks = t % p.ksplit;
+      const int cb_lo = ks * p.cb_per, cb_hi = min(p.CB, cb_lo + p.cb_per);
+      for (int cb = cb_lo; cb < cb_hi; ++cb, ++ucount) {
         const int s0 = dbl ? (ucount & 1) * p.NP : 0;
         const uint32_t par_full = ((uint32_t)(dbl ? (ucount >> 1) : ucount)) & 1u;
         const uint32_t unit_enc = smP_enc + (uint32_t)s0 * pstride_enc;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
               if (last_stage)
                 for (int q = 0; q < p.NP; ++q) tc::mma_commit(&pl_empty[s0 + q]);
             } else if (jk == 0) {
-              zs_issue_stage<TZ_, KZ_, true>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, cb == 0,
+              zs_issue_stage<TZ_, KZ_, true>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, cb == cb_lo,
                                              last_stage, pl_full + s0, pl_empty + s0, par_full, nk);
             } else {
               zs_issue_stage<TZ_, KZ_, false>(ad0, pstride_enc, bd0, wblk_enc, acc0, bn, idesc0, idesc_step, false,
@@ -302,8 +311,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
     int buf = 0;
     uint32_t fpar = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      int in_, z0, x0, y0, n0;
-      tile_coords(t, in_, z0, x0, y0, n0);
+      int in_, z0, x0, y0, n0, cb_lo, cb_hi;
+      tile_coords(t, in_, z0, x0, y0, n0, cb_lo, cb_hi);
       for (int i = lane; i < p.BN; i += 32) bias_w[i] = (p.bias && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       __syncwarp();
       long long e0 = clock64();
@@ -425,10 +434,71 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
   }
 }
 
+
+
+// Split-K second pass: sums the raw partial tiles [split][n][z][x][y][Np] and applies the fused epilogue
+// (+bias -> act -> ReLU gate -> accumulate -> tf32 round).  One thread per position x 4 channels.
+__global__ void __launch_bounds__(256) k_zstack_reduce(const float* __restrict__ part, int ksplit, int64_t positions, int Np,
+                                                       int N, float* __restrict__ C, int c_pitch,
+                                                       const float* __restrict__ bias, const float* __restrict__ gate, int act,
+                                                       int accumulate, int round_tf32) {
+  const uint32_t q4 = (uint32_t)Np / 4;
+  const uint32_t total = (uint32_t)positions * q4;            // < 2^31 (checked by the launcher)
+  const int64_t zstride = positions * Np;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t pos = i / q4;                              // 32-bit division: cheap next to the ksplit loads
+    const int c = (int)(i - pos * q4) * 4;
+    const float* src = part + (int64_t)pos * Np + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < ksplit; ++z) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)z * zstride));
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    const int64_t ofs = (int64_t)pos * c_pitch + c;
+    const bool full = c + 3 < N;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e >= N) continue;
+      if (bias) v[e] += __ldg(bias + c + e);
+      v[e] = e2_apply_act(v[e], act);
+    }
+    if (full) {
+      if (gate) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate + ofs));
+        v[0] = g4.x > 0.f ? v[0] : 0.f, v[1] = g4.y > 0.f ? v[1] : 0.f;
+        v[2] = g4.z > 0.f ? v[2] : 0.f, v[3] = g4.w > 0.f ? v[3] : 0.f;
+      }
+      if (accumulate) {
+        const float4 c4 = *reinterpret_cast<const float4*>(C + ofs);
+        v[0] += c4.x, v[1] += c4.y, v[2] += c4.z, v[3] += c4.w;
+      }
+      if (round_tf32) v[0] = e2_round_tf32(v[0]), v[1] = e2_round_tf32(v[1]), v[2] = e2_round_tf32(v[2]), v[3] = e2_round_tf32(v[3]);
+      *reinterpret_cast<float4*>(C + ofs) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c + e >= N) continue;
+        float x = v[e];
+        if (gate && !(__ldg(gate + ofs + e) > 0.f)) x = 0.f;
+        if (accumulate) x += C[ofs + e];
+        if (round_tf32) x = e2_round_tf32(x);
+        C[ofs + e] = x;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // Decide whether the kernel applies and is worthwhile for this problem; fill the geometry.
-static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
+// The N tile, the number of output planes per tile and the K split are chosen together by a cycle model:
+//   * an MMA of width n costs max(48, 32 + n/4, n/2) cycles (measured, scripts/mma_bench.cu) and a stage
+//     ((channel block, in-plane tap): NP plane MMA groups) carries ~250 cycles of wait / descriptor / commit work,
+//     so layers whose tiles have a single output plane want wide N tiles (up to 256 / min(TZ, kz));
+//   * layers with few output positions have fewer tiles than SMs and a long serial K loop: their channel blocks
+//     are split over CTAs (raw partial tiles in the caller's workspace + k_zstack_reduce).
+static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bool may_split) {
   if (g.sz != 1 || g.sx != 1 || g.sy != 1 || g.shuffle) return false;
   if (g.ty > 9 || g.tx > 9 || g.tz > 4) return false;
   const int T = g.tz * g.tx * g.ty;
@@ -440,60 +510,66 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   p->YP = TY + g.ty - 1;
   p->plane_bytes = p->XH * p->YP * 128;
   p->plane_stride = (p->plane_bytes + 1023) / 1024 * 1024;   // slots stay 1024-B aligned (swizzle period)
-  // N tile: multiple of 16 with S*BN <= 256; minimise the padded width, prefer wide tiles
-  const int bn_max = (256 / S) / 16 * 16;
-  int bn = 0, ntn = 0;
-  double bn_cost = 0;
-  for (int b = bn_max; b >= 16; b -= 16) {
-    const int n = (g.N + b - 1) / b;
-    if (n > 1 && (b % 32)) continue;   // the epilogue stores 32-channel boxes: inner N tiles must be whole boxes
-    const double c = n * std::max(56.0, S * b / 2.0);   // cycles per K step of a full-span MMA, all N tiles
-    if (bn == 0 || c < bn_cost) bn = b, ntn = n, bn_cost = c;
-  }
-  p->BN = bn, p->ntn = ntn;
-  p->wblk_bytes = bn * 128;
-  p->w_bytes = S * bn * 128;
   if (g.c_pitch % 4 || (reinterpret_cast<uintptr_t>(g.C) & 15) || (reinterpret_cast<uintptr_t>(g.gate) & 15)) return false;
-  const int epi_bytes = EPI_WARPS * 4096 + EPI_WARPS * bn * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
-  const int budget = 227 * 1024 - 1024 - 1024 - epi_bytes;   // alignment slack + barriers + epilogue
-  // TZ: as many output planes as TMEM (double-buffered) and shared memory allow; among those, the one
-  // with the least z-quantisation / wave-quantisation waste
   const int ntx = (g.Ox + TX - 1) / TX, nty = (g.Oy + TY - 1) / TY;
-  // Cost model per tile: CB * T9 stages, each max(MMA cycles, TMA round trip / weight-ring depth), plus one
-  // round trip when the unit's planes are single-buffered.  Layers with few MMAs per stage (K <= 8: one K
-  // slice per plane) are latency-bound unless the weight ring is deep, so TZ may shrink to make room.
-  const double kLatency = 1200.0;
+  const double kLatency = 1200.0, kStageOvh = 250.0, kEpiChunk = 1200.0, kReduceFixed = 8000.0, kReduceBpc = 2500.0;
   const int T9 = g.tx * g.ty, CBn = (g.K + 31) / 32;
   const double nk_avg = (double)((g.K + 7) / 8) / CBn;   // K = 8 slices per 32-channel block
-  int best_tz = 0, best_w = 0, best_dbl = 0;
+  const double c_bytes = (double)g.On * g.Oz * g.Ox * g.Oy * ((g.N + 3) / 4 * 4) * 4.0;
+  static const int ks_opts[] = {1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 24};
+  if (c_bytes / 16.0 >= 2147483648.0) may_split = false;     // k_zstack_reduce indexes float4s with 32 bits
+  static const bool no_split = getenv("E2_ZS_NOSPLIT") != nullptr;
+  static const bool narrow = getenv("E2_ZS_NARROW") != nullptr;     // A/B switch: N tiles as before (kz * BN <= 256)
+  int best_tz = 0, best_w = 0, best_dbl = 0, best_bn = 0, best_ntn = 0, best_ks = 1;
   double best_cost = 0;
-  for (int tz = 8; tz >= 1; --tz) {
-    if (2 * tz * bn > 512) continue;
-    const int np = tz + S - 1;
-    if (np > 11) continue;
-    if (np * p->plane_stride + 2 * p->w_bytes > budget) continue;
-    int rest = budget - np * p->plane_stride;
-    int wsl = std::min(MAX_WSLOTS, rest / p->w_bytes);
-    int dbl = 0;
-    // double buffering the planes is worth more than weight slots beyond the third
-    if (wsl >= 3 && rest - 3 * p->w_bytes >= np * p->plane_stride) {
-      dbl = 1;
-      wsl = std::min(MAX_WSLOTS, (rest - np * p->plane_stride) / p->w_bytes);
+  const int bn_cap = std::min(256, (g.N + 15) / 16 * 16);
+  for (int b = bn_cap; b >= 16; b -= 16) {
+    const int ntn = (g.N + b - 1) / b;
+    if (ntn > 1 && (b % 32)) continue;   // the epilogue stores 32-channel boxes: inner N tiles must be whole boxes
+    if (narrow && S * b > 256) continue;
+    const int w_bytes = S * b * 128;
+    const int epi_bytes = EPI_WARPS * 4096 + EPI_WARPS * b * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
+    const int budget = 227 * 1024 - 1024 - 1024 - epi_bytes;   // alignment slack + barriers + epilogue
+    for (int tz = 8; tz >= 1; --tz) {
+      if (std::min(tz, S) * b > 256) continue;   // widest stacked MMA
+      if (2 * tz * b > 512) continue;            // double-buffered accumulators in TMEM
+      const int np = tz + S - 1;
+      if (np > 11) continue;
+      if (np * p->plane_stride + 2 * w_bytes > budget) continue;
+      int rest = budget - np * p->plane_stride;
+      int wsl = std::min(MAX_WSLOTS, rest / w_bytes);
+      int dbl = 0;
+      // double buffering the planes is worth more than weight slots beyond the third
+      if (wsl >= 3 && rest - 3 * w_bytes >= np * p->plane_stride) {
+        dbl = 1;
+        wsl = std::min(MAX_WSLOTS, (rest - np * p->plane_stride) / w_bytes);
+      }
+      const int ntz = (g.Oz + tz - 1) / tz;
+      const int64_t tiles = (int64_t)g.On * ntz * ntx * nty * ntn;
+      double mma = 0;
+      for (int q = 0; q < np; ++q) {
+        const int nblk = std::min(q, tz - 1) - std::max(0, q - (S - 1)) + 1;
+        const double n = nblk * b;
+        mma += std::max(std::max(48.0, 32.0 + n / 4.0), n / 2.0);   // operand fetch (128 B/clk) or math bound
+      }
+      const double stage = std::max(mma * nk_avg + kStageOvh, kLatency / (wsl - 1));
+      for (int ks : ks_opts) {
+        if (ks > 1 && (!may_split || no_split || ks > CBn)) break;
+        const int cb_per = (CBn + ks - 1) / ks;
+        if ((CBn + cb_per - 1) / cb_per != ks) continue;   // same split as a smaller ks
+        const int64_t waves = (tiles * ks + h->sm_count - 1) / h->sm_count;
+        double cost = (double)waves * (cb_per * T9 * stage + (dbl ? 0.0 : kLatency) + 200.0) + tz * (b / 32.0) / 2.0 * kEpiChunk;
+        if (ks > 1) cost += kReduceFixed + (ks + 1.0) * c_bytes / kReduceBpc;
+        if (best_tz == 0 || cost < best_cost * 0.97)
+          best_tz = tz, best_cost = cost, best_w = wsl, best_dbl = dbl, best_bn = b, best_ntn = ntn, best_ks = ks;
+      }
     }
-    const int ntz = (g.Oz + tz - 1) / tz;
-    const int64_t tiles = (int64_t)g.On * ntz * ntx * nty * ntn;
-    const int64_t waves = (tiles + h->sm_count - 1) / h->sm_count;
-    double mma = 0;
-    for (int q = 0; q < np; ++q) {
-      const int nblk = std::min(q, tz - 1) - std::max(0, q - (S - 1)) + 1;
-      const double n = nblk * bn;
-      mma += std::max(std::max(48.0, 32.0 + n / 4.0), n / 2.0);   // operand fetch (128 B/clk) or math bound
-    }
-    const double stage = std::max(mma * nk_avg, kLatency / (wsl - 1));
-    const double cost = (double)waves * (CBn * T9 * stage + (dbl ? 0.0 : kLatency) + 200.0);
-    if (best_tz == 0 || cost < best_cost * 0.97) best_tz = tz, best_cost = cost, best_w = wsl, best_dbl = dbl;
   }
   if (best_tz == 0) return false;
+  const int bn = best_bn;
+  p->BN = bn, p->ntn = best_ntn;
+  p->wblk_bytes = bn * 128;
+  p->w_bytes = S * bn * 128;
   p->TZ = best_tz;
   p->NP = best_tz + S - 1;
   p->nslot = best_dbl ? 2 * p->NP : p->NP;
@@ -505,8 +581,10 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   p->On = g.On, p->Oz = g.Oz, p->Ox = g.Ox, p->Oy = g.Oy;
   p->ntz = (g.Oz + p->TZ - 1) / p->TZ, p->ntx = ntx, p->nty = nty;
   p->kz = g.tz, p->kx = g.tx, p->ky = g.ty, p->oz = g.oz, p->ox = g.ox, p->oy = g.oy;
-  p->K = g.K, p->N = g.N, p->CB = (g.K + 31) / 32;
-  p->num_tiles = p->On * p->ntz * p->ntx * p->nty * p->ntn;
+  p->K = g.K, p->N = g.N, p->CB = CBn;
+  p->cb_per = (CBn + best_ks - 1) / best_ks;
+  p->ksplit = (CBn + p->cb_per - 1) / p->cb_per;
+  p->num_tiles = p->On * p->ntz * p->ntx * p->nty * p->ntn * p->ksplit;
   p->epi_off = (p->nslot * p->plane_stride + p->wslot * p->w_bytes + 1023) / 1024 * 1024;
   // tile-quantisation efficiency: useful outputs / computed outputs
   const double eff = (double)g.Oz * g.Ox * g.Oy * g.N /
@@ -515,23 +593,61 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p) {
   return true;
 }
 
+static size_t zs_ws_bytes(const GatherGemm& g, const ZsParams& p) {
+  if (p.ksplit <= 1) return 0;
+  return (size_t)p.ksplit * g.On * g.Oz * g.Ox * g.Oy * ((g.N + 3) / 4 * 4) * sizeof(float);
+}
+
+size_t e2_conv_zstack_workspace_bytes(int sm_count, const GatherGemm& g) {
+  e2_handle fake;
+  memset(&fake, 0, sizeof(fake));
+  fake.sm_count = sm_count;
+  ZsParams p;
+  if (!plan_zstack(&fake, g, &p, true)) return 0;
+  return zs_ws_bytes(g, p);
+}
+
+// debug / test hook: the plan for a problem as 8 ints {BN, TZ, ksplit, cb_per, wslot, nslot, num_tiles, ntn}
+extern "C" int e2_debug_zstack_plan(int sm_count, int K, int N, int Oz, int Ox, int Oy, int kz, int kx, int ky, int may_split,
+                                    int* out) {
+  e2_handle fake;
+  memset(&fake, 0, sizeof(fake));
+  fake.sm_count = sm_count;
+  GatherGemm g;
+  memset(&g, 0, sizeof(g));
+  g.K = K, g.N = N, g.On = 1, g.Oz = Oz, g.Ox = Ox, g.Oy = Oy, g.tz = kz, g.tx = kx, g.ty = ky, g.sz = g.sx = g.sy = 1;
+  g.c_pitch = (N + 3) / 4 * 4;
+  ZsParams p;
+  if (!plan_zstack(&fake, g, &p, may_split != 0)) return 0;
+  out[0] = p.BN, out[1] = p.TZ, out[2] = p.ksplit, out[3] = p.cb_per, out[4] = p.wslot, out[5] = p.nslot, out[6] = p.num_tiles,
+  out[7] = p.ntn;
+  return 1;
+}
+
 bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g) {
   ZsParams p;
-  return plan_zstack(h, g, &p);
+  return plan_zstack(h, g, &p, g.ws != nullptr);
 }
 
 int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
   EncodeTiledFn enc = e2_get_tmap_encode();
   if (!enc) return e2_fail(h, E2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available");
   ZsParams p;
-  if (!plan_zstack(h, g, &p)) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: problem does not qualify");
-  p.C = g.C, p.c_pitch = g.c_pitch, p.bias = g.bias, p.gate = g.gate;
-  p.act = g.act, p.accumulate = g.accumulate, p.round_tf32 = g.round_tf32;
+  bool may_split = g.ws && !(reinterpret_cast<uintptr_t>(g.ws) & 15);
+  if (!plan_zstack(h, g, &p, may_split)) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: problem does not qualify");
+  if (zs_ws_bytes(g, p) > g.ws_bytes && !plan_zstack(h, g, &p, false))
+    return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: problem does not qualify");
+  const bool split = p.ksplit > 1;
+  // split-K: the kernel stores raw partial tiles, the epilogue moves to k_zstack_reduce
+  p.C = split ? static_cast<float*>(g.ws) : g.C;
+  p.c_pitch = split ? (g.N + 3) / 4 * 4 : g.c_pitch;
+  p.bias = split ? nullptr : g.bias, p.gate = split ? nullptr : g.gate;
+  p.act = split ? E2_ACT_LIN : g.act, p.accumulate = split ? 0 : g.accumulate, p.round_tf32 = split ? 0 : g.round_tf32;
   p.idesc0 = tc::make_idesc(2 /*TF32*/, 0, 0, 128, 0);
   {
     const char* e = getenv("E2_ZS_DBG");
     p.dbg = e ? atoi(e) : 0;
-    if (getenv("E2_ZS_INFO")) fprintf(stderr, "zstack: TZ %d NP %d nslot %d wslot %d BN %d CB %d tiles %d smem plane %d w %d\n", p.TZ, p.NP, p.nslot, p.wslot, p.BN, p.CB, p.num_tiles, p.plane_stride, p.w_bytes);
+    if (getenv("E2_ZS_INFO")) fprintf(stderr, "zstack: TZ %d NP %d nslot %d wslot %d BN %d CB %d ksplit %d units %d smem plane %d w %d\n", p.TZ, p.NP, p.nslot, p.wslot, p.BN, p.CB, p.ksplit, p.num_tiles, p.plane_stride, p.w_bytes);
   }
   p.idesc_step = (uint32_t)(p.BN >> 3) << 17;
   CUtensorMap tmA, tmB;
@@ -560,13 +676,13 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   // C (and the gate, same geometry) as 32-channel x 8 y x 4 x boxes for the epilogue's TMA store / aux loads
   CUtensorMap tmC, tmG;
   for (int which = 0; which < 2; ++which) {
-    const float* base = which == 0 ? g.C : g.gate;
+    const float* base = which == 0 ? p.C : p.gate;
     if (!base) {
       tmG = tmC;
       continue;
     }
-    cuuint64_t dims[5] = {(cuuint64_t)g.N, (cuuint64_t)g.Oy, (cuuint64_t)g.Ox, (cuuint64_t)g.Oz, (cuuint64_t)g.On};
-    cuuint64_t pitch = (cuuint64_t)g.c_pitch * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)g.N, (cuuint64_t)g.Oy, (cuuint64_t)g.Ox, (cuuint64_t)g.Oz, (cuuint64_t)g.On * p.ksplit};
+    cuuint64_t pitch = (cuuint64_t)p.c_pitch * 4;
     cuuint64_t strides[4] = {pitch, pitch * g.Oy, pitch * g.Oy * g.Ox, pitch * g.Oy * g.Ox * g.Oz};
     cuuint32_t box[5] = {32, 8, 4, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -603,5 +719,14 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   }
   h->launches++;
   E2_CUDA_CHECK(h, "conv_zstack_tc");
+  if (split) {
+    const int64_t positions = (int64_t)g.On * g.Oz * g.Ox * g.Oy;
+    const int Np = p.c_pitch;
+    k_zstack_reduce<<<e2_grid_1d(positions * (Np / 4), 256, h->sm_count, 16), 256, 0, s>>>(
+        static_cast<const float*>(g.ws), p.ksplit, positions, Np, g.N, g.C, g.c_pitch, g.bias, g.gate,
+        g.act, g.accumulate, g.round_tf32);
+    h->launches++;
+    E2_CUDA_CHECK(h, "zstack_reduce");
+  }
   return E2_OK;
 }

@@ -493,10 +493,34 @@ class Plan(object):
         launches (and the step is not graph-captured)."""
         dp = self.model.data_parallel if self.train else None
         if dp is not None and dp.world > 1:
-            self.pack()
-            dp.begin_step(self.store)
-            self._launch_all(hook=dp.on_gradients_ready)
-            dp.finish_step(self.store)
+            def dp_step():
+                self.pack()
+                dp.begin_step(self.store)
+                self._launch_all(hook=dp.on_gradients_ready)
+                dp.finish_step(self.store)
+
+            # The bucketed NCCL all-reduces (side stream, forked and joined with events) are captured into the
+            # same CUDA graph as the kernels: one graph launch per step on every rank.  If this torch/NCCL
+            # build refuses the capture the step stays eager (E2_DP_GRAPH=0 forces that).
+            if self.use_graph and dp.graph_ok:
+                if self._graph is None:
+                    dp_step()                  # eager warm-up: creates the communicators outside the capture
+                    torch.cuda.synchronize(self.device)
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                            dp_step()
+                        self._graph = g
+                    except Exception as e:     # noqa: BLE001 - any capture failure -> eager
+                        import warnings
+                        warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
+                        dp.graph_ok = False
+                        torch.cuda.synchronize(self.device)
+                        dp_step()
+                        return
+                self._graph.replay()
+                return
+            dp_step()
             return
         if self.train:
             # weights change every step: the re-pack is part of the step itself

@@ -63,6 +63,7 @@ class DataParallel(object):
         self.bucket_floats = int(bucket_mb * 1024 * 1024 / 4)
         self.overlap = overlap
         self.comm_stream = None
+        self.graph_ok = os.environ.get('E2_DP_GRAPH', '1') != '0'   # capture the step incl. the collectives
         model.data_parallel = self
         self.bytes_reduced = 0
 

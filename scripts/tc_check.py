@@ -125,6 +125,9 @@ def main():
     cases += [(1, 32, (6, 30, 18), 48, (3, 3, 3)), (1, 20, (5, 30, 26), 40, (3, 3, 3)), (2, 64, (4, 18, 18), 128, (1, 3, 3)),
               (1, 40, (7, 19, 19), 80, (4, 4, 4)), (1, 64, (3, 18, 18), 300, (3, 3, 3)), (1, 100, (5, 27, 19), 36, (2, 4, 4)),
               (1, 32, (9, 34, 34), 64, (3, 3, 3))]
+    # few tiles + long K: split-K plans of the z-stack kernel (partial tiles + reduce/epilogue kernel)
+    cases += [(1, 256, (5, 16, 16), 128, (3, 3, 3)), (1, 200, (4, 15, 14), 72, (3, 3, 3)), (1, 768, (6, 18, 18), 256, (3, 3, 3)),
+              (1, 384, (5, 28, 28), 128, (3, 3, 3))]
     for c in cases:
         ok &= check_conv(h, *c)
     for c in [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (1, 64, (3, 4, 5), 64, (2, 2, 2)), (1, 512, (7, 9, 9), 512, (2, 2, 2)),

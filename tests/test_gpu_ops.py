@@ -85,6 +85,8 @@ CONV_CASES = [
     (1, 200, (2, 6, 6), 200, (1, 1, 1)),     # 1x1x1 (the reference's tensordot shortcut)
     (1, 200, (2, 6, 6), 2, (1, 1, 1)),       # last layer, c_out == 2
     (1, 128, (4, 6, 6), 256, (3, 3, 3)),
+    (1, 256, (5, 16, 16), 128, (3, 3, 3)),   # few tiles, long K: the z-stack kernel splits K over channel blocks
+    (1, 200, (4, 15, 14), 72, (3, 3, 3)),    # same with ragged channel counts and edges
 ]
 
 
