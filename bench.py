@@ -198,7 +198,9 @@ def main():
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    # ---- e2e: the public API call with host buffers -----------------------------------
+    # ---- e2e: the public API call with host buffers (page-locked, as the contract says) --
+    x = torch.from_numpy(x).pin_memory().numpy()
+    t = torch.from_numpy(t).pin_memory().numpy()
     for _ in range(2):
         model.trainingstep(x, t, optimiser='Adam')
     barrier()
@@ -241,6 +243,16 @@ def main():
         roof = dict(bound='hbm', kernel=top, achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'],
                     traffic=None, launches=tf['n'], avg_launch_ms=tf['ms'] / tf['n'], share_of_step=tf['ms'] / step_ms,
                     peak_source='%s copy bandwidth' % peaks['source'])
+    # DRAM traffic of that family from the committed ncu pass (scripts/ncu_traffic.py), per launch like `achieved`
+    tpath = os.path.join(ROOT, 'profiles', 'traffic_%s.json' % args.workload)
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        tf_ = tj.get('families', {}).get(top)
+        if tf_:
+            roof['traffic'] = tf_['dram_bytes_per_step'] / tf['n']
+            roof['traffic_source'] = 'profiles/traffic_%s.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %s)' % (
+                args.workload, tj.get('source', ''))
+            roof['algorithmic_bytes'] = tf['bytes'] / tf['n']
     all_flops = sum(p[2] for p in prof)
     roof['step_conv_tflops'] = all_flops / (dev_ms / K * 1e-3) / 1e12
     if args.profile_out:
@@ -259,7 +271,7 @@ def main():
                 steps=K, warmup=W, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype=e2cfg.compute, data='synthetic', config=config, roofline=roof, cpu_baseline=cpu,
                 e2e=dict(value=n_vox * K / (e2e_ms * 1e-3), unit='voxels/s', h2d_bytes_per_step=in_bytes,
-                         d2h_bytes_per_step=16, ms_per_step=e2e_ms / K),
+                         d2h_bytes_per_step=16, ms_per_step=e2e_ms / K, host_buffers='page-locked numpy arrays'),
                 gpu_launches=launches_per_step * K, clocks=clocks, loss=float(loss),
                 cuda_graph=plan._graph is not None)
     print(json.dumps(line))

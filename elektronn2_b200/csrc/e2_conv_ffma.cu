@@ -57,21 +57,37 @@ __global__ void __launch_bounds__(256) k_pack_conv_wd(const float* __restrict__ 
     if (m < M && o < O) wd[(int64_t)m * op + o] = tile[tx][j];
   }
 }
-//   wf: per output channel the [C][T] slab transposed to [flip(T)][cp]; one block = one o x 32 input channels
+//   wf: per output channel the [C][T] slab transposed to [flip(T)][cp]; one block = one o x WF_CH input channels
+constexpr int WF_CH = 128;
 __global__ void __launch_bounds__(256) k_pack_conv_wf(const float* __restrict__ w, float* __restrict__ wf, int C, int kz,
-                                                      int kx, int ky, int cp, int tf32) {
-  extern __shared__ float slab[];   // [32][T + 1]
+                                                      int kx, int ky, int cp, int tf32, E2FastDiv dT) {
+  extern __shared__ float slab[];   // [WF_CH][T + 1]
   const int T = kz * kx * ky;
-  const int o = blockIdx.y, c0 = blockIdx.x * 32;
-  const int nc = min(32, C - c0);
+  const int o = blockIdx.y, c0 = blockIdx.x * WF_CH;
+  const int nc = min(WF_CH, C - c0);
   const float* src = w + ((int64_t)o * C + c0) * T;
-  for (int i = threadIdx.x; i < nc * T; i += 256) {
-    const float v = src[i];
-    slab[(i / T) * (T + 1) + (i % T)] = tf32 ? e2_round_tf32(v) : v;
+  const int n = nc * T;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (n & 3) == 0) {
+    for (int i4 = threadIdx.x; i4 < n / 4; i4 += 256) {
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(src) + i4);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i4 * 4 + e;
+        const int c = (int)dT.div((uint32_t)i);
+        slab[c * (T + 1) + (i - c * T)] = tf32 ? e2_round_tf32(v[e]) : v[e];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float v = src[i];
+      const int c = (int)dT.div((uint32_t)i);
+      slab[c * (T + 1) + (i - c * T)] = tf32 ? e2_round_tf32(v) : v;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * 32; i += 256) {
-    const int t = i >> 5, c = i & 31;
+  for (int i = threadIdx.x; i < T * WF_CH; i += 256) {
+    const int t = i / WF_CH, c = i % WF_CH;
     if (c >= nc) continue;
     const int k = t % ky, j = (t / ky) % kx, ii = t / (ky * kx);
     const int tflip = ((kz - 1 - ii) * kx + (kx - 1 - j)) * ky + (ky - 1 - k);
@@ -134,8 +150,15 @@ extern "C" int e2_conv3d_pack_weights(e2_handle* h, const e2_conv_desc* d, const
   if (total >= 4096 && T <= 343 && d->y.c <= 65535) {
     const int M = d->x.c * T;
     if (wf) {
-      dim3 grid((unsigned)((d->x.c + 31) / 32), (unsigned)d->y.c);
-      k_pack_conv_wf<<<grid, 256, sizeof(float) * 32 * (T + 1), s>>>(w, wf, d->x.c, d->kz, d->kx, d->ky, cp, tf32);
+      dim3 grid((unsigned)((d->x.c + WF_CH - 1) / WF_CH), (unsigned)d->y.c);
+      const size_t slab_bytes = sizeof(float) * WF_CH * (T + 1);
+      if (slab_bytes > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) cudaFuncSetAttribute(k_pack_conv_wf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+      }
+      k_pack_conv_wf<<<grid, 256, slab_bytes, s>>>(w, wf, d->x.c, d->kz, d->kx, d->ky, cp, tf32,
+                                                  e2_fastdiv((uint32_t)T, (uint64_t)WF_CH * T));
       h->launches++;
     }
     if (wd) {

@@ -117,6 +117,10 @@ class Plan(object):
         self.loss_op = None
         self.inputs = {}
         self._graph = None
+        self._pack_graph = None
+        self._copy_stream = None
+        self._inputs_free = None
+        self._live_sources = {}
         self._packed_version = -1
         self.grad_scale = 1.0
         dp = model.data_parallel
@@ -465,18 +469,42 @@ class Plan(object):
         self._packed_version = self.store.version
 
     def feed(self, values):
-        """H2D copies of the inputs from pinned host memory (async on the current stream).
+        """H2D copies of the inputs.  A source array that already lives in page-locked memory is copied from where
+        it is; anything else goes through the plan's pinned staging buffer first.  The copies run on a side stream
+        that waits only for the previous step's readers of the input buffers, so they overlap with whatever else
+        is still queued (optimiser, weight re-pack); the compute stream waits for them.
         Returns the number of bytes copied."""
         nbytes = 0
-        for n, a in values.items():
-            t, pinned, staging = self.inputs[n]
-            a = np.asarray(a, dtype=np.float32)
-            if tuple(a.shape) != tuple(pinned.shape):
-                raise ValueError("Input '%s' expects shape %s, got %s" % (n.name, tuple(pinned.shape), a.shape))
-            pinned.copy_(torch.from_numpy(np.ascontiguousarray(a)))
-            dst = staging if staging is not None else t.buf[t.offset:t.offset + pinned.numel()].view(pinned.shape)
-            dst.copy_(pinned, non_blocking=True)
-            nbytes += pinned.numel() * 4
+        cur = torch.cuda.current_stream(self.device)
+        side = cur
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("Plan.feed() inside a CUDA-graph capture")
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        side = self._copy_stream
+        if self._inputs_free is not None:
+            side.wait_event(self._inputs_free)
+        else:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for n, a in values.items():
+                t, pinned, staging = self.inputs[n]
+                a = np.asarray(a, dtype=np.float32)
+                if tuple(a.shape) != tuple(pinned.shape):
+                    raise ValueError("Input '%s' expects shape %s, got %s" % (n.name, tuple(pinned.shape), a.shape))
+                src = None
+                if a.flags['C_CONTIGUOUS'] and a.flags['WRITEABLE']:
+                    cand = torch.from_numpy(a)
+                    if cand.is_pinned():
+                        src = cand
+                        self._live_sources[n] = cand      # keep the caller's buffer alive until the copy has run
+                if src is None:
+                    pinned.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+                    src = pinned
+                dst = staging if staging is not None else t.buf[t.offset:t.offset + pinned.numel()].view(pinned.shape)
+                dst.copy_(src, non_blocking=True)
+                nbytes += pinned.numel() * 4
+        cur.wait_stream(side)
         return nbytes
 
     def _launch_all(self, hook=None):
@@ -487,14 +515,35 @@ class Plan(object):
             if hook is not None and f.param_end is not None:
                 hook(f.param_end)
 
+    def _ensure_packed(self, need_dgrad=None):
+        """Re-pack the weights (tf32 rounding, tap flip, K-major layouts) if the parameters changed since the last
+        pack.  In training this is a small CUDA graph of its own: ``Model.trainingstep`` replays it right after
+        the optimiser so the next step starts with the first convolution."""
+        if self._packed_version == self.store.version:
+            return
+        if self.train and self.use_graph:
+            if self._pack_graph is None:
+                self.pack(need_dgrad)          # warm-up outside capture
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    self.pack(need_dgrad)
+                self._pack_graph = g
+            self._pack_graph.replay()
+            self._packed_version = self.store.version
+        else:
+            self.pack(need_dgrad)
+
+    def repack(self):
+        self._ensure_packed()
+
     def execute(self):
-        """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.
-        With data parallelism the bucketed all-reduce is interleaved with the backward
-        launches (and the step is not graph-captured)."""
+        """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.  With data parallelism
+        the bucketed all-reduce is interleaved with the backward launches and captured with them."""
         dp = self.model.data_parallel if self.train else None
+        self._ensure_packed(None if self.train else False)
         if dp is not None and dp.world > 1:
             def dp_step():
-                self.pack()
                 dp.begin_step(self.store)
                 self._launch_all(hook=dp.on_gradients_ready)
                 dp.finish_step(self.store)
@@ -517,33 +566,16 @@ class Plan(object):
                         dp.graph_ok = False
                         torch.cuda.synchronize(self.device)
                         dp_step()
+                        self._mark_inputs_free()
                         return
                 self._graph.replay()
-                return
-            dp_step()
-            return
-        if self.train:
-            # weights change every step: the re-pack is part of the step itself
-            if self.use_graph:
-                if self._graph is None:
-                    self.pack()
-                    self._launch_all()  # warm-up outside capture
-                    torch.cuda.synchronize(self.device)
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self.pack()
-                        self._launch_all()
-                    self._graph = g
-                self._graph.replay()
             else:
-                self.pack()
-                self._launch_all()
+                dp_step()
+            self._mark_inputs_free()
             return
-        if self._packed_version != self.store.version:
-            self.pack(need_dgrad=False)
         if self.use_graph:
             if self._graph is None:
-                self._launch_all()
+                self._launch_all()  # warm-up outside capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -552,6 +584,12 @@ class Plan(object):
             self._graph.replay()
         else:
             self._launch_all()
+        self._mark_inputs_free()
+
+    def _mark_inputs_free(self):
+        if self._inputs_free is None:
+            self._inputs_free = torch.cuda.Event()
+        self._inputs_free.record()
 
     def launches_per_step(self):
         """Kernel launches of one step (counted by the library, eager pass)."""
@@ -580,7 +618,17 @@ class Plan(object):
             torch.cuda.synchronize(self.device)
             for i, (a, b) in enumerate(evs):
                 acc[i] += a.elapsed_time(b)
-        return [(f.label, f.kind, f.flops, f.bytes, acc[i] / repeats) for i, f in enumerate(all_ops)]
+        out = [(f.label, f.kind, f.flops, f.bytes, acc[i] / repeats) for i, f in enumerate(all_ops)]
+        if self.train:
+            # the per-step weight re-pack (read the fp32 master once, write the fwd and dgrad layouts)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(repeats):
+                self.pack()
+            b.record()
+            torch.cuda.synchronize(self.device)
+            out.append(('pack_weights', 'hbm', 0.0, 12.0 * self.store.n_reg, a.elapsed_time(b) / repeats))
+        return out
 
     def fetch(self, node):
         if isinstance(node, loss_nodes.AggregateLoss):

@@ -146,8 +146,10 @@ class Model(object):
         plan.execute()
         if self.data_parallel is not None:
             self.data_parallel.allreduce_gradients(plan.store)
+        plan.loss_op.read_async()                  # D2H of the loss scalars, behind the backward pass
         opt.step(plan.store)
-        loss = np.float32(plan.loss_op.read()[0])  # the only device->host sync of the step
+        plan.repack()                              # next step's weights; overlaps with the host side of the next call
+        loss = np.float32(plan.loss_op.read_wait()[0])  # the only device->host sync of the step
         if kwargs.get('update_loss', False):
             loss = self.loss(*args)
         t = time.time() - t0

@@ -232,6 +232,21 @@ class LossOp(object):
         n_pos = self.logits.desc.positions
         return float(s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
 
+    def read_async(self):
+        """Enqueue the D2H copy of the 4 scalars behind the work submitted so far; ``read_wait`` blocks on that
+        copy only, so kernels enqueued afterwards (optimiser, weight re-pack) overlap with the host."""
+        if getattr(self, '_host', None) is None:
+            self._host = torch.empty(4, dtype=torch.float32).pin_memory()
+            self._ev = torch.cuda.Event()
+        self._host.copy_(self.scalars, non_blocking=True)
+        self._ev.record()
+
+    def read_wait(self):
+        self._ev.synchronize()
+        s = self._host.numpy()
+        n_pos = self.logits.desc.positions
+        return float(s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
+
 
 def act_bwd(h, t, act, y, dy, dpre):
     h.call('e2_act_bwd', C.byref(t.desc), _lib.i32(ACT[act]), y.ptr(), dy.ptr(), dpre.ptr(), h.stream())
