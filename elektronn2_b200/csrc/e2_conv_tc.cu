@@ -22,7 +22,8 @@ namespace {
 constexpr int BM = 128;          // rows per tile (TMEM lanes)
 constexpr int BK = 32;           // fp32 per K block = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 4;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;     // two per TMEM lane quadrant, alternating over the 32-column chunks of the tile
+constexpr int NUM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct TcParams {
   int On, Oz, Ox, Oy;        // output position grid
@@ -45,6 +46,37 @@ struct TcParams {
   int its_per_split;         // K iterations (tap x channel block) per blockIdx.z
   float* part;               // split-K: raw partial tiles [z][n tile][m tile][col/4][row][4]; NULL: fused epilogue
 };
+
+// Epilogue of one transposed 32 x 32 chunk: this lane serves rows rsub, rsub+4, ... (8 lanes per 128-byte row).
+// ACT: 0 lin, 1 relu, 2 anything else -- compile-time so the row loop carries no per-value activation branches.
+template <int ACT>
+__device__ __forceinline__ void tc_store_rows(const TcParams& p, const uint8_t* st, const int64_t (&rowofs)[8], uint32_t rowmask,
+                                              int64_t colofs, float4 b4, int rsub, int pc) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (!((rowmask >> it) & 1u)) continue;
+    const int rl = it * 4 + rsub;
+    const int64_t ofs = rowofs[it] + colofs;
+    const float4 raw = *reinterpret_cast<const float4*>(st + rl * 128 + ((pc ^ (rl & 7)) << 4));
+    float4 v = make_float4(raw.x + b4.x, raw.y + b4.y, raw.z + b4.z, raw.w + b4.w);
+    if (ACT == 1) {
+      v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    } else if (ACT == 2) {
+      v.x = e2_apply_act(v.x, p.act), v.y = e2_apply_act(v.y, p.act), v.z = e2_apply_act(v.z, p.act), v.w = e2_apply_act(v.w, p.act);
+    }
+    if (p.gate) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + ofs));
+      v.x = g4.x > 0.f ? v.x : 0.f, v.y = g4.y > 0.f ? v.y : 0.f;
+      v.z = g4.z > 0.f ? v.z : 0.f, v.w = g4.w > 0.f ? v.w : 0.f;
+    }
+    if (p.accumulate) {
+      const float4 c4 = *reinterpret_cast<const float4*>(p.C + ofs);
+      v.x += c4.x, v.y += c4.y, v.z += c4.z, v.w += c4.w;
+    }
+    if (p.round_tf32) v.x = e2_round_tf32(v.x), v.y = e2_round_tf32(v.y), v.z = e2_round_tf32(v.z), v.w = e2_round_tf32(v.w);
+    *reinterpret_cast<float4*>(p.C + ofs) = v;
+  }
+}
 
 __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -146,6 +178,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
     // activation run in the transposed domain.  Row offsets are decoded once per tile; the chunk loop is kept
     // rolled -- an unrolled version of this epilogue was 17 k instructions and instruction-fetch bound.
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;       // warps w and w+4 share a quadrant and alternate over the chunks
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
     uint8_t* st = smA + (warp - 2) * 4096;
@@ -167,7 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
       if (!vec_ok && it == 0) break;
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
       uint32_t r[32];
       if (p.BN - c0 >= 32) {
         tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -206,26 +239,9 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
           }
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = make_float4(__ldg(p.bias + ch), __ldg(p.bias + ch + 1), __ldg(p.bias + ch + 2), __ldg(p.bias + ch + 3));
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            if (!((rowmask >> it) & 1u)) continue;
-            const int rl = it * 4 + rsub;
-            const int64_t ofs = rowofs[it] + colofs;
-            const float4 raw = *reinterpret_cast<const float4*>(st + rl * 128 + ((pc ^ (rl & 7)) << 4));
-            float4 v = make_float4(e2_apply_act(raw.x + b4.x, p.act), e2_apply_act(raw.y + b4.y, p.act),
-                                   e2_apply_act(raw.z + b4.z, p.act), e2_apply_act(raw.w + b4.w, p.act));
-            if (p.gate) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + ofs));
-              v.x = g4.x > 0.f ? v.x : 0.f, v.y = g4.y > 0.f ? v.y : 0.f;
-              v.z = g4.z > 0.f ? v.z : 0.f, v.w = g4.w > 0.f ? v.w : 0.f;
-            }
-            if (p.accumulate) {
-              const float4 c4 = *reinterpret_cast<const float4*>(p.C + ofs);
-              v.x += c4.x, v.y += c4.y, v.z += c4.z, v.w += c4.w;
-            }
-            if (p.round_tf32) v.x = e2_round_tf32(v.x), v.y = e2_round_tf32(v.y), v.z = e2_round_tf32(v.z), v.w = e2_round_tf32(v.w);
-            *reinterpret_cast<float4*>(p.C + ofs) = v;
-          }
+          if (p.act == E2_ACT_RELU) tc_store_rows<1>(p, st, rowofs, rowmask, colofs, b4, rsub, pc);
+          else if (p.act == E2_ACT_LIN) tc_store_rows<0>(p, st, rowofs, rowmask, colofs, b4, rsub, pc);
+          else tc_store_rows<2>(p, st, rowofs, rowmask, colofs, b4, rsub, pc);
         }
       } else if (rowmask & 1u) {
         // scalar path (channel counts / pointers that are not 16-byte friendly): one element at a time

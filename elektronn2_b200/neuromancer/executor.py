@@ -117,7 +117,9 @@ class Plan(object):
         self.loss_op = None
         self.inputs = {}
         self._graph = None
+        self._pack_stream = None
         self._pack_graph = None
+        self.overlap_pack = os.environ.get('E2_PACK_OVERLAP', '0') == '1'
         self._copy_stream = None
         self._inputs_free = None
         self._live_sources = {}
@@ -516,74 +518,135 @@ class Plan(object):
                 hook(f.param_end)
 
     def _ensure_packed(self, need_dgrad=None):
-        """Re-pack the weights (tf32 rounding, tap flip, K-major layouts) if the parameters changed since the last
-        pack.  In training this is a small CUDA graph of its own: ``Model.trainingstep`` replays it right after
-        the optimiser so the next step starts with the first convolution."""
+        """Re-pack the weights (tf32 rounding, tap flip, K-major layouts) if the parameters changed since the
+        last pack (inference plans; training plans re-pack inside every step, see ``_step_with_pack``)."""
+        if self._packed_version != self.store.version:
+            self.pack(need_dgrad)
+
+    def _ensure_packed_train(self):
+        """Training: the re-pack is a small CUDA graph of its own.  ``Model.trainingstep`` replays it right after
+        the optimiser, so it overlaps with the host side of the next call and the next step starts with the
+        first convolution; a step that finds stale packed weights replays it first."""
         if self._packed_version == self.store.version:
             return
-        if self.train and self.use_graph:
+        if self.use_graph:
             if self._pack_graph is None:
-                self.pack(need_dgrad)          # warm-up outside capture
+                self.pack()                    # warm-up outside capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode='thread_local'):
-                    self.pack(need_dgrad)
+                    self.pack()
                 self._pack_graph = g
             self._pack_graph.replay()
             self._packed_version = self.store.version
         else:
-            self.pack(need_dgrad)
+            self.pack()
 
     def repack(self):
-        self._ensure_packed()
+        """Refresh the packed weights now (after an optimiser step) instead of at the start of the next step."""
+        if not self.train:
+            self._ensure_packed(False)
+        elif not self.overlap_pack:
+            self._ensure_packed_train()
+
+    EARLY_PACKS = 2     # layers whose weights are packed on the compute stream, ahead of the first convolution
+
+    def _step_with_pack(self, hook=None):
+        """E2_PACK_OVERLAP=1 variant of a training step: the weight re-pack (fp32 master -> tf32 forward / dgrad
+        layouts, ~230 MB of traffic for unet3d) is part of the step's launch list; only the first layers' packs sit
+        in front of the forward pass, the rest run on a side stream underneath the first (tensor-bound) convolutions
+        and are joined before the third conv layer.  Measured on unet3d: no gain over the sequential order (the
+        packs slow conv0/conv1 by what they save), so the default keeps the re-pack outside the step graph."""
+        conv_idx = [i for i, f in enumerate(self.fwd_ops) if f.label.startswith(('conv_fwd:', 'upconv_fwd:'))]
+        k = self.EARLY_PACKS
+        if len(conv_idx) <= k or len(conv_idx) != len(self.pack_ops):
+            self.pack()
+            self._launch_all(hook)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._pack_stream is None:
+            self._pack_stream = torch.cuda.Stream(device=self.device)
+        side = self._pack_stream
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            for op in self.pack_ops[k:]:
+                op.pack(True)
+            join.record(side)
+        for op in self.pack_ops[:k]:
+            op.pack(True)
+        self._packed_version = self.store.version
+        for i, f in enumerate(self.fwd_ops):
+            if i == conv_idx[k]:
+                main.wait_event(join)
+            f()
+        for f in self.bwd_ops:
+            f()
+            if hook is not None and f.param_end is not None:
+                hook(f.param_end)
 
     def execute(self):
         """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.  With data parallelism
         the bucketed all-reduce is interleaved with the backward launches and captured with them."""
-        dp = self.model.data_parallel if self.train else None
-        self._ensure_packed(None if self.train else False)
-        if dp is not None and dp.world > 1:
-            def dp_step():
-                dp.begin_step(self.store)
-                self._launch_all(hook=dp.on_gradients_ready)
-                dp.finish_step(self.store)
-
-            # The bucketed NCCL all-reduces (side stream, forked and joined with events) are captured into the
-            # same CUDA graph as the kernels: one graph launch per step on every rank.  If this torch/NCCL
-            # build refuses the capture the step stays eager (E2_DP_GRAPH=0 forces that).
-            if self.use_graph and dp.graph_ok:
+        if not self.train:
+            self._ensure_packed(False)
+            if self.use_graph:
                 if self._graph is None:
-                    dp_step()                  # eager warm-up: creates the communicators outside the capture
+                    self._launch_all()  # warm-up outside capture
                     torch.cuda.synchronize(self.device)
-                    try:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, capture_error_mode='thread_local'):
-                            dp_step()
-                        self._graph = g
-                    except Exception as e:     # noqa: BLE001 - any capture failure -> eager
-                        import warnings
-                        warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
-                        dp.graph_ok = False
-                        torch.cuda.synchronize(self.device)
-                        dp_step()
-                        self._mark_inputs_free()
-                        return
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch_all()
+                    self._graph = g
                 self._graph.replay()
             else:
-                dp_step()
+                self._launch_all()
             self._mark_inputs_free()
             return
-        if self.use_graph:
+        dp = self.model.data_parallel
+        if dp is not None and dp.world <= 1:
+            dp = None
+
+        if not self.overlap_pack:
+            self._ensure_packed_train()
+
+        def body():
+            hook = dp.on_gradients_ready if dp is not None else None
+            if dp is not None:
+                dp.begin_step(self.store)
+            if self.overlap_pack:
+                self._step_with_pack(hook)
+            else:
+                self._launch_all(hook)
+            if dp is not None:
+                dp.finish_step(self.store)
+
+        # Data parallel: the bucketed NCCL all-reduces (side stream, forked and joined with events) are captured
+        # into the same CUDA graph as the kernels: one graph launch per step on every rank.  If this torch/NCCL
+        # build refuses the capture the step stays eager (E2_DP_GRAPH=0 forces that).
+        if self.use_graph and (dp is None or dp.graph_ok):
             if self._graph is None:
-                self._launch_all()  # warm-up outside capture
+                body()                      # eager warm-up (also creates the communicators outside the capture)
                 torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch_all()
-                self._graph = g
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                        body()
+                    self._graph = g
+                except Exception as e:      # noqa: BLE001 - any capture failure -> eager
+                    if dp is None:
+                        raise
+                    import warnings
+                    warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
+                    dp.graph_ok = False
+                    torch.cuda.synchronize(self.device)
+                    body()
+                    self._mark_inputs_free()
+                    return
             self._graph.replay()
         else:
-            self._launch_all()
+            body()
         self._mark_inputs_free()
 
     def _mark_inputs_free(self):
