@@ -727,6 +727,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   conv_fwd_problem(d, x, wf, bias, y, &g);
   g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
+  if (e2_conv_pw_fwd_ok(g)) return e2_launch_conv_pw_fwd(h, g, s);
   if (d->x.c == 1) {
     // a single input channel is HBM-bound either way; with 16-byte rows (pitch % 4 == 0) the halo-plane
     // tcgen05 kernel takes it (one K = 8 MMA per tap and plane, TMA zero-fills the 7 missing channels) and
@@ -737,6 +738,8 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
     if (tc1 && d->compute == E2_COMPUTE_TF32 && d->x.c_pitch % 4 == 0 && d->y.c >= 8 &&
         !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(wf) & 15) && e2_conv_zstack_tc_ok(h, g))
       return e2_launch_conv_zstack_tc(h, g, s);
+    // TF32 mode: the threads build the im2col tile, the tensor core does the 27 MACs per output (e2_conv_c1_tc.cu)
+    if (d->compute == E2_COMPUTE_TF32 && e2_conv_c1_fwd_tc_ok(g)) return e2_launch_conv_c1_fwd_tc(h, g, s);
     if (e2_conv_c1_fwd_reg_ok(g)) return e2_launch_conv_c1_fwd_reg(h, g, s);
     return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);
   }
@@ -752,6 +755,7 @@ extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float*
   conv_dgrad_problem(d, dy, wd, dx, relu_gate, &g);
   g.ws = ws, g.ws_bytes = ws_bytes;
   cudaStream_t s = (cudaStream_t)stream;
+  if (e2_conv_pw_dgrad_ok(g)) return e2_launch_conv_pw_dgrad(h, g, s);
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
@@ -764,7 +768,9 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   conv_wgrad_problem(d, x, dy, dw, &g);
   bool db_done = false;
   cudaStream_t s = (cudaStream_t)stream;
-  if (d->x.c == 1 && e2_conv_c1_wgrad_reg_ok(g))
+  if (e2_conv_pw_wgrad_ok(g))
+    rc = e2_launch_conv_pw_wgrad(h, g, db, s), db_done = (db != nullptr);
+  else if (d->x.c == 1 && e2_conv_c1_wgrad_reg_ok(g))
     rc = e2_launch_conv_c1_wgrad_reg(h, g, db, s), db_done = (db != nullptr);
   else if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))
     rc = e2_launch_conv_c1_wgrad_line(h, g, s);

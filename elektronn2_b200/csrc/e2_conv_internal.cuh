@@ -52,6 +52,17 @@ bool e2_conv_c1_wgrad_reg_ok(const ReduceGemm& g);
 int e2_launch_conv_c1_wgrad_reg(e2_handle* h, const ReduceGemm& g, float* db, cudaStream_t s);
 int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pitch, float* db, cudaStream_t s);
 
+// first layer on the tensor cores: thread-built im2col tile + tcgen05 (e2_conv_c1_tc.cu), TF32 mode
+bool e2_conv_c1_fwd_tc_ok(const GatherGemm& g);
+int e2_launch_conv_c1_fwd_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+// 1x1x1 convolutions with <= 4 output channels (e2_conv_pw.cu): streaming fp32 kernels; wgrad fuses the bias gradient
+bool e2_conv_pw_fwd_ok(const GatherGemm& g);
+int e2_launch_conv_pw_fwd(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+bool e2_conv_pw_dgrad_ok(const GatherGemm& g);
+int e2_launch_conv_pw_dgrad(e2_handle* h, const GatherGemm& g, cudaStream_t s);
+bool e2_conv_pw_wgrad_ok(const ReduceGemm& g);
+int e2_launch_conv_pw_wgrad(e2_handle* h, const ReduceGemm& g, float* db, cudaStream_t s);
+
 // tcgen05 path (e2_conv_tc.cu)
 bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);

@@ -77,6 +77,8 @@ CONV_CASES = [
     # (n, c_in, spatial, c_out, k)
     (1, 1, (5, 20, 21), 20, (1, 4, 4)),      # first layer of neuro3d_lite (c_in == 1 kernel)
     (1, 1, (6, 12, 12), 32, (3, 3, 3)),      # first layer of unet3d
+    (1, 1, (6, 40, 40), 32, (3, 3, 3)),      # same, large enough for the tensor-core first-layer kernel (ragged tiles)
+    (2, 1, (5, 40, 45), 20, (1, 6, 6)),      # neuro3d first layer: 36 taps = two K blocks, 20 channels padded to 32
     (2, 20, (5, 12, 11), 40, (3, 3, 3)),     # odd channel counts
     (1, 40, (4, 9, 9), 150, (2, 4, 4)),      # even, asymmetric kernel
     (1, 35, (3, 8, 8), 42, (1, 3, 3)),       # litelite channels
