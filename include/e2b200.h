@@ -244,6 +244,15 @@ int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int
 int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom, float wd,
                 int32_t apply_wd, void* stream);
 
+/* ---------------------------------------------------------------- introspection
+ * Host-only (no GPU needed): the tile plan the z-stack conv kernel would use for a conv of K input / N output
+ * channels with a (kz,kx,ky) filter and (Oz,Ox,Oy) output positions on a device with sm_count SMs.
+ * out[8] = {BN, TZ, ksplit, channel blocks per split, weight slots, plane slots, units, N tiles}.
+ * Returns 1 if the kernel takes the problem, 0 if it is left to the tap kernel.  (No reference counterpart:
+ * cuDNN's algorithm choice is opaque; used by tests/test_host_api.py to pin the planner.) */
+int e2_debug_zstack_plan(int sm_count, int K, int N, int Oz, int Ox, int Oy, int kz, int kx, int ky, int may_split,
+                         int* out);
+
 #ifdef __cplusplus
 }
 #endif

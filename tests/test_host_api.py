@@ -193,3 +193,33 @@ def test_tile_geometry_config4():
     tiles = tile_list(n_tiles)
     parts = [shard_tiles(tiles, r, 8) for r in range(8)]
     assert sum(len(p) for p in parts) == 2268 and sorted(sum(parts, [])) == sorted(tiles)
+
+
+def test_zstack_planner_invariants():
+    """Host-side tile planner of the z-stack conv kernel (no GPU): resource limits hold for every
+    BASELINE layer shape, the K split only appears when a workspace is allowed, and layers with few
+    tiles and a long reduction (unet3d mconv0: 768 -> 256 on 12x16x16) are split over channel blocks."""
+    import ctypes as C
+    from elektronn2_b200 import _lib
+    fn = _lib.lib.e2_debug_zstack_plan
+    layers = [(32, 64, 112, 128, 128), (64, 64, 54, 62, 62), (64, 128, 52, 60, 60), (128, 128, 24, 28, 28),
+              (128, 256, 22, 26, 26), (768, 256, 12, 16, 16), (256, 256, 10, 14, 14), (384, 128, 18, 26, 26),
+              (128, 128, 16, 24, 24), (192, 64, 30, 46, 46), (64, 64, 28, 44, 44), (64, 32, 114, 130, 130)]
+    out = (C.c_int * 8)()
+    for K, N, z, x, y in layers:
+        for may_split in (0, 1):
+            assert fn(148, K, N, z, x, y, 3, 3, 3, may_split, out) == 1, (K, N, z, x, y)
+            bn, tz, ks, cb_per, wsl, nslot, units, ntn = list(out)
+            assert bn % 16 == 0 and 16 <= bn <= 256 and min(tz, 3) * bn <= 256      # widest stacked MMA
+            assert 2 * tz * bn <= 512                                               # double-buffered TMEM accumulators
+            assert ntn * bn >= N and (ntn == 1 or bn % 32 == 0)
+            assert wsl >= 2 and nslot in (tz + 2, 2 * (tz + 2))
+            cbn = (K + 31) // 32
+            assert 1 <= ks <= cbn and (ks - 1) * cb_per < cbn <= ks * cb_per       # no empty split
+            if not may_split:
+                assert ks == 1
+            ntz = (z + tz - 1) // tz
+            assert units == ntz * ((x + 15) // 16) * ((y + 7) // 8) * ntn * ks
+    assert fn(148, 768, 256, 12, 16, 16, 3, 3, 3, 1, out) == 1 and out[2] > 1
+    assert fn(148, 32, 64, 112, 128, 128, 3, 3, 3, 1, out) == 1 and out[2] == 1      # 3584 tiles: never split
+    assert fn(148, 256, 512, 7, 9, 9, 3, 3, 3, 1, out) == 0                          # 9x9 planes: tap kernel
