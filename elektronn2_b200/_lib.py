@@ -157,6 +157,8 @@ class Handle(object):
             raise E2Error(rc, "e2_create(device=%d) failed" % self.device)
         self._h = h
         self._ws, self._ws_old = None, []     # caller-owned scratch shared by all ops of this handle's stream
+        self._ws_side = {}                    # further scratch buffers for ops launched on side streams (ws_slot >= 1)
+        self.ws_slot = 0
         msg = lib.e2_last_error(self._h)
         if msg:
             raise E2Error(ERR_UNSUPPORTED, msg.decode())
@@ -176,9 +178,19 @@ class Handle(object):
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device='cuda:%d' % self.device)
 
     def workspace(self):
-        """(void* ws, size_t ws_bytes) for the entry points that take a workspace."""
+        """(void* ws, size_t ws_bytes) for the entry points that take a workspace.  ``ws_slot`` >= 1 selects another
+        buffer of the same size: kernels that run concurrently on a side stream must not share scratch."""
         if self._ws is None:
             return None, 0
+        if self.ws_slot >= 1:
+            import torch
+            cur = self._ws_side.get(self.ws_slot)
+            if cur is None or cur.numel() < self._ws.numel():
+                if cur is not None:
+                    self._ws_old.append(cur)
+                cur = torch.empty(self._ws.numel(), dtype=torch.uint8, device='cuda:%d' % self.device)
+                self._ws_side[self.ws_slot] = cur
+            return C.c_void_p(cur.data_ptr()), C.c_size_t(cur.numel())
         return C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel())
 
     def call(self, name, *args):

@@ -564,8 +564,20 @@ __global__ void __launch_bounds__(256) k_bias_grad(const float* __restrict__ dy,
   const int c = blockIdx.y * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5;
   float a = 0.f;
-  if (c < C)
-    for (int64_t m = (int64_t)blockIdx.x * 8 + lane; m < M; m += (int64_t)gridDim.x * 8) a += __ldg(dy + m * pitch + c);
+  if (c < C) {
+    // four independent loads in flight per thread: the serial a += load chain was latency-bound
+    const int64_t step = (int64_t)gridDim.x * 8;
+    int64_t m = (int64_t)blockIdx.x * 8 + lane;
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (; m + 3 * step < M; m += 4 * step) {
+      a += __ldg(dy + m * pitch + c);
+      a1 += __ldg(dy + (m + step) * pitch + c);
+      a2 += __ldg(dy + (m + 2 * step) * pitch + c);
+      a3 += __ldg(dy + (m + 3 * step) * pitch + c);
+    }
+    for (; m < M; m += step) a += __ldg(dy + m * pitch + c);
+    a += a1 + a2 + a3;
+  }
   red[lane][threadIdx.x & 31] = a;
   __syncthreads();
   if (lane == 0 && c < C) {

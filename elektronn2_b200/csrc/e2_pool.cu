@@ -61,7 +61,8 @@ struct PoolP {
 // One block per OUTPUT row (n, zo, xo): the row's Yo*C outputs and each of its window taps are contiguous in
 // HBM, the block decomposes its row index once, and a thread needs a single multiply-high to split its item
 // into (yo, channel group) -- the 64-bit div/mod chain of a flat index cost more than the memory traffic.
-template <int V>
+// PZ/PX/PY > 0: compile-time window (all loads of a window are issued before the compares); 0: run-time window
+template <int V, int PZ, int PX, int PY>
 __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, E2FastDiv dcv, const float* __restrict__ x,
                                                      const float* __restrict__ bias, float* __restrict__ y,
                                                      int* __restrict__ amax) {
@@ -81,23 +82,48 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, E2FastDiv dcv, con
     int bi[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) best[j] = -INFINITY, bi[j] = 0;
-    bool first = true;
-    for (int dz = 0; dz < p.pz; ++dz)
-      for (int dx = 0; dx < p.px; ++dx) {
-        const int lin0 = ((zo * p.pz + dz) * p.X + xo * p.px + dx) * p.Y + yo * p.py;
-        const float* src = xn + (int64_t)lin0 * p.xp + c;
-#pragma unroll 2
-        for (int dy = 0; dy < p.py; ++dy) {
-          Vec<V> v;
-          v.load(src + (int64_t)dy * p.xp);
+    if (PZ > 0) {
+      Vec<V> w[PZ > 0 ? PZ * PX * PY : 1];
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            // strict '>' keeps the FIRST maximum in (z,x,y) scan order
-            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin0 + dy;
+      for (int dz = 0; dz < PZ; ++dz)
+#pragma unroll
+        for (int dx = 0; dx < PX; ++dx)
+#pragma unroll
+          for (int dy = 0; dy < PY; ++dy) {
+            const int lin = ((zo * PZ + dz) * p.X + xo * PX + dx) * p.Y + yo * PY + dy;
+            w[(dz * PX + dx) * PY + dy].load(xn + (int64_t)lin * p.xp + c);
           }
-          first = false;
+#pragma unroll
+      for (int dz = 0; dz < PZ; ++dz)
+#pragma unroll
+        for (int dx = 0; dx < PX; ++dx)
+#pragma unroll
+          for (int dy = 0; dy < PY; ++dy) {
+            const int lin = ((zo * PZ + dz) * p.X + xo * PX + dx) * p.Y + yo * PY + dy;
+            const int wi = (dz * PX + dx) * PY + dy;
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (wi == 0 || w[wi].v[j] > best[j]) best[j] = w[wi].v[j], bi[j] = lin;   // strict '>': FIRST maximum
+          }
+    } else {
+      bool first = true;
+      for (int dz = 0; dz < p.pz; ++dz)
+        for (int dx = 0; dx < p.px; ++dx) {
+          const int lin0 = ((zo * p.pz + dz) * p.X + xo * p.px + dx) * p.Y + yo * p.py;
+          const float* src = xn + (int64_t)lin0 * p.xp + c;
+#pragma unroll 2
+          for (int dy = 0; dy < p.py; ++dy) {
+            Vec<V> v;
+            v.load(src + (int64_t)dy * p.xp);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              // strict '>' keeps the FIRST maximum in (z,x,y) scan order
+              if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin0 + dy;
+            }
+            first = false;
+          }
         }
-      }
+    }
     Vec<V> o;
     IVec<V> oi;
 #pragma unroll
@@ -270,10 +296,19 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
   E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_fwd: too many rows");
   if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp})) {
     const int rowlen = p.Yo * (p.C / 4);
-    k_maxpool_fwd<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C / 4, rowlen), x, bias, y, argmax);
+    const E2FastDiv dv = e2_fastdiv(p.C / 4, rowlen);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.pz == 2 && p.px == 2 && p.py == 2)
+      k_maxpool_fwd<4, 2, 2, 2><<<(int)rows, pool_block(rowlen), 0, s>>>(p, dv, x, bias, y, argmax);
+    else if (p.pz == 1 && p.px == 2 && p.py == 2)
+      k_maxpool_fwd<4, 1, 2, 2><<<(int)rows, pool_block(rowlen), 0, s>>>(p, dv, x, bias, y, argmax);
+    else if (p.pz == 2 && p.px == 1 && p.py == 1)
+      k_maxpool_fwd<4, 2, 1, 1><<<(int)rows, pool_block(rowlen), 0, s>>>(p, dv, x, bias, y, argmax);
+    else
+      k_maxpool_fwd<4, 0, 0, 0><<<(int)rows, pool_block(rowlen), 0, s>>>(p, dv, x, bias, y, argmax);
   } else {
     const int rowlen = p.Yo * p.C;
-    k_maxpool_fwd<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
+    k_maxpool_fwd<1, 0, 0, 0><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
   }
   h->launches++;
   E2_CUDA_CHECK(h, "maxpool3d_fwd");

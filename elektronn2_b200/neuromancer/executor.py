@@ -118,6 +118,9 @@ class Plan(object):
         self.inputs = {}
         self._graph = None
         self._pack_stream = None
+        self._wgrad_stream = None
+        self.wgrad_overlap = self.train and os.environ.get('E2_WGRAD_OVERLAP', '1') != '0'
+        self.wgrad_streams = max(1, int(os.environ.get('E2_WGRAD_STREAMS', '2')))
         self._pack_graph = None
         self.overlap_pack = os.environ.get('E2_PACK_OVERLAP', '0') == '1'
         self._copy_stream = None
@@ -509,13 +512,53 @@ class Plan(object):
         cur.wait_stream(side)
         return nbytes
 
+    _WGRAD = ('conv_wgrad:', 'upconv_wgrad:')
+
     def _launch_all(self, hook=None):
         for f in self.fwd_ops:
             f()
+        self._launch_bwd(hook)
+
+    def _launch_bwd(self, hook=None):
+        """Backward launches.  A weight gradient feeds nothing but the optimiser (and the all-reduce), so the wgrad
+        kernels go to a side stream, each behind an event that marks its place in the sequence, and run underneath
+        the dgrad chain: the layers at the bottom of the U-Net have too few tiles to fill 148 SMs on their own.
+        They use the handle's second scratch buffer.  Joined before the step ends."""
+        if not self.wgrad_overlap:
+            for f in self.bwd_ops:
+                f()
+                if hook is not None and f.param_end is not None:
+                    hook(f.param_end)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._wgrad_stream is None:
+            self._wgrad_stream = [torch.cuda.Stream(device=self.device) for _ in range(self.wgrad_streams)]
+        used = False
+        k = 0
         for f in self.bwd_ops:
-            f()
-            if hook is not None and f.param_end is not None:
-                hook(f.param_end)
+            if f.label.startswith(self._WGRAD):
+                slot = k % len(self._wgrad_stream)
+                side = self._wgrad_stream[slot]
+                k += 1
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self.h.ws_slot = 1 + slot
+                    try:
+                        f()
+                        if hook is not None and f.param_end is not None:
+                            hook(f.param_end)
+                    finally:
+                        self.h.ws_slot = 0
+                used = True
+            else:
+                f()
+                if hook is not None and f.param_end is not None:
+                    hook(f.param_end)
+        if used:
+            for side in self._wgrad_stream:
+                main.wait_stream(side)
 
     def _ensure_packed(self, need_dgrad=None):
         """Re-pack the weights (tf32 rounding, tap flip, K-major layouts) if the parameters changed since the
@@ -581,10 +624,7 @@ class Plan(object):
             if i == conv_idx[k]:
                 main.wait_event(join)
             f()
-        for f in self.bwd_ops:
-            f()
-            if hook is not None and f.param_end is not None:
-                hook(f.param_end)
+        self._launch_bwd(hook)
 
     def execute(self):
         """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.  With data parallelism
