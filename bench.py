@@ -47,38 +47,62 @@ def load_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region.  ONE long-running ``nvidia-smi -lms`` child
+    (a Python thread forking a query every 200 ms stalled the timed host loop through the GIL); rows are kept by
+    their timestamp, so only samples taken between ``mark_begin`` and ``stop`` count."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        super(ClockSampler, self).__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.p, self.t0 = index, None, None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(',')]
-                if len(f) >= 7:
-                    self.rows.append(f)
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def mark_begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        if not self.rows:
+        import datetime
+        if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        sm = sorted(float(r[0]) for r in self.rows)
+        t1 = datetime.datetime.now()
+        time.sleep(0.12)                 # let the sample that covers the end of the region be printed
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ''
+        rows, inside = [], []
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f')
+                float(f[1]), float(f[2]), float(f[3])
+            except Exception:
+                continue
+            rows.append(f[1:])
+            if self.t0 is not None and self.t0 - datetime.timedelta(milliseconds=60) <= ts <= t1 + datetime.timedelta(milliseconds=60):
+                inside.append(f[1:])
+        use = inside or rows[-5:]
+        if not use:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        sm = sorted(float(r[0]) for r in use)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
-                    power_w_max=max(float(r[2]) for r in self.rows), samples=len(self.rows))
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in use)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(use[0][1]), reasons=reasons,
+                    power_w_max=max(float(r[2]) for r in use), samples=len(use), samples_in_timed_region=len(inside))
 
 
 def synthetic_batch(model, seed):
@@ -158,6 +182,8 @@ def main():
     rank, world, local = parallel.init_from_env()
     torch.cuda.set_device(local)
     dist = torch.distributed
+    sampler = ClockSampler(local)
+    sampler.start()                                     # running well before the timed region starts
     np.random.seed(2)                                   # identical initial weights on every rank
     with contextlib.redirect_stdout(io.StringIO()):
         model = examples.BUILDERS[args.workload]()
@@ -189,8 +215,7 @@ def main():
     for _ in range(W):
         device_step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
@@ -204,11 +229,15 @@ def main():
     for _ in range(2):
         model.trainingstep(x, t, optimiser='Adam')
     barrier()
+    import gc
+    gc.collect()
+    gc.disable()                                        # no collector pauses inside the timed host loop
     t0 = time.perf_counter()
     for _ in range(K):
         loss, _, _ = model.trainingstep(x, t, optimiser='Adam')
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    gc.enable()
     clocks = sampler.stop()
     if world > 1:
         tt = torch.tensor([dev_ms, e2e_ms], device='cuda', dtype=torch.float64)

@@ -598,8 +598,9 @@ class Plan(object):
         """E2_PACK_OVERLAP=1 variant of a training step: the weight re-pack (fp32 master -> tf32 forward / dgrad
         layouts, ~230 MB of traffic for unet3d) is part of the step's launch list; only the first layers' packs sit
         in front of the forward pass, the rest run on a side stream underneath the first (tensor-bound) convolutions
-        and are joined before the third conv layer.  Measured on unet3d: no gain over the sequential order (the
-        packs slow conv0/conv1 by what they save), so the default keeps the re-pack outside the step graph."""
+        and are joined before the third conv layer.  Measured on unet3d (forked at the step start and forked behind
+        the first layer): no gain over the sequential order -- the packs slow the convolution they run under by
+        what they save -- so the default keeps the re-pack outside the step graph."""
         conv_idx = [i for i, f in enumerate(self.fwd_ops) if f.label.startswith(('conv_fwd:', 'upconv_fwd:'))]
         k = self.EARLY_PACKS
         if len(conv_idx) <= k or len(conv_idx) != len(self.pack_ops):
@@ -611,12 +612,6 @@ class Plan(object):
             self._pack_stream = torch.cuda.Stream(device=self.device)
         side = self._pack_stream
         fork, join = torch.cuda.Event(), torch.cuda.Event()
-        fork.record(main)
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
-            for op in self.pack_ops[k:]:
-                op.pack(True)
-            join.record(side)
         for op in self.pack_ops[:k]:
             op.pack(True)
         self._packed_version = self.store.version
@@ -624,6 +619,14 @@ class Plan(object):
             if i == conv_idx[k]:
                 main.wait_event(join)
             f()
+            if i == conv_idx[0]:
+                # behind the first (HBM-bound) layer: the remaining packs run underneath the second, tensor-bound one
+                fork.record(main)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    for op in self.pack_ops[k:]:
+                        op.pack(True)
+                    join.record(side)
         self._launch_bwd(hook)
 
     def execute(self):
