@@ -198,7 +198,7 @@ def main():
     if dp is not None:
         dp.broadcast_parameters(plan.store)
     opt = model.optimisers['Adam']
-    launches_per_step = plan.launches_per_step() + 2    # + the two Adam region launches
+    launches_per_step = plan.launches_per_step() + 4    # + adam_prepare and the three Adam region launches
     n_vox = float(np.prod(x.shape)) * world
 
     def barrier():
@@ -207,8 +207,7 @@ def main():
         torch.cuda.synchronize()
 
     def device_step():
-        plan.execute()
-        opt.step(plan.store)
+        plan.train_step(opt)                            # fwd + bwd (+ all-reduce) + Adam + weight re-pack
 
     # ---- value: inputs resident in HBM ------------------------------------------------
     plan.feed({model.input_node: x, model.target_node: t})

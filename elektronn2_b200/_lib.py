@@ -126,6 +126,8 @@ SIGNATURES = {
     'e2_softmax_nll_bwd': (C.c_int, [vp, P(Tensor), vp, vp, vp, C.c_float, vp, vp]),
     'e2_adam_step': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]),
     'e2_sgd_step': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, i32, vp]),
+    'e2_adam_prepare': (C.c_int, [vp, vp, vp, vp]),
+    'e2_adam_step_dev': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, i32, vp]),
     'e2_debug_zstack_plan': (C.c_int, [C.c_int] * 10 + [P(C.c_int)]),
 }
 

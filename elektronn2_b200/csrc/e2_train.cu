@@ -119,6 +119,50 @@ extern "C" int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, fl
   return E2_OK;
 }
 
+// ---- optimiser step inside a CUDA graph: hyper-parameters and the step counter live in device memory ----
+// hyper = [lr, mom, beta2, wd, factor, -, -, -]; e2_adam_prepare advances the counter and refreshes `factor`.
+__global__ void k_adam_prepare(float* __restrict__ hyper, int* __restrict__ t_dev) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int t = t_dev[0] + 1;
+    t_dev[0] = t;
+    const double beta2 = (double)hyper[2], mom = (double)hyper[1];
+    hyper[4] = (float)(sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(mom, (double)t)));   // optimiser.py:304
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                  float* __restrict__ s, int64_t n, const float* __restrict__ hyper,
+                                                  int apply_wd) {
+  const float lr = hyper[0], mom = hyper[1], beta2 = hyper[2], wd = hyper[3], factor = hyper[4];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float nm = mom * m[i] + (1.0f - mom) * gi;
+    float ns = beta2 * s[i] + (1.0f - beta2) * gi * gi;
+    float dir = factor * nm / sqrtf(ns + 1e-5f);
+    float pi = p[i];
+    pi = apply_wd ? pi - lr * (dir + wd * pi) : pi - lr * dir;
+    m[i] = nm, s[i] = ns, p[i] = pi;
+  }
+}
+
+extern "C" int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void* stream) {
+  E2_REQUIRE(h, hyper && t_dev, "adam_prepare: null pointer");
+  k_adam_prepare<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, t_dev);
+  h->launches++;
+  E2_CUDA_CHECK(h, "adam_prepare");
+  return E2_OK;
+}
+
+extern "C" int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count,
+                                const float* hyper, int32_t apply_wd, void* stream) {
+  E2_REQUIRE(h, p && g && m && s && hyper && count >= 0, "adam_step_dev: bad arguments");
+  if (count == 0) return E2_OK;
+  k_adam_dev<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, hyper, apply_wd);
+  h->launches++;
+  E2_CUDA_CHECK(h, "adam_step_dev");
+  return E2_OK;
+}
+
 __global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ d,
                                              int64_t n, float lr, float mom, float wd, int apply_wd) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

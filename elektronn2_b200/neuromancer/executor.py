@@ -68,11 +68,12 @@ class ParamStore(object):
 class Launch(object):
     """One entry of a plan: a bound C-ABI call plus its algorithmic work (for rooflines:
     SURVEY.md 8d "Algorithmic work")."""
-    __slots__ = ('label', 'fn', 'flops', 'bytes', 'kind', 'param_end')
+    __slots__ = ('label', 'fn', 'flops', 'bytes', 'kind', 'param_end', 'param_start')
 
     def __init__(self, label, fn, flops=0, nbytes=0, kind='hbm'):
         self.label, self.fn, self.flops, self.bytes, self.kind = label, fn, float(flops), float(nbytes), kind
         self.param_end = None  # wgrad launches: end offset (floats) of the gradient region now complete
+        self.param_start = None
 
     def __call__(self):
         self.fn()
@@ -118,6 +119,11 @@ class Plan(object):
         self.inputs = {}
         self._graph = None
         self._pack_stream = None
+        self._stage_in, self._pending, self._fed = {}, {}, False
+        self._opt_stream = None
+        self._opt_graphs = {}
+        self._split = None
+        self.fuse_optimiser = os.environ.get('E2_FUSE_OPT', '1') != '0'
         self._wgrad_stream = None
         self.wgrad_overlap = self.train and os.environ.get('E2_WGRAD_OVERLAP', '1') != '0'
         self.wgrad_streams = max(1, int(os.environ.get('E2_WGRAD_STREAMS', '2')))
@@ -355,6 +361,7 @@ class Plan(object):
                 l = self._b('upconv_wgrad:' + n.name, lambda op=op, dy=dy, n=n: op.wgrad(dy, n.w._grad, n.b._grad),
                             fl, 4 * (_nel(op.x) + _nel(dy)), kind)
                 l.param_end = n.w._offset + int(np.prod(n.w.shape))
+                l.param_start = n.w._offset
                 self._emit_dgrad(op, dy, n.parent, written, 'upconv_dgrad:' + n.name, fl, kind)
             elif isinstance(n, Conv):
                 dy, op = self.grad[n], self.conv_ops[n]
@@ -371,6 +378,7 @@ class Plan(object):
                 l = self._b('conv_wgrad:' + n.name, lambda op=op, dlin=dlin, n=n: op.wgrad(dlin, n.w._grad, n.b._grad),
                             fl, 4 * (_nel(op.x) + _nel(dlin)), kind)
                 l.param_end = n.w._offset + int(np.prod(n.w.shape))
+                l.param_start = n.w._offset
                 self._emit_dgrad(op, dlin, n.parent, written, 'conv_dgrad:' + n.name, fl, kind)
             elif isinstance(n, Pool):
                 par = n.parent
@@ -476,19 +484,19 @@ class Plan(object):
     def feed(self, values):
         """H2D copies of the inputs.  A source array that already lives in page-locked memory is copied from where
         it is; anything else goes through the plan's pinned staging buffer first.  The copies run on a side stream
-        that waits only for the previous step's readers of the input buffers, so they overlap with whatever else
-        is still queued (optimiser, weight re-pack); the compute stream waits for them.
+        into device STAGING buffers (the input tensors themselves are still being read by the previous step's
+        first-layer wgrad when ``Model.trainingstep`` has returned its loss), so they overlap with the backward pass
+        still in flight; ``_commit_inputs`` moves them into place (device-to-device) when the next step is submitted.
         Returns the number of bytes copied."""
         nbytes = 0
-        cur = torch.cuda.current_stream(self.device)
-        side = cur
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("Plan.feed() inside a CUDA-graph capture")
+        cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         side = self._copy_stream
         if self._inputs_free is not None:
-            side.wait_event(self._inputs_free)
+            side.wait_event(self._inputs_free)     # the staging buffers have been consumed by the previous step
         else:
             side.wait_stream(cur)
         with torch.cuda.stream(side):
@@ -506,11 +514,30 @@ class Plan(object):
                 if src is None:
                     pinned.copy_(torch.from_numpy(np.ascontiguousarray(a)))
                     src = pinned
-                dst = staging if staging is not None else t.buf[t.offset:t.offset + pinned.numel()].view(pinned.shape)
+                if staging is not None:
+                    dst = staging                         # multi-channel: the layout kernel reads this buffer
+                else:
+                    dst = self._stage_in.get(n)
+                    if dst is None:
+                        dst = self._stage_in[n] = torch.empty(pinned.shape, dtype=torch.float32, device=self.device)
+                    self._pending[n] = dst
                 dst.copy_(src, non_blocking=True)
                 nbytes += pinned.numel() * 4
-        cur.wait_stream(side)
+        self._fed = True
         return nbytes
+
+    def _commit_inputs(self):
+        """Submit point of a step: the compute stream waits for the H2D copies and moves single-channel inputs from
+        their staging buffers into the input tensors (a few microseconds of device-to-device copy)."""
+        if not self._fed:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self._copy_stream)
+        for n, stage in self._pending.items():
+            t, pinned, _ = self.inputs[n]
+            t.buf[t.offset:t.offset + pinned.numel()].view(pinned.shape).copy_(stage, non_blocking=True)
+        self._pending = {}
+        self._fed = False
 
     _WGRAD = ('conv_wgrad:', 'upconv_wgrad:')
 
@@ -519,23 +546,47 @@ class Plan(object):
             f()
         self._launch_bwd(hook)
 
-    def _launch_bwd(self, hook=None):
+    def _launch_bwd(self, hook=None, early=None):
         """Backward launches.  A weight gradient feeds nothing but the optimiser (and the all-reduce), so the wgrad
-        kernels go to a side stream, each behind an event that marks its place in the sequence, and run underneath
+        kernels go to side streams, each behind an event that marks its place in the sequence, and run underneath
         the dgrad chain: the layers at the bottom of the U-Net have too few tiles to fill 148 SMs on their own.
-        They use the handle's second scratch buffer.  Joined before the step ends."""
+        They use the handle's extra scratch buffers.  Joined before the step ends.
+        ``early`` = (index into bwd_ops, fn): fn() is called on the optimiser stream once everything launched before
+        that index is complete (fused optimiser step for the layers whose gradients are final by then)."""
+        main = torch.cuda.current_stream(self.device)
         if not self.wgrad_overlap:
-            for f in self.bwd_ops:
+            for i, f in enumerate(self.bwd_ops):
+                if early is not None and i == early[0]:
+                    early[1]()
                 f()
                 if hook is not None and f.param_end is not None:
                     hook(f.param_end)
             return
-        main = torch.cuda.current_stream(self.device)
         if self._wgrad_stream is None:
             self._wgrad_stream = [torch.cuda.Stream(device=self.device) for _ in range(self.wgrad_streams)]
-        used = False
+        # fork every side stream here: an all-reduce bucket waits on events recorded on ALL of them, so they must
+        # already be part of the step (and of a CUDA-graph capture) before the first bucket is launched
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        for side in self._wgrad_stream:
+            side.wait_event(ev0)
+        dp = self.model.data_parallel
+        if dp is not None:
+            dp.producer_streams = list(self._wgrad_stream)
+        used = True
         k = 0
-        for f in self.bwd_ops:
+        for i, f in enumerate(self.bwd_ops):
+            if early is not None and i == early[0]:
+                if self._opt_stream is None:
+                    self._opt_stream = torch.cuda.Stream(device=self.device)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._opt_stream.wait_event(ev)
+                if used:
+                    for side in self._wgrad_stream:
+                        self._opt_stream.wait_stream(side)
+                with torch.cuda.stream(self._opt_stream):
+                    early[1]()
             if f.label.startswith(self._WGRAD):
                 slot = k % len(self._wgrad_stream)
                 side = self._wgrad_stream[slot]
@@ -559,6 +610,124 @@ class Plan(object):
         if used:
             for side in self._wgrad_stream:
                 main.wait_stream(side)
+        if early is not None and self._opt_stream is not None:
+            main.wait_stream(self._opt_stream)
+
+    # ------------------------------------------------------------- training step with the optimiser inside
+    TAIL_LAYERS = 4     # layers (from the input side) whose update waits for the end of the backward pass
+
+    def _opt_split(self):
+        """(S, j, packs_early, packs_late): parameters [0, S) of the flat buffer -- every layer except the first
+        TAIL_LAYERS -- have their final gradients once everything before bwd_ops[j] has run.  Those layers hold
+        >95 % of the parameters of a U-Net and their update + re-pack is HBM-bound, so it runs on its own stream
+        underneath the tensor-bound dgrad / wgrad of the large first layers."""
+        if self._split is not None:
+            return self._split
+        wg = [i for i, f in enumerate(self.bwd_ops) if f.label.startswith(self._WGRAD)]
+        S, j = 0, None
+        if len(wg) >= 3:
+            keep = min(self.TAIL_LAYERS, len(wg) - 1)
+            j = wg[-keep]
+            S = min(self.bwd_ops[i].param_start for i in wg[-keep:])
+            ok = all(self.bwd_ops[i].param_end <= S for i in wg[:-keep]) and S <= self.store.n_reg
+            if not ok:
+                S, j = 0, None
+        off = {op: n.w._offset for n, op in self.conv_ops.items()}
+        early = [op for op in self.pack_ops if off.get(op, 1 << 62) < S]
+        late = [op for op in self.pack_ops if op not in early]
+        self._split = (S, j, early, late)
+        return self._split
+
+    def _train_body_fwd(self, opt):
+        opt.dev_prepare()
+        for f in self.fwd_ops:
+            f()
+
+    def _train_body_bwd(self, opt, dp):
+        store = self.store
+        S, j, packs_early, packs_late = self._opt_split()
+        hook = dp.on_gradients_ready if dp is not None else None
+        if dp is not None:
+            dp.begin_step(store, split=S)
+
+        def early_update():
+            if dp is not None:
+                dp.on_gradients_ready(S)           # every bucket below S is launched by now
+                dp.wait_launched()                 # this stream waits for those collectives
+            opt.dev_step(store, 0, S, 1)
+            for op in packs_early:
+                op.pack(True)
+
+        self._launch_bwd(hook, (j, early_update) if j is not None and S > 0 else None)
+        if dp is not None:
+            dp.finish_step(store)
+        opt.dev_step(store, S, store.n_reg - S, 1)
+        opt.dev_step(store, store.n_reg, store.total - store.n_reg, 0)
+        for op in (packs_late if j is not None and S > 0 else self.pack_ops):
+            op.pack(True)
+
+    def train_step(self, opt, loss_async=False):
+        """Forward + backward + optimiser update + weight re-pack as two CUDA graphs -- [forward, loss] and
+        [backward, all-reduce, update, re-pack] -- so that the loss scalars can be copied out in between
+        (``loss_async``: enqueue that copy; the caller collects it with ``loss_op.read_wait()`` while the backward
+        pass is still running).  Adam only; other optimisers and ``keep_history`` fall back to execute() +
+        opt.step().  The caller feeds the inputs first."""
+        dp = self.model.data_parallel
+        if dp is not None and dp.world <= 1:
+            dp = None
+        if not (self.train and self.fuse_optimiser and getattr(opt, 'fusable', False) and not opt.keep_history):
+            self.execute()
+            if loss_async:
+                self.loss_op.read_async()
+            if dp is not None:
+                dp.allreduce_gradients(self.store)
+            opt.step(self.store)
+            self.repack()
+            return
+        self._commit_inputs()
+        opt.dev_sync(self.store)
+        self._ensure_packed_train()            # first step / weights set from outside; afterwards the step re-packs
+        key = id(opt)
+        graphs = None
+        if self.use_graph and (dp is None or dp.graph_ok):
+            graphs = self._opt_graphs.get(key)
+            if graphs is None:
+                # eager warm-up WITHOUT the update (creates streams / communicators, touches every kernel once)
+                if dp is not None:
+                    dp.begin_step(self.store)
+                self._launch_all(dp.on_gradients_ready if dp is not None else None)
+                if dp is not None:
+                    dp.finish_step(self.store)
+                torch.cuda.synchronize(self.device)
+                try:
+                    g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1, capture_error_mode='thread_local'):
+                        self._train_body_fwd(opt)
+                    with torch.cuda.graph(g2, capture_error_mode='thread_local'):
+                        self._train_body_bwd(opt, dp)
+                    # the captures ran no kernel: t_dev / parameters are untouched
+                    graphs = self._opt_graphs[key] = (g1, g2)
+                except Exception as e:      # noqa: BLE001
+                    if dp is None:
+                        raise
+                    import warnings
+                    warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
+                    dp.graph_ok = False
+                    torch.cuda.synchronize(self.device)
+                    graphs = None
+        if graphs is not None:
+            graphs[0].replay()
+        else:
+            self._train_body_fwd(opt)
+        self._mark_inputs_free()               # staging buffers / input layout kernel consumed
+        if loss_async:
+            self.loss_op.read_async()
+        if graphs is not None:
+            graphs[1].replay()
+        else:
+            self._train_body_bwd(opt, dp)
+        opt.dev_after(self.store)
+        self._packed_version = self.store.version
 
     def _ensure_packed(self, need_dgrad=None):
         """Re-pack the weights (tf32 rounding, tap flip, K-major layouts) if the parameters changed since the
@@ -632,6 +801,7 @@ class Plan(object):
     def execute(self):
         """Run the launch list: eagerly the first time (warm-up), then as a CUDA graph.  With data parallelism
         the bucketed all-reduce is interleaved with the backward launches and captured with them."""
+        self._commit_inputs()
         if not self.train:
             self._ensure_packed(False)
             if self.use_graph:

@@ -143,12 +143,10 @@ class Model(object):
         t0 = time.time()
         plan = self._train_plan(np.shape(args[0])[0])
         plan.feed(self._feed_dict(plan, args))
-        plan.execute()
-        if self.data_parallel is not None:
-            self.data_parallel.allreduce_gradients(plan.store)
-        plan.loss_op.read_async()                  # D2H of the loss scalars, behind the backward pass
-        opt.step(plan.store)
-        plan.repack()                              # next step's weights; overlaps with the host side of the next call
+        # [fwd, loss] graph -> loss D2H enqueued -> [bwd (+ all-reduce), update, weight re-pack] graph; the call returns
+        # when the loss has arrived, i.e. while the backward pass is still running: the next call's host work and H2D
+        # copies overlap with it (stream order keeps everything else sequential)
+        plan.train_step(opt, loss_async=True)
         loss = np.float32(plan.loss_op.read_wait()[0])  # the only device->host sync of the step
         if kwargs.get('update_loss', False):
             loss = self.loss(*args)

@@ -112,3 +112,42 @@ class Adam(Optimiser):
                        _slice_ptr(self._state[0], off), _slice_ptr(self._state[1], off), cnt, lr, mom, beta2, wd,
                        awd, self.t, h.stream())
         self._after_step(store)
+
+    # -- in-graph form (executor.Plan.train_step): hyper-parameters and step counter in device memory ----------
+    fusable = True
+
+    def dev_sync(self, store):
+        """Make the device copies of (lr, mom, beta2, wd) and of the step counter match the host values.  Only
+        touches the device when something changed since the last call (a schedule, set_opt_meta_params, ...)."""
+        if self._state is None:
+            self._state = self._alloc(store, 2)
+        if getattr(self, '_hyper_dev', None) is None:
+            self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=store.device)
+            self._t_dev = torch.zeros(1, dtype=torch.int32, device=store.device)
+            self._hyper_host, self._t_host = None, None
+        lr, mom, wd = self._hyper()
+        cur = (lr, mom, float(self.beta2.get_value()), wd)
+        if cur != self._hyper_host:
+            self._hyper_dev[:4].copy_(torch.tensor(cur, dtype=torch.float32))
+            self._hyper_host = cur
+        if self._t_host != self.t:
+            self._t_dev.fill_(int(self.t))
+            self._t_host = self.t
+
+    def dev_prepare(self):
+        """First launch of a fused step: t += 1 on the device, factor(t) refreshed."""
+        h = _lib.get_handle()
+        h.call('e2_adam_prepare', _lib.ptr(self._hyper_dev), _lib.ptr(self._t_dev), h.stream())
+
+    def dev_step(self, store, off, cnt, apply_wd):
+        if cnt <= 0:
+            return
+        h = _lib.get_handle()
+        h.call('e2_adam_step_dev', _slice_ptr(store.P, off), _slice_ptr(store.G, off), _slice_ptr(self._state[0], off),
+               _slice_ptr(self._state[1], off), cnt, _lib.ptr(self._hyper_dev), int(apply_wd), h.stream())
+
+    def dev_after(self, store):
+        """Host bookkeeping after a fused step has been submitted."""
+        self.t += 1
+        self._t_host = self.t
+        self._after_step(store)

@@ -63,6 +63,7 @@ class DataParallel(object):
         self.bucket_floats = int(bucket_mb * 1024 * 1024 / 4)
         self.overlap = overlap
         self.comm_stream = None
+        self.producer_streams = []            # set by the executor: the streams its wgrad kernels run on
         self.graph_ok = os.environ.get('E2_DP_GRAPH', '1') != '0'   # capture the step incl. the collectives
         model.data_parallel = self
         self.bytes_reduced = 0
@@ -87,11 +88,17 @@ class DataParallel(object):
     # -- overlapped, bucketed form (driven by executor.Plan.execute) ------------------
     _step_reduced = False
 
-    def begin_step(self, store):
-        if getattr(self, '_buckets', None) is None:
+    def begin_step(self, store, split=None):
+        """``split``: an offset that must be a bucket boundary (the fused optimiser updates [0, split) as soon as
+        those buckets are reduced)."""
+        if getattr(self, '_buckets', None) is None or getattr(self, '_split', None) != split:
+            self._split = split
             # weight region in buckets, the (tiny) bias tail as the last bucket
             w_entries = [e for e in store.entries if e[2] < store.n_reg]
             self._buckets = [(s, e) for s, e, _ in bucket_ranges(w_entries, store.n_reg, self.bucket_floats)]
+            if split:
+                self._buckets = [r for (s, e) in self._buckets
+                                 for r in ([(s, split), (split, e)] if s < split < e else [(s, e)])]
             if store.total > store.n_reg:
                 self._buckets.append((store.n_reg, store.total))
             if torch.cuda.is_available() and store.G.is_cuda:
@@ -102,9 +109,15 @@ class DataParallel(object):
         view = store.G[s:e]
         if self.comm_stream is not None and self.overlap:
             ev = torch.cuda.Event()
-            ev.record()                       # everything enqueued so far on the compute stream
+            ev.record()                       # everything enqueued so far on the current stream ...
+            evs = [ev]
+            for st in self.producer_streams:  # ... and on every stream that runs wgrad kernels
+                e2 = torch.cuda.Event()
+                e2.record(st)
+                evs.append(e2)
             with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
+                for e2 in evs:
+                    self.comm_stream.wait_event(e2)
                 self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
         else:
             self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
@@ -119,6 +132,11 @@ class DataParallel(object):
             s, e = self._buckets[self._next]
             self._launch_bucket(store, s, e)
             self._next += 1
+
+    def wait_launched(self):
+        """Make the current stream wait for every collective launched so far in this step."""
+        for w in self._works:
+            w.wait()
 
     def finish_step(self, store):
         while self._next < len(self._buckets):

@@ -240,6 +240,13 @@ int e2_softmax_nll_bwd(e2_handle* h, const e2_tensor* logits, const float* probs
  * sqrt(1-beta2^t)/(1-mom^t), L2 term wd*p when apply_wd.  t is the 1-based step. */
 int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, float lr, float mom,
                  float beta2, float wd, int32_t apply_wd, int32_t t, void* stream);
+/* The same update with its hyper-parameters in DEVICE memory, so that the step can live inside a CUDA graph
+ * (graph nodes bake their scalar arguments): hyper = float[8] {lr, mom, beta2, wd, factor, -, -, -}, t_dev = the
+ * number of steps taken so far.  e2_adam_prepare increments *t_dev and refreshes hyper[4] = factor(t); it is the
+ * first node of a training-step graph, e2_adam_step_dev may then run on any stream ordered behind it. */
+int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void* stream);
+int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, const float* hyper,
+                     int32_t apply_wd, void* stream);
 /* SGD with momentum, optimiser.py:146-160 */
 int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom, float wd,
                 int32_t apply_wd, void* stream);
