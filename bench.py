@@ -243,6 +243,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = float(tt[0]), float(tt[1])
     if rank != 0:
+        _finish(dist, world)
         return 0
 
     # ---- roofline of the dominant kernel family (eager, per-launch CUDA events) ---------
@@ -301,9 +302,24 @@ def main():
                 e2e=dict(value=n_vox * K / (e2e_ms * 1e-3), unit='voxels/s', h2d_bytes_per_step=in_bytes,
                          d2h_bytes_per_step=16, ms_per_step=e2e_ms / K, host_buffers='page-locked numpy arrays'),
                 gpu_launches=launches_per_step * K, clocks=clocks, loss=float(loss),
-                cuda_graph=plan._graph is not None)
+                cuda_graph=bool(plan._opt_graphs) or plan._graph is not None)
     print(json.dumps(line))
+    _finish(dist, world)
     return 0
+
+
+def _finish(dist, world):
+    """Leave without running interpreter teardown: destroying NCCL communicators that CUDA graphs still reference
+    can block at exit (seen with a 2-rank check script); everything that matters has been printed."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        try:
+            import torch
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+    os._exit(0)
 
 
 if __name__ == '__main__':

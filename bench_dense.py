@@ -79,7 +79,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         dt, done = float(mx[0]), int(tt[1])
     if rank != 0:
-        return 0
+        sys.stdout.flush()
+        os._exit(0)          # no interpreter teardown with live NCCL communicators (see bench.py:_finish)
     vox_per_tile = float(np.prod(prob_sh))
     n_vox = min(done * vox_per_tile, float(np.prod(pred_sh)) if done == len(tiles) else done * vox_per_tile)
     flops_per_vox = 0.0
@@ -97,6 +98,9 @@ def main():
                 e2e=dict(value=n_vox / dt, unit='voxels/s', h2d_bytes=st['h2d_bytes'], d2h_bytes=st['d2h_bytes']),
                 tflops_asymptotic=n_vox * flops_per_vox / dt / 1e12)
     print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        os._exit(0)
     return 0
 
 
