@@ -121,6 +121,7 @@ class Plan(object):
         self._pack_stream = None
         self._stage_in, self._pending, self._fed = {}, {}, False
         self._opt_stream = None
+        self._capture_stream = None
         self._opt_graphs = {}
         self._split = None
         self.fuse_optimiser = os.environ.get('E2_FUSE_OPT', '1') != '0'
@@ -614,7 +615,8 @@ class Plan(object):
             main.wait_stream(self._opt_stream)
 
     # ------------------------------------------------------------- training step with the optimiser inside
-    TAIL_LAYERS = 4     # layers (from the input side) whose update waits for the end of the backward pass
+    # layers (from the input side) whose update waits for the end of the backward pass
+    TAIL_LAYERS = int(os.environ.get('E2_TAIL_LAYERS', '4'))
 
     def _opt_split(self):
         """(S, j, packs_early, packs_late): parameters [0, S) of the flat buffer -- every layer except the first
@@ -701,9 +703,15 @@ class Plan(object):
                 torch.cuda.synchronize(self.device)
                 try:
                     g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1, capture_error_mode='thread_local'):
+                    # captured on a high-priority stream: kernel nodes inherit it, so whenever a dgrad (critical
+                    # path) and a wgrad / optimiser kernel (side streams, default priority) are both ready, the
+                    # dgrad's CTAs are scheduled first
+                    if self._capture_stream is None:
+                        self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1) \
+                            if os.environ.get('E2_MAIN_PRIO', '1') != '0' else torch.cuda.Stream(device=self.device)
+                    with torch.cuda.graph(g1, stream=self._capture_stream, capture_error_mode='thread_local'):
                         self._train_body_fwd(opt)
-                    with torch.cuda.graph(g2, capture_error_mode='thread_local'):
+                    with torch.cuda.graph(g2, stream=self._capture_stream, capture_error_mode='thread_local'):
                         self._train_body_bwd(opt, dp)
                     # the captures ran no kernel: t_dev / parameters are untouched
                     graphs = self._opt_graphs[key] = (g1, g2)

@@ -1,4 +1,5 @@
 set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r63_dp2.log 2>&1; echo rc=$?; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r63_dp2.log | tr '\n' ' '; grep -o '"loss": [0-9.]*' gpurun_out/r63_dp2.log; grep -o '"cuda_graph": [a-z]*' gpurun_out/r63_dp2.log; grep -i "warn.*capture\|error" gpurun_out/r63_dp2.log | head -3
-E2_DP_GRAPH=0 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r63_dp2_eager.log 2>&1; echo rc=$?; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r63_dp2_eager.log | tr '\n' ' '; grep -o '"loss": [0-9.]*' gpurun_out/r63_dp2_eager.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/dp_check.py > gpurun_out/r63_dpcheck.log 2>&1; echo rc=$?; tail -5 gpurun_out/r63_dpcheck.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_a.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_a.log | tr '\n' ' '; echo prio
+E2_MAIN_PRIO=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_b.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_b.log | tr '\n' ' '; echo noprio
+E2_TAIL_LAYERS=3 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_c.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_c.log | tr '\n' ' '; echo tail3
+E2_TAIL_LAYERS=6 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_d.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_d.log | tr '\n' ' '; echo tail6
