@@ -1,5 +1,3 @@
 set -x
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_a.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_a.log | tr '\n' ' '; echo prio
-E2_MAIN_PRIO=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_b.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_b.log | tr '\n' ' '; echo noprio
-E2_TAIL_LAYERS=3 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_c.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_c.log | tr '\n' ' '; echo tail3
-E2_TAIL_LAYERS=6 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r64_d.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/r64_d.log | tr '\n' ' '; echo tail6
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r65_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r65_ncu.log 2>&1; echo rc=$?; tail -c 200 gpurun_out/r65_ncu.log
+python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/r65_prof_unet3d.json > gpurun_out/r65_bench.log 2>&1; tail -1 gpurun_out/r65_bench.log | cut -c1-1800
