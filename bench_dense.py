@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--uint8-out', action='store_true')
     ap.add_argument('--max-tiles', type=int, default=0, help='bound the run: only the first N tiles of each rank')
     ap.add_argument('--compute', default=None, choices=['tf32', 'f32'])
+    ap.add_argument('--profile-out', default=None, help='per-launch CUDA-event table of one tile (JSON)')
     args = ap.parse_args()
 
     import torch
@@ -81,6 +82,13 @@ def main():
     if rank != 0:
         sys.stdout.flush()
         os._exit(0)          # no interpreter teardown with live NCCL communicators (see bench.py:_finish)
+    if args.profile_out:
+        plan = next(iter(node._plans.values()))
+        prof = plan.profile(repeats=3)
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        json.dump(dict(tile_ms=sum(p[4] for p in prof),
+                       launches=[dict(label=p[0], kind=p[1], flops=p[2], bytes=p[3], ms=p[4]) for p in prof]),
+                  open(args.profile_out, 'w'), indent=1)
     vox_per_tile = float(np.prod(prob_sh))
     n_vox = min(done * vox_per_tile, float(np.prod(pred_sh)) if done == len(tiles) else done * vox_per_tile)
     flops_per_vox = 0.0

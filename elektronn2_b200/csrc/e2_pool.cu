@@ -50,6 +50,11 @@ static inline bool vec4_ok(std::initializer_list<const void*> ptrs, std::initial
   return true;
 }
 
+// float4 paths also serve channel counts that are not a multiple of 4 when the lanes up to the next multiple are real
+// padding of the tensor (pitch - C < 4, never the neighbour slice of a concat buffer): pad lanes are read (finite:
+// buffers start zeroed and pads only ever receive zeros) and written as zeros.
+static inline bool pad4_ok(int C, int pitch) { return (pitch & 3) == 0 && pitch - C < 4; }
+
 struct PoolP {
   int n, Z, X, Y, C, xp;  // input dims, input pitch
   int Zo, Xo, Yo, yp;     // output dims, output pitch
@@ -66,7 +71,7 @@ template <int V, int PZ, int PX, int PY>
 __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, E2FastDiv dcv, const float* __restrict__ x,
                                                      const float* __restrict__ bias, float* __restrict__ y,
                                                      int* __restrict__ amax) {
-  const int cv = p.C / V;
+  const int cv = (p.C + V - 1) / V;
   int r = blockIdx.x;
   const int xo = r % p.Xo;
   r /= p.Xo;
@@ -129,9 +134,13 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(PoolP p, E2FastDiv dcv, con
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float r2 = best[j];
-      if (p.has_bias) r2 += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
-      r2 = e2_apply_act(r2, p.act);
-      o.v[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
+      if (c + j < p.C) {
+        if (p.has_bias) r2 += __ldg(bias + c + j);  // reference order: pool -> +bias -> act (neural.py:678,711-712)
+        r2 = e2_apply_act(r2, p.act);
+        o.v[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
+      } else {
+        o.v[j] = 0.f;                               // pad lane
+      }
       oi.v[j] = bi[j];
     }
     const int64_t oofs = (orow + yo) * p.yp + c;
@@ -216,7 +225,7 @@ template <int V>
 __global__ void __launch_bounds__(256) k_maxpool_bwd_gather(PoolP p, E2FastDiv dcv, const float* __restrict__ dy,
                                                             const int* __restrict__ amax, float* __restrict__ dx,
                                                             const float* __restrict__ gate) {
-  const int cv = p.C / V;
+  const int cv = (p.C + V - 1) / V;
   int r = blockIdx.x;
   const int xx = r % p.X;
   r /= p.X;
@@ -294,9 +303,9 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
   E2_REQUIRE(h, x && y && (!d->has_bias || bias), "maxpool3d_fwd: null pointer");
   const int64_t rows = (int64_t)p.n * p.Zo * p.Xo;
   E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_fwd: too many rows");
-  if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp})) {
-    const int rowlen = p.Yo * (p.C / 4);
-    const E2FastDiv dv = e2_fastdiv(p.C / 4, rowlen);
+  if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
+    const int rowlen = p.Yo * ((p.C + 3) / 4);
+    const E2FastDiv dv = e2_fastdiv((p.C + 3) / 4, rowlen);
     cudaStream_t s = (cudaStream_t)stream;
     if (p.pz == 2 && p.px == 2 && p.py == 2)
       k_maxpool_fwd<4, 2, 2, 2><<<(int)rows, pool_block(rowlen), 0, s>>>(p, dv, x, bias, y, argmax);
@@ -329,9 +338,9 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
   if (p.tie == E2_TIE_FIRST) {
     const int64_t rows = (int64_t)p.n * p.Z * p.X;
     E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_bwd: too many rows");
-    if (vec4_ok({dy, dx, argmax, relu_gate}, {p.C, p.xp, p.yp})) {
-      const int rowlen = p.Yo * (p.C / 4);
-      k_maxpool_bwd_gather<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C / 4, rowlen), dy, argmax, dx, relu_gate);
+    if (vec4_ok({dy, dx, argmax, relu_gate}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
+      const int rowlen = p.Yo * ((p.C + 3) / 4);
+      k_maxpool_bwd_gather<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv((p.C + 3) / 4, rowlen), dy, argmax, dx, relu_gate);
     } else {
       const int rowlen = p.Yo * p.C;
       k_maxpool_bwd_gather<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), dy, argmax, dx, relu_gate);
@@ -353,50 +362,60 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
 // concat copy, computations.py:665-674).  Fragment index = off_idx * n_in + n_old with
 // off_idx = (iz*px + ix)*py + iy  (itertools.product order, last axis fastest).
 template <int V>
-__global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, const float* __restrict__ x, const float* __restrict__ bias,
-                                                 float* __restrict__ y, int* __restrict__ amax) {
-  const int cv = p.C / V;
-  const int nfr = p.n * p.pz * p.px * p.py;
-  const int64_t total = (int64_t)nfr * p.Zo * p.Xo * p.Yo * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V;
-    int64_t pos = i / cv;
-    int yo = (int)(pos % p.Yo);
-    int64_t t = pos / p.Yo;
-    int xo = (int)(t % p.Xo);
-    t /= p.Xo;
-    int zo = (int)(t % p.Zo);
-    int fr = (int)(t / p.Zo);
-    int n = fr % p.n, off = fr / p.n;
-    int iy = off % p.py, ix = (off / p.py) % p.px, iz = off / (p.py * p.px);
+__global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, E2FastDiv dcv, const float* __restrict__ x,
+                                                 const float* __restrict__ bias, float* __restrict__ y,
+                                                 int* __restrict__ amax) {
+  // one block per output row (fragment, zo, xo), see k_maxpool_fwd
+  const int cv = (p.C + V - 1) / V;
+  int r = blockIdx.x;
+  const int xo = r % p.Xo;
+  r /= p.Xo;
+  const int zo = r % p.Zo;
+  const int fr = r / p.Zo;
+  const int n = fr % p.n, off = fr / p.n;
+  const int iy = off % p.py, ix = (off / p.py) % p.px, iz = off / (p.py * p.px);
+  const int rowlen = p.Yo * cv;
+  const float* xn = x + (int64_t)n * p.Z * p.X * p.Y * p.xp;
+  const int64_t orow = (((int64_t)fr * p.Zo + zo) * p.Xo + xo) * p.Yo;
+  for (int t = threadIdx.x; t < rowlen; t += blockDim.x) {
+    const int yo = (int)dcv.div((uint32_t)t);
+    const int c = (t - yo * cv) * V;
     float best[V];
     int bi[V];
     bool first = true;
 #pragma unroll
     for (int j = 0; j < V; ++j) best[j] = -INFINITY, bi[j] = 0;
     for (int dz = 0; dz < p.pz; ++dz)
-      for (int dx = 0; dx < p.px; ++dx)
+      for (int dx = 0; dx < p.px; ++dx) {
+        const int lin0 = ((iz + zo * p.pz + dz) * p.X + ix + xo * p.px + dx) * p.Y + iy + yo * p.py;
+        const float* src = xn + (int64_t)lin0 * p.xp + c;
+#pragma unroll 2
         for (int dy = 0; dy < p.py; ++dy) {
-          int lin = ((iz + zo * p.pz + dz) * p.X + ix + xo * p.px + dx) * p.Y + iy + yo * p.py + dy;
           Vec<V> v;
-          v.load(x + ((int64_t)n * p.Z * p.X * p.Y + lin) * p.xp + c);
+          v.load(src + (int64_t)dy * p.xp);
 #pragma unroll
           for (int j = 0; j < V; ++j)
-            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin;
+            if (first || v.v[j] > best[j]) best[j] = v.v[j], bi[j] = lin0 + dy;
           first = false;
         }
+      }
     Vec<V> o;
     IVec<V> oi;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float r = best[j];
-      if (p.has_bias) r += __ldg(bias + c + j);
-      r = e2_apply_act(r, p.act);
-      o.v[j] = p.round_tf32 ? e2_round_tf32(r) : r;
+      float r2 = best[j];
+      if (c + j < p.C) {
+        if (p.has_bias) r2 += __ldg(bias + c + j);
+        r2 = e2_apply_act(r2, p.act);
+        o.v[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
+      } else {
+        o.v[j] = 0.f;
+      }
       oi.v[j] = bi[j];
     }
-    o.store(y + pos * p.yp + c);
-    if (amax) oi.store(amax + pos * p.yp + c);
+    const int64_t oofs = (orow + yo) * p.yp + c;
+    o.store(y + oofs);
+    if (amax) oi.store(amax + oofs);
   }
 }
 
@@ -478,11 +497,15 @@ extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, co
   int rc = fill_mfp(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, x && y && (!d->has_bias || bias), "mfp_fwd: null pointer");
-  int64_t work = e2_positions(&d->y) * d->y.c;
-  if (vec4_ok({x, y, argmax}, {p.C, p.xp, p.yp}))
-    k_mfp_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
-  else
-    k_mfp_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, x, bias, y, argmax);
+  const int64_t rows = (int64_t)p.n * p.pz * p.px * p.py * p.Zo * p.Xo;
+  E2_REQUIRE(h, rows < (1ll << 31), "mfp_fwd: too many rows");
+  if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
+    const int rowlen = p.Yo * ((p.C + 3) / 4);
+    k_mfp_fwd<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv((p.C + 3) / 4, rowlen), x, bias, y, argmax);
+  } else {
+    const int rowlen = p.Yo * p.C;
+    k_mfp_fwd<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
+  }
   h->launches++;
   E2_CUDA_CHECK(h, "mfp_fwd");
   return E2_OK;

@@ -1,3 +1,3 @@
 set -x
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r65_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r65_ncu.log 2>&1; echo rc=$?; tail -c 200 gpurun_out/r65_ncu.log
-python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/r65_prof_unet3d.json > gpurun_out/r65_bench.log 2>&1; tail -1 gpurun_out/r65_bench.log | cut -c1-1800
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r68_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r68_pytest.log
+timeout 300 python bench_dense.py --max-tiles 2 --profile-out gpurun_out/r68_dense_prof.json > gpurun_out/r68_dense.log 2>&1; echo rc=$?; grep -o '"value": [0-9.]*' gpurun_out/r68_dense.log | head -1
