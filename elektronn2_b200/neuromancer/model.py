@@ -185,15 +185,27 @@ class Model(object):
     def test_run_prediction(self):
         return self.prediction_node.test_run()
 
-    # -- persistence (weights only; the .mdl descriptor format is SURVEY 8f-3) ---------
+    # -- persistence: the reference's .mdl format (model.py:229-235; graphmanager.py) -----
     def save(self, file_name):
-        with open(file_name, 'wb') as f:
-            pickle.dump(dict(name=self.name, params=self.get_param_values()), f, protocol=2)
+        """Pickle ``(descriptors, desig_descr)`` exactly as the reference's ``Model.save`` does, so the file loads
+        in a Theano install of ELEKTRONN2 and, through ``modelload``, here."""
+        from . import graphmanager
+        graphmanager.save_model(self, file_name)
 
-    def load_params(self, file_name):
-        with open(file_name, 'rb') as f:
-            d = pickle.load(f)
-        self.set_param_values(d['params'])
+    def serialise(self):
+        from . import graphmanager
+        return graphmanager.serialise(self)
+
+
+def modelload(file_name, override_mfp_to_active=False, imposed_patch_size=None, imposed_batch_size=None, name=None,
+              **model_load_kwargs):
+    """Load a Model from a ``.mdl`` file written by ``Model.save`` -- the reference's or this package's
+    (model.py:623-729).  ``model_load_kwargs`` (remove_bn, make_weights_constant, ...) concern features outside the
+    B200 hot path and raise if set."""
+    if any(model_load_kwargs.values()):
+        raise NotImplementedError("modelload options %s are not on the B200 hot path" % sorted(model_load_kwargs))
+    from . import graphmanager
+    return graphmanager.load_model(file_name, override_mfp_to_active, imposed_patch_size, imposed_batch_size, name)
 
 
 def kernel_lists_from_node_descr(model):

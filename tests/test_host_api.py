@@ -223,3 +223,48 @@ def test_zstack_planner_invariants():
     assert fn(148, 768, 256, 12, 16, 16, 3, 3, 3, 1, out) == 1 and out[2] > 1
     assert fn(148, 32, 64, 112, 128, 128, 3, 3, 3, 1, out) == 1 and out[2] == 1      # 3584 tiles: never split
     assert fn(148, 256, 512, 7, 9, 9, 3, 3, 3, 1, out) == 0                          # 9x9 planes: tap kernel
+
+
+def test_mdl_round_trip_uses_reference_module_paths(tmp_path):
+    """``Model.save`` writes the reference's .mdl pickle (model.py:229-235, graphmanager.py:236-247): every global in
+    the stream carries the REFERENCE's module path (so a Theano install can load it), and ``modelload`` brings back
+    the same graph and weights; with ``override_mfp_to_active`` the strided net comes back as an MFP net."""
+    import contextlib
+    import io
+    import pickletools
+    from elektronn2_b200 import examples, neuromancer as nm
+    np.random.seed(2)
+    nm.model_manager.reset()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = examples.unet3d_litelite()
+    fn = str(tmp_path / 'unet.mdl')
+    m.save(fn)
+    globs = sorted(set(arg for op, arg, _ in pickletools.genops(open(fn, 'rb').read()) if op.name == 'GLOBAL'))
+    assert 'elektronn2.neuromancer.graphmanager NodeDescriptor' in globs
+    assert 'elektronn2.neuromancer.neural Conv' in globs and 'numpy.core.multiarray _reconstruct' in globs
+    assert not [g for g in globs if 'elektronn2_b200' in g or 'numpy._core' in g]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m2 = nm.modelload(fn)
+    assert list(m2.nodes) == list(m.nodes)
+    assert [tuple(n.shape.shape) for n in m2.nodes.values()] == [tuple(n.shape.shape) for n in m.nodes.values()]
+    for a, b in zip(m.trainable_params, m2.trainable_params):
+        assert a.get_value().dtype == np.float32 and np.array_equal(a.get_value(), b.get_value())
+    assert m2.input_node.name == m.input_node.name and m2.loss_node.name == m.loss_node.name
+    # descriptor content follows graphmanager.py:49-117: parents as NodePointers, no ndarray kwargs
+    d = m.serialise()['conv1'][0]
+    assert isinstance(d.args[0], nm.graphmanager.NodePointer) and d.args[0].target_id == 'conv'
+    assert not any(isinstance(v, np.ndarray) for v in d.kwargs.values())
+    # a strided net re-loaded for dense prediction (model.py:655-689)
+    nm.model_manager.reset()
+    with contextlib.redirect_stdout(io.StringIO()):
+        s = examples.neuro3d_lite()
+    fn2 = str(tmp_path / 'n3d.mdl')
+    s.save(fn2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        s2 = nm.modelload(fn2, override_mfp_to_active=True, imposed_patch_size=(12, 156, 156))
+    assert all(int(v) == 1 for v in s2.prediction_node.shape.strides)
+    assert any(type(n).__name__ == 'FragmentsToDense' for n in s2.nodes.values())
+    for a, b in zip(s.trainable_params, s2.trainable_params):
+        assert np.array_equal(a.get_value(), b.get_value())
+    with pytest.raises(NotImplementedError):
+        nm.modelload(fn2, make_weights_constant=True)
