@@ -407,3 +407,127 @@ def test_full_size_properties_unet3d_conv1(h):
         o, z, xx, yy = r.randint(64), r.randint(112), r.randint(128), r.randint(128)
         ref = float((x1[0, :, z:z + 3, xx:xx + 3, yy:yy + 3].astype(np.float64) * wf[o]).sum())
         assert abs(ys[0][0, o, z, xx, yy] - ref) <= tol * np.abs(ys[0]).max()
+
+
+# ------------------------------------------------------------ out-of-bounds canaries
+CANARY = 12345.678
+GUARD = 4096          # floats on either side (multiple of 4: the tensor keeps its 16-byte alignment)
+
+
+def guarded(n, c, sp, dtype=torch.float32):
+    """A DevTensor placed between two canary zones of one larger buffer."""
+    from elektronn2_b200.devtensor import DevTensor, pitch_for
+    floats = n * sp[0] * sp[1] * sp[2] * pitch_for(c)
+    fill = CANARY if dtype == torch.float32 else 123456789
+    buf = torch.full((floats + 2 * GUARD,), fill, dtype=dtype, device='cuda')
+    buf[GUARD:GUARD + floats] = 0
+    return DevTensor(n, sp[0], sp[1], sp[2], c, buf=buf, offset=GUARD)
+
+
+def guards_intact(tn):
+    b, f = tn.buf, tn.desc.floats
+    fill = CANARY if b.dtype == torch.float32 else 123456789
+    ref = torch.full((GUARD,), fill, dtype=b.dtype, device=b.device)
+    return bool(torch.equal(b[:GUARD], ref)) and bool(torch.equal(b[GUARD + f:], ref))
+
+
+def guarded_flat(shape):
+    numel = int(np.prod(shape))
+    pad = (numel + 3) // 4 * 4
+    buf = torch.full((pad + 2 * GUARD,), CANARY, dtype=torch.float32, device='cuda')
+    view = buf[GUARD:GUARD + numel].view(*shape)
+    view.zero_()
+    return buf, view, numel
+
+
+@pytest.mark.parametrize('case', [
+    (1, 1, (6, 40, 40), 32, (3, 3, 3)),      # first-layer tensor-core kernel, ragged tiles
+    (2, 1, (5, 40, 45), 20, (1, 6, 6)),      # ... two K blocks, 20 channels
+    (1, 256, (5, 16, 16), 128, (3, 3, 3)),   # z-stack kernel with a K split (workspace partial tiles)
+    (1, 200, (4, 15, 14), 72, (3, 3, 3)),    # ragged channels and edges
+    (2, 20, (5, 12, 11), 40, (3, 3, 3)),     # tap kernel, scalar epilogue path
+    (1, 200, (2, 6, 6), 2, (1, 1, 1)),       # few-output-channel kernels
+    (1, 128, (4, 6, 6), 256, (3, 3, 3)),     # tap kernel with split-K
+])
+def test_conv_kernels_stay_inside_their_buffers(h, case):
+    """compute-sanitizer is not available on the GPU pool: every output tensor sits between canary zones and the
+    zones must be untouched after fwd / dgrad / wgrad (TMA stores clip at the tensor-map extents, the hand-written
+    epilogues bound-check rows and channel tails)."""
+    from elektronn2_b200.ops import ConvOp
+    n, ci, sp, co, k = case
+    r = np.random.RandomState(7)
+    x = r.rand(n, ci, *sp).astype(np.float32)
+    w = (r.randn(co, ci, *k) * 0.1).astype(np.float32)
+    b = (r.randn(co) * 0.1).astype(np.float32)
+    osp = [s - f + 1 for s, f in zip(sp, k)]
+    xd, yd = dev(x), guarded(n, co, osp)
+    op = ConvOp(h, xd, yd, t(w), t(b), k, 'relu', 'tf32')
+    op.pack()
+    op.fwd()
+    torch.cuda.synchronize()
+    assert guards_intact(yd)
+    assert rel(yd.numpy(), oo.activation(oo.conv3d(x, w) + b.reshape(1, -1, 1, 1, 1), 'relu')) <= TOL['tf32']
+    dyd = dev(r.randn(n, co, *osp).astype(np.float32))
+    if ci > 1:
+        dxd = guarded(n, ci, sp)
+        op.dgrad(dyd, dxd)
+        op.dgrad(dyd, dxd, accumulate=True)
+        torch.cuda.synchronize()
+        assert guards_intact(dxd)
+    wbuf, dw, _ = guarded_flat(w.shape)
+    bbuf, db, _ = guarded_flat(b.shape)
+    op.wgrad(dyd, dw, db)
+    torch.cuda.synchronize()
+    for buf, numel in ((wbuf, w.size), (bbuf, b.size)):
+        ref = torch.full((GUARD,), CANARY, device='cuda')
+        assert torch.equal(buf[:GUARD], ref) and torch.equal(buf[GUARD + (numel + 3) // 4 * 4:], ref)
+
+
+@pytest.mark.parametrize('case', [(1, 42, (3, 4, 4), 45, (1, 4, 4)), (1, 64, (3, 4, 5), 64, (2, 2, 2)),
+                                  (1, 128, (6, 10, 10), 96, (2, 2, 2))])
+def test_upconv_kernels_stay_inside_their_buffers(h, case):
+    from elektronn2_b200.ops import UpConvOp
+    n, ci, sp, co, p = case
+    r = np.random.RandomState(8)
+    x = r.rand(n, ci, *sp).astype(np.float32)
+    w = (r.randn(co, ci, *p) * 0.2).astype(np.float32)
+    b = (r.randn(co) * 0.1).astype(np.float32)
+    osp = [s * q for s, q in zip(sp, p)]
+    xd, yd = dev(x), guarded(n, co, osp)
+    op = UpConvOp(h, xd, yd, t(w), t(b), p, 'relu', 'tf32')
+    op.pack()
+    op.fwd()
+    dyd = dev(r.randn(n, co, *osp).astype(np.float32))
+    dxd = guarded(n, ci, sp)
+    op.dgrad(dyd, dxd)
+    wbuf, dw, _ = guarded_flat(w.shape)
+    op.wgrad(dyd, dw, None)
+    torch.cuda.synchronize()
+    assert guards_intact(yd) and guards_intact(dxd)
+    ref = torch.full((GUARD,), CANARY, device='cuda')
+    assert torch.equal(wbuf[:GUARD], ref) and torch.equal(wbuf[GUARD + (w.size + 3) // 4 * 4:], ref)
+
+
+@pytest.mark.parametrize('c', [3, 30, 64])
+def test_pool_and_mfp_kernels_stay_inside_their_buffers(h, c):
+    """Channel counts that are not a multiple of 4 take the float4 paths through the tensors' pad lanes."""
+    from elektronn2_b200.ops import PoolOp, MfpOp
+    r = np.random.RandomState(9)
+    x = r.rand(1, c, 6, 10, 12).astype(np.float32)
+    xd, yd = dev(x), guarded(1, c, (3, 5, 6))
+    op = PoolOp(h, xd, yd, (2, 2, 2))
+    op.argmax = guarded(1, c, (3, 5, 6), dtype=torch.int32)
+    op.fwd()
+    dxd = guarded(1, c, (6, 10, 12))
+    op.bwd(dev(r.randn(1, c, 3, 5, 6).astype(np.float32)), dxd)
+    torch.cuda.synchronize()
+    assert guards_intact(yd) and guards_intact(op.argmax) and guards_intact(dxd)
+    assert np.array_equal(yd.numpy(), oo.pooling(x, (2, 2, 2)))
+    xm = r.rand(1, c, 7, 9, 11).astype(np.float32)
+    ym = guarded(8, c, (3, 4, 5))
+    mop = MfpOp(h, dev(xm), ym, (2, 2, 2))
+    mop.argmax = guarded(8, c, (3, 4, 5), dtype=torch.int32)
+    mop.fwd()
+    torch.cuda.synchronize()
+    assert guards_intact(ym) and guards_intact(mop.argmax)
+    assert np.array_equal(ym.numpy(), oo.fragmentpool(xm, (2, 2, 2), np.zeros((1, 3), int), [1, 1, 1])[0])
