@@ -589,7 +589,10 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
   // tile-quantisation efficiency: useful outputs / computed outputs
   const double eff = (double)g.Oz * g.Ox * g.Oy * g.N /
                      ((double)p->ntz * p->TZ * p->ntx * TX * p->nty * TY * p->ntn * bn);
-  if (eff < 0.5) return false;
+  // Big layers with badly fitting planes are left to the tap kernel (its tiles are free-form position boxes).  Small
+  // ones stay here even at low efficiency: their time is launch / pipeline latency either way, and the alternative
+  // halo-plane kernel needed 75-115 us for the decoder layers of unet3d_litelite (here: ~19 us).
+  if (eff < 0.5 && !(eff >= 0.25 && best_cost < 120000.0)) return false;
   return true;
 }
 
