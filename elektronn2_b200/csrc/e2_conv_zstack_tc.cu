@@ -530,7 +530,9 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
     const int w_bytes = S * b * 128;
     const int epi_bytes = EPI_WARPS * 4096 + EPI_WARPS * b * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
     const int budget = 227 * 1024 - 1024 - 1024 - epi_bytes;   // alignment slack + barriers + epilogue
+    static const int force_tz = getenv("E2_ZS_TZ") ? atoi(getenv("E2_ZS_TZ")) : 0;   // experiments only
     for (int tz = 8; tz >= 1; --tz) {
+      if (force_tz && tz != force_tz) continue;
       if (std::min(tz, S) * b > 256) continue;   // widest stacked MMA
       if (2 * tz * b > 512) continue;            // double-buffered accumulators in TMEM
       const int np = tz + S - 1;
