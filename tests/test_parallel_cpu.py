@@ -77,6 +77,22 @@ def _worker(rank, world, port, q):
     # the simple whole-buffer form must not reduce a second time in the same step
     dp.allreduce_gradients(store)
     ok = ok and bool(torch.equal(store.G, expect))
+    # second step, the way the fused optimiser step drives it (executor.Plan._train_body_bwd): a split offset S
+    # that is NOT a natural bucket end becomes one; once the wgrads below S have been launched, on_gradients_ready(S)
+    # + wait_launched() must leave [0, S) fully reduced while the rest is still local
+    store.G = torch.arange(store.total, dtype=torch.float32) * (rank + 1)
+    S = store.entries[3][2]                    # offset of the 4th weight: inside the second ~1000-float bucket
+    dp.begin_step(store, split=S)
+    ok = ok and any(e == S for _, e in dp._buckets) and all(a[1] == b[0] for a, b in zip(dp._buckets, dp._buckets[1:]))
+    ok = ok and not any(s < S < e for s, e in dp._buckets)
+    for _, _, off, size in store.entries[:3]:
+        dp.on_gradients_ready(off + size)
+    dp.on_gradients_ready(S)
+    dp.wait_launched()
+    ok = ok and bool(torch.equal(store.G[:S], expect[:S]))
+    ok = ok and bool(torch.equal(store.G[S:store.n_reg], (torch.arange(store.total, dtype=torch.float32) * (rank + 1))[S:store.n_reg]))
+    dp.finish_step(store)
+    ok = ok and bool(torch.equal(store.G, expect))
     q.put((rank, ok))
     dist.destroy_process_group()
 
