@@ -72,7 +72,6 @@ class _TileRunner(object):
         self.in_shape = (d.n, d.c, d.z, d.x, d.y)
         self.int_input = int_input
         if int_input:
-            self.pinned_u8 = torch.empty(self.in_shape, dtype=torch.uint8).pin_memory()
             self.dev_u8 = torch.empty(self.in_shape, dtype=torch.uint8, device=self.plan.device)
         out = self.plan.val[node]
         od = out.desc
@@ -81,37 +80,66 @@ class _TileRunner(object):
         self.as_uint8 = as_uint8
         if as_uint8:
             self.out_u8 = torch.empty_like(self.out_ncdhw, dtype=torch.uint8)
-            self.host_out = torch.empty(self.out_ncdhw.shape, dtype=torch.uint8).pin_memory()
-        else:
-            self.host_out = torch.empty(self.out_ncdhw.shape, dtype=torch.float32).pin_memory()
         self.h2d_bytes = self.d2h_bytes = 0
 
     def forward(self, patch):
         """patch: (ch,z,x,y) host array (uint8 if int_input else float32 already scaled).
         Returns the (n_lab, zo, xo, yo) host array (float32, or uint8 = trunc(p*255))."""
+        self.submit(patch)
+        return self.collect()
+
+    # Two-deep software pipeline for the one-call-per-tile case: ``submit`` enqueues H2D -> network -> conversion ->
+    # D2H for a tile and returns; ``collect`` waits for the OLDEST submitted tile.  With two slots of pinned input /
+    # output staging the host prepares tile i+1 and assembles tile i-1 while the GPU computes tile i.
+    SLOTS = 2
+
+    def _slots(self):
+        if getattr(self, '_slot_bufs', None) is None:
+            self._slot_bufs = []
+            for _ in range(self.SLOTS):
+                pin_in = (torch.empty(self.in_shape, dtype=torch.uint8) if self.int_input
+                          else torch.empty(self.in_shape, dtype=torch.float32)).pin_memory()
+                host_out = torch.empty(self.out_ncdhw.shape, dtype=torch.uint8 if self.as_uint8 else torch.float32).pin_memory()
+                self._slot_bufs.append(dict(pin_in=pin_in, host_out=host_out, done=torch.cuda.Event(), busy=False))
+            self._queue, self._next_slot = [], 0
+        return self._slot_bufs
+
+    def submit(self, patch):
         h, s = self.h, self.h.stream()
+        slots = self._slots()
+        slot = slots[self._next_slot]
+        if slot['busy']:
+            raise RuntimeError("predict_dense pipeline: collect() the oldest tile before submitting a third one")
+        self._next_slot = (self._next_slot + 1) % self.SLOTS
         if self.int_input:
-            self.pinned_u8[0].copy_(torch.from_numpy(np.ascontiguousarray(patch)))
-            self.dev_u8.copy_(self.pinned_u8, non_blocking=True)
+            slot['pin_in'][0].copy_(torch.from_numpy(np.ascontiguousarray(patch)))
+            self.dev_u8.copy_(slot['pin_in'], non_blocking=True)
             h.call('e2_u8_to_f32', _lib.ptr(self.dev_u8), self.t_in.ptr(), self.dev_u8.numel(), C.c_float(255.0), s)
             self.h2d_bytes += self.dev_u8.numel()
         else:
-            self.pinned_f32[0].copy_(torch.from_numpy(np.ascontiguousarray(patch, dtype=np.float32)))
+            slot['pin_in'][0].copy_(torch.from_numpy(np.ascontiguousarray(patch, dtype=np.float32)))
             dst = self.staging if self.staging is not None else \
-                self.t_in.buf[self.t_in.offset:self.t_in.offset + self.pinned_f32.numel()].view(self.in_shape)
-            dst.copy_(self.pinned_f32, non_blocking=True)
-            self.h2d_bytes += self.pinned_f32.numel() * 4
+                self.t_in.buf[self.t_in.offset:self.t_in.offset + slot['pin_in'].numel()].view(self.in_shape)
+            dst.copy_(slot['pin_in'], non_blocking=True)
+            self.h2d_bytes += slot['pin_in'].numel() * 4
         self.plan.execute()
         h.call('e2_ndhwc_to_ncdhw', C.byref(self.out.desc), self.out.ptr(), _lib.ptr(self.out_ncdhw), s)
         if self.as_uint8:
             h.call('e2_f32_to_u8', _lib.ptr(self.out_ncdhw), _lib.ptr(self.out_u8), self.out_ncdhw.numel(),
                    C.c_float(255.0), s)
-            self.host_out.copy_(self.out_u8, non_blocking=True)
+            slot['host_out'].copy_(self.out_u8, non_blocking=True)
         else:
-            self.host_out.copy_(self.out_ncdhw, non_blocking=True)
-        torch.cuda.current_stream(self.plan.device).synchronize()
-        self.d2h_bytes += self.host_out.numel() * self.host_out.element_size()
-        return self.host_out.numpy()[0]
+            slot['host_out'].copy_(self.out_ncdhw, non_blocking=True)
+        slot['done'].record()
+        slot['busy'] = True
+        self._queue.append(slot)
+        self.d2h_bytes += slot['host_out'].numel() * slot['host_out'].element_size()
+
+    def collect(self):
+        slot = self._queue.pop(0)
+        slot['done'].synchronize()
+        slot['busy'] = False
+        return slot['host_out'].numpy()[0]
 
 
 def predict_dense(node, raw_img, as_uint8=False, pad_raw=False, tile_range=None, out=None, return_stats=False):
@@ -145,6 +173,12 @@ def predict_dense(node, raw_img, as_uint8=False, pad_raw=False, tile_range=None,
         tiles = tiles[tile_range[0]:tile_range[1]]
     one_call = all(s == 1 for s in strides)
     prob = np.zeros([n_lab] + list(prob_sh), dtype=dtype)
+    def place(lo, right, end_tile, p):
+        if end_tile:
+            p = p[:, :prob_sh[0] - right[0], :prob_sh[1] - right[1], :prob_sh[2] - right[2]]
+        predictions[:, lo[0]:lo[0] + prob_sh[0], lo[1]:lo[1] + prob_sh[1], lo[2]:lo[2] + prob_sh[2]] = p
+
+    pending = None
     for (z_t, x_t, y_t) in tiles:
         lo = [z_t * prob_sh[0], x_t * prob_sh[1], y_t * prob_sh[2]]
         raw_tile = raw_img[:, lo[0]:lo[0] + tile_sh[0], lo[1]:lo[1] + tile_sh[1], lo[2]:lo[2] + tile_sh[2]]
@@ -153,17 +187,20 @@ def predict_dense(node, raw_img, as_uint8=False, pad_raw=False, tile_range=None,
         if end_tile:
             raw_tile = np.pad(raw_tile, [(0, 0)] + [(0, int(r)) for r in right], mode='constant')
         if one_call:
-            prob[:] = runner.forward(raw_tile)
+            # the GPU works on this tile while the host assembles the previous one and cuts the next
+            runner.submit(raw_tile)
+            if pending is not None:
+                place(*pending, runner.collect())
+            pending = (lo, right, end_tile)
         else:
             for x_off in range(strides[1]):
                 for y_off in range(strides[2]):
                     for z_off in range(strides[0]):
                         cut = raw_tile[:, z_off:z_off + patch[0], x_off:x_off + patch[1], y_off:y_off + patch[2]]
                         prob[:, z_off::strides[0], x_off::strides[1], y_off::strides[2]] = runner.forward(cut)
-        p = prob
-        if end_tile:
-            p = prob[:, :prob_sh[0] - right[0], :prob_sh[1] - right[1], :prob_sh[2] - right[2]]
-        predictions[:, lo[0]:lo[0] + prob_sh[0], lo[1]:lo[1] + prob_sh[1], lo[2]:lo[2] + prob_sh[2]] = p
+            place(lo, right, end_tile, prob)
+    if pending is not None:
+        place(*pending, runner.collect())
     dt = time.time() - t_start
     n_vox = float(np.prod(pred_sh))
     logger.info("Predicted img %s in %d Blocks %s: %.3f MPix/s" % (raw_img.shape, len(tiles), n_tiles, n_vox / 1e6 / dt))
