@@ -17,7 +17,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
-ACT = {'lin': 0, 'linear': 0, 'relu': 1, 'tanh': 2, 'sig': 3, 'sigmoid': 3, 'logistic': 3, 'abs': 4}
+ACT = {'lin': 0, 'linear': 0, 'relu': 1, 'tanh': 2, 'sig': 3, 'sigmoid': 3, 'logistic': 3, 'abs': 4, 'soft+': 5, 'elu': 6,
+       'selu': 7}
 COMPUTE = {'f32': 0, 'tf32': 1, 'bf16': 2}
 TIE = {'first': 0, 'all': 1}
 

@@ -70,6 +70,9 @@ static __device__ __noinline__ float e2_apply_act_slow(float v, int act) {
     case E2_ACT_TANH: return tanhf(v);
     case E2_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
     case E2_ACT_ABS: return fabsf(v);
+    case E2_ACT_SOFTPLUS: return v > 20.f ? v : log1pf(expf(v));                      // T.nnet.softplus
+    case E2_ACT_ELU: return v > 0.f ? v : expm1f(v);                                   // T.nnet.elu(x, alpha=1)
+    case E2_ACT_SELU: return 1.0507009873554805f * (v > 0.f ? v : 1.6732632423543772f * expm1f(v));   // computations.py:89-98
     default: return v;
   }
 }

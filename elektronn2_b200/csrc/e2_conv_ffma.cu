@@ -612,6 +612,10 @@ __global__ void __launch_bounds__(256) k_act_bwd(const float* __restrict__ y, co
       case E2_ACT_RELU: r = yv > 0.f ? g : 0.f; break;
       case E2_ACT_TANH: r = g * (1.f - yv * yv); break;
       case E2_ACT_SIGMOID: r = g * yv * (1.f - yv); break;
+      // derivatives expressed through the OUTPUT y (the pre-activation is not kept):
+      case E2_ACT_SOFTPLUS: r = g * (1.f - __expf(-yv)); break;                        // sigmoid(x) = 1 - exp(-softplus(x))
+      case E2_ACT_ELU: r = yv > 0.f ? g : g * (yv + 1.f); break;                        // exp(x) = y + 1 for x <= 0
+      case E2_ACT_SELU: r = yv > 0.f ? g * 1.0507009873554805f : g * (yv + 1.0507009873554805f * 1.6732632423543772f); break;
       default: r = g; break;
     }
     dpre[ofs] = r;

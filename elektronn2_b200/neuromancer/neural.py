@@ -21,7 +21,7 @@ from .shapecalc import mfp_bookkeeping
 
 logger = logging.getLogger('elektronn2log')
 
-_ACTS = ('relu', 'lin', 'linear', 'tanh', 'sig', 'sigmoid', 'logistic', 'abs')
+_ACTS = ('relu', 'lin', 'linear', 'tanh', 'sig', 'sigmoid', 'logistic', 'abs', 'soft+', 'elu', 'selu')
 
 
 class NeuralLayer(Node):

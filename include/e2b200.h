@@ -45,7 +45,9 @@ typedef enum {
 } e2_status;
 
 /* apply_activation, computations.py:57-134 (the parameter-free subset) */
-typedef enum { E2_ACT_LIN = 0, E2_ACT_RELU = 1, E2_ACT_TANH = 2, E2_ACT_SIGMOID = 3, E2_ACT_ABS = 4 } e2_act;
+/* apply_activation, computations.py:57-134: 'soft+' = log(1+exp(x)), 'elu' = T.nnet.elu(x, 1), 'selu' = scale * elu(x, alpha) */
+typedef enum { E2_ACT_LIN = 0, E2_ACT_RELU = 1, E2_ACT_TANH = 2, E2_ACT_SIGMOID = 3, E2_ACT_ABS = 4,
+               E2_ACT_SOFTPLUS = 5, E2_ACT_ELU = 6, E2_ACT_SELU = 7 } e2_act;
 
 /* arithmetic used inside the conv GEMMs (accumulation is always fp32) */
 typedef enum {

@@ -328,6 +328,10 @@ def concat_f(parts):
 
 
 # --------------------------------------------------------------------- epilogue
+SELU_ALPHA = 1.6732632423543772848170429916717     # computations.py:96-97
+SELU_SCALE = 1.0507009873554804934193349852946
+
+
 def activation(x, name):
     """apply_activation (computations.py:57-134), the parameter-free ones."""
     x = np.asarray(x, F64)
@@ -345,6 +349,8 @@ def activation(x, name):
         return np.logaddexp(0.0, x)
     if name == 'elu':
         return np.where(x > 0, x, np.expm1(np.minimum(x, 0)))
+    if name == 'selu':   # computations.py:89-98: scale * T.nnet.elu(x, alpha)
+        return SELU_SCALE * np.where(x > 0, x, SELU_ALPHA * np.expm1(np.minimum(x, 0)))
     raise NotImplementedError(name)
 
 
@@ -365,6 +371,12 @@ def activation_bwd(dy, pre, name):
         return dy * s * (1 - s)
     if name == 'abs':
         return dy * np.sign(pre)
+    if name == 'soft+':
+        return dy / (1.0 + np.exp(-pre))
+    if name == 'elu':
+        return dy * np.where(pre > 0, 1.0, np.exp(np.minimum(pre, 0)))
+    if name == 'selu':
+        return dy * SELU_SCALE * np.where(pre > 0, 1.0, SELU_ALPHA * np.exp(np.minimum(pre, 0)))
     raise NotImplementedError(name)
 
 

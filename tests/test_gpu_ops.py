@@ -531,3 +531,28 @@ def test_pool_and_mfp_kernels_stay_inside_their_buffers(h, c):
     torch.cuda.synchronize()
     assert guards_intact(ym) and guards_intact(mop.argmax)
     assert np.array_equal(ym.numpy(), oo.fragmentpool(xm, (2, 2, 2), np.zeros((1, 3), int), [1, 1, 1])[0])
+
+
+@pytest.mark.parametrize('act', ['tanh', 'sigmoid', 'soft+', 'elu', 'selu'])
+def test_epilogue_activations_and_their_backward(h, act):
+    """apply_activation (computations.py:57-134) in the fused conv epilogue (z-stack kernel shape and tap-kernel
+    shape) and its derivative, which the B200 path evaluates from the OUTPUT y (the pre-activation is not kept)."""
+    from elektronn2_b200.ops import ConvOp, act_bwd
+    r = np.random.RandomState(11)
+    for (ci, sp, co) in [(32, (5, 16, 12), 48), (20, (3, 7, 9), 24)]:
+        x = (r.rand(1, ci, *sp) - 0.5).astype(np.float32)
+        w = (r.randn(co, ci, 3, 3, 3) * np.sqrt(2.0 / (ci * 27))).astype(np.float32)
+        b = (r.randn(co) * 0.1).astype(np.float32)
+        osp = [s - 2 for s in sp]
+        pre = oo.conv3d(x, w) + b.reshape(1, -1, 1, 1, 1)
+        for compute in ('f32', 'tf32'):
+            xd, yd = dev(x), empty(1, co, osp)
+            op = ConvOp(h, xd, yd, t(w), t(b), (3, 3, 3), act, compute)
+            op.pack()
+            op.fwd()
+            assert rel(yd.numpy(), oo.activation(pre, act)) <= TOL[compute]
+        dy = r.randn(1, co, *osp).astype(np.float32)
+        yref = dev(oo.activation(pre, act).astype(np.float32))
+        dyd = dev(dy)
+        act_bwd(h, dyd, act, yref, dyd, dyd)           # in place, as the executor does
+        assert rel(dyd.numpy(), oo.activation_bwd(dy, pre, act)) <= 2e-5
