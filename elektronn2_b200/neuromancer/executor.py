@@ -16,7 +16,9 @@ Data layout in HBM:
                             reverse graph order so the backward pass completes them
                             front to back (bucketed all-reduce overlaps with wgrad)
 """
+import contextlib
 import ctypes as C
+import gc
 import os
 
 import numpy as np
@@ -29,6 +31,25 @@ from ..devtensor import DevTensor
 from . import loss as loss_nodes
 from .neural import Conv, UpConv, Pool, Crop, FragmentsToDense
 from .node_basic import Input, Concat
+
+
+@contextlib.contextmanager
+def _capture(graph, stream=None):
+    """``torch.cuda.graph`` with the cyclic garbage collector off.  A collection in the middle of a capture can run
+    finalisers of objects from earlier plans (CUDA graphs, handles, pinned buffers) whose CUDA calls invalidate the
+    capture -- seen as an intermittent "operation failed due to a previous error during capture"."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        kw = dict(capture_error_mode='thread_local')
+        if stream is not None:
+            kw['stream'] = stream
+        with torch.cuda.graph(graph, **kw):
+            yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class ParamStore(object):
@@ -709,9 +730,9 @@ class Plan(object):
                     if self._capture_stream is None:
                         self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1) \
                             if os.environ.get('E2_MAIN_PRIO', '1') != '0' else torch.cuda.Stream(device=self.device)
-                    with torch.cuda.graph(g1, stream=self._capture_stream, capture_error_mode='thread_local'):
+                    with _capture(g1, self._capture_stream):
                         self._train_body_fwd(opt)
-                    with torch.cuda.graph(g2, stream=self._capture_stream, capture_error_mode='thread_local'):
+                    with _capture(g2, self._capture_stream):
                         self._train_body_bwd(opt, dp)
                     # the captures ran no kernel: t_dev / parameters are untouched
                     graphs = self._opt_graphs[key] = (g1, g2)
@@ -754,7 +775,7 @@ class Plan(object):
                 self.pack()                    # warm-up outside capture
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with _capture(g):
                     self.pack()
                 self._pack_graph = g
             self._pack_graph.replay()
@@ -817,7 +838,7 @@ class Plan(object):
                     self._launch_all()  # warm-up outside capture
                     torch.cuda.synchronize(self.device)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with _capture(g):
                         self._launch_all()
                     self._graph = g
                 self._graph.replay()
@@ -852,7 +873,7 @@ class Plan(object):
                 torch.cuda.synchronize(self.device)
                 try:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    with _capture(g):
                         body()
                     self._graph = g
                 except Exception as e:      # noqa: BLE001 - any capture failure -> eager
