@@ -52,6 +52,23 @@ def _capture(graph, stream=None):
             gc.enable()
 
 
+def _try_capture(fn, device, what):
+    """Capture ``fn`` into a CUDA graph; None (with a warning) if the capture is refused or invalidated."""
+    g = torch.cuda.CUDAGraph()
+    try:
+        with _capture(g):
+            fn()
+        return g
+    except Exception as e:          # noqa: BLE001
+        import warnings
+        warnings.warn('CUDA-graph capture of %s failed (%s); running eagerly' % (what, e))
+        try:
+            torch.cuda.synchronize(device)
+        except Exception:           # noqa: BLE001
+            torch.cuda.synchronize(device)
+        return None
+
+
 class ParamStore(object):
     """Flat device buffers for all trainable parameters of a model."""
 
@@ -737,12 +754,16 @@ class Plan(object):
                     # the captures ran no kernel: t_dev / parameters are untouched
                     graphs = self._opt_graphs[key] = (g1, g2)
                 except Exception as e:      # noqa: BLE001
-                    if dp is None:
-                        raise
+                    # a refused / invalidated capture must not cost the step: run it eagerly from now on
                     import warnings
-                    warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
-                    dp.graph_ok = False
-                    torch.cuda.synchronize(self.device)
+                    warnings.warn('CUDA-graph capture of the training step failed (%s); running eagerly' % (e,))
+                    if dp is not None:
+                        dp.graph_ok = False
+                    self.use_graph = False
+                    try:
+                        torch.cuda.synchronize(self.device)
+                    except Exception:       # noqa: BLE001 - the capture error may surface once more here
+                        torch.cuda.synchronize(self.device)
                     graphs = None
         if graphs is not None:
             graphs[0].replay()
@@ -774,12 +795,12 @@ class Plan(object):
             if self._pack_graph is None:
                 self.pack()                    # warm-up outside capture
                 torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with _capture(g):
-                    self.pack()
-                self._pack_graph = g
-            self._pack_graph.replay()
-            self._packed_version = self.store.version
+                self._pack_graph = _try_capture(self.pack, self.device, 'the weight re-pack') or False
+            if self._pack_graph:
+                self._pack_graph.replay()
+                self._packed_version = self.store.version
+            else:
+                self.pack()
         else:
             self.pack()
 
@@ -833,14 +854,13 @@ class Plan(object):
         self._commit_inputs()
         if not self.train:
             self._ensure_packed(False)
-            if self.use_graph:
+            if self.use_graph and self._graph is None:
+                self._launch_all()  # warm-up outside capture
+                torch.cuda.synchronize(self.device)
+                self._graph = _try_capture(self._launch_all, self.device, 'the forward pass')
                 if self._graph is None:
-                    self._launch_all()  # warm-up outside capture
-                    torch.cuda.synchronize(self.device)
-                    g = torch.cuda.CUDAGraph()
-                    with _capture(g):
-                        self._launch_all()
-                    self._graph = g
+                    self.use_graph = False
+            if self._graph is not None:
                 self._graph.replay()
             else:
                 self._launch_all()
@@ -871,18 +891,11 @@ class Plan(object):
             if self._graph is None:
                 body()                      # eager warm-up (also creates the communicators outside the capture)
                 torch.cuda.synchronize(self.device)
-                try:
-                    g = torch.cuda.CUDAGraph()
-                    with _capture(g):
-                        body()
-                    self._graph = g
-                except Exception as e:      # noqa: BLE001 - any capture failure -> eager
-                    if dp is None:
-                        raise
-                    import warnings
-                    warnings.warn('data-parallel CUDA-graph capture failed (%s); running eagerly' % (e,))
-                    dp.graph_ok = False
-                    torch.cuda.synchronize(self.device)
+                self._graph = _try_capture(body, self.device, 'the training pass')
+                if self._graph is None:     # refused / invalidated: this plan stays eager
+                    self.use_graph = False
+                    if dp is not None:
+                        dp.graph_ok = False
                     body()
                     self._mark_inputs_free()
                     return
