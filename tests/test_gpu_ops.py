@@ -556,3 +556,51 @@ def test_epilogue_activations_and_their_backward(h, act):
         dyd = dev(dy)
         act_bwd(h, dyd, act, yref, dyd, dyd)           # in place, as the executor does
         assert rel(dyd.numpy(), oo.activation_bwd(dy, pre, act)) <= 2e-5
+
+
+def _round_tf32(a):
+    """Round-to-nearest-even to 10 explicit mantissa bits (what the producers of tensor-core operands do)."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize('case', [
+    (768, (14, 18, 18), 256),    # unet3d mconv0: z-stack kernel with K split (fwd), tap kernel split-K (dgrad)
+    (256, (11, 13, 13), 256),    # unet3d conv6: tiny planes -> tap kernel with split-K, wgrad with many splits
+    (64, (56, 64, 64), 64),      # unet3d conv2: z-stack / halo-wgrad kernels, several waves
+    (512, (7, 9, 9), 512),       # upconv mrg0 (as UpConv below)
+])
+def test_full_size_adjoint_identities(h, case):
+    """Size-independent property at the BASELINE layer sizes (the float64 oracle would take minutes here):
+    forward, dgrad and wgrad are the three faces of one bilinear form,
+        <dy, conv(x, w)> == <dgrad(dy, w), x> == <wgrad(dy, x), w>.
+    With tf32-representable x, w, dy the tensor-core products are exact, so the three numbers differ only by fp32
+    accumulation order / output rounding."""
+    from elektronn2_b200.ops import ConvOp, UpConvOp
+    ci, sp, co = case
+    r = np.random.RandomState(5)
+    up = ci == 512
+    k = (2, 2, 2) if up else (3, 3, 3)
+    osp = [s * 2 for s in sp] if up else [s - 2 for s in sp]
+    x = _round_tf32(r.rand(1, ci, *sp).astype(np.float32) - 0.5)
+    w = _round_tf32((r.randn(co, ci, *k) * np.sqrt(2.0 / (ci * np.prod(k)))).astype(np.float32))
+    dy = _round_tf32(r.randn(1, co, *osp).astype(np.float32))
+    xd, yd, dyd, dxd = dev(x), empty(1, co, osp), dev(dy), empty(1, ci, sp)
+    op = (UpConvOp if up else ConvOp)(h, xd, yd, t(w), None, k, 'lin', 'tf32')
+    op.pack()
+    d = op.d
+    d.has_bias = 0
+    op.fwd() if up else op.fwd(act='lin', has_bias=0)
+    op.dgrad(dyd, dxd)
+    dw = torch.zeros(w.shape, device='cuda')
+    op.wgrad(dyd, dw, None)
+    y = yd.numpy().astype(np.float64)
+    a = float((dy.astype(np.float64) * y).sum())
+    b = float((dxd.numpy().astype(np.float64) * x.astype(np.float64)).sum())
+    c = float((dw.cpu().numpy().astype(np.float64) * w.astype(np.float64)).sum())
+    # y and dx are rounded to tf32 on store (relative 2^-11 per element, random sign), dw is plain fp32: with
+    # nat = the natural magnitude of such an inner product (||dy|| ||y|| / sqrt(#elements)) the three numbers agree
+    # to ~3e-4 * nat; a dropped filter tap (1/27) or a lost tile would show up at >= 1e-2 * nat
+    nat = float(np.sqrt((dy.astype(np.float64) ** 2).sum() * (y ** 2).sum() / y.size))
+    assert abs(a - b) <= 2e-3 * nat and abs(a - c) <= 2e-3 * nat and abs(b - c) <= 2e-3 * nat, (a, b, c, nat)
