@@ -391,8 +391,12 @@ static void plan_tc(int sm_count, const GatherGemm& g, int tiles_m, bool may_spl
   if (bn > 256) bn = 256;
   // the shuffle epilogue wants whole 32-channel runs; keep multiples of 32 when N allows
   while (bn > 64 && (int64_t)tiles_m * ((g.N + bn - 1) / bn) < sm_count) bn = (bn / 2 + 31) / 32 * 32;
-  const int tiles_n = (g.N + bn - 1) / bn;
   const int total = g.tz * g.tx * g.ty * ((g.K + BK - 1) / BK);
+  // short K loops (upconv forward: K = F_in, one tap) are epilogue-dominated: with N tiles of 128 two CTAs fit an SM
+  // and one's epilogue runs under the other's loads and MMAs
+  static const int short_bn = getenv("E2_TC_SHORT_BN") ? atoi(getenv("E2_TC_SHORT_BN")) : 128;
+  if (total <= 8 && bn > short_bn && short_bn >= 32) bn = short_bn;
+  const int tiles_n = (g.N + bn - 1) / bn;
   int ksplit = 1;
   if (may_split) {
     const int64_t ctas = (int64_t)tiles_m * tiles_n;
