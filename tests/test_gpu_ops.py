@@ -604,3 +604,52 @@ def test_full_size_adjoint_identities(h, case):
     # to ~3e-4 * nat; a dropped filter tap (1/27) or a lost tile would show up at >= 1e-2 * nat
     nat = float(np.sqrt((dy.astype(np.float64) ** 2).sum() * (y ** 2).sum() / y.size))
     assert abs(a - b) <= 2e-3 * nat and abs(a - c) <= 2e-3 * nat and abs(b - c) <= 2e-3 * nat, (a, b, c, nat)
+
+
+def test_functional_layer_and_theano_perform(h):
+    """numpy in / numpy out face (elektronn2_b200.functional: the granularity of computations.py and of a Theano
+    Op.perform) against the oracle, and B200Conv3d / B200MaxPool3d .perform() driven through the stand-in theano."""
+    import sys
+    from elektronn2_b200 import functional as F
+    r = np.random.RandomState(13)
+    x = r.rand(2, 6, 5, 9, 10).astype(np.float32)
+    w = (r.randn(8, 6, 3, 3, 3) * 0.2).astype(np.float32)
+    y = F.conv3d(x, w, compute='f32')
+    assert rel(y, oo.conv3d(x, w)) <= TOL['f32']
+    dy = r.randn(*y.shape).astype(np.float32)
+    assert rel(F.conv3d_grad_input(dy, w, x.shape, compute='f32'), oo.conv3d_dgrad(dy, w, x.shape)) <= TOL['f32']
+    assert rel(F.conv3d_grad_weights(x, dy, w.shape, compute='f32'), oo.conv3d_wgrad(dy, x, w.shape)) <= TOL['f32']
+    assert rel(F.conv3d(x, w), oo.conv3d(x, w)) <= TOL['tf32']
+    wu = (r.randn(4, 6, 1, 2, 2) * 0.3).astype(np.float32)
+    yu = F.upconv3d(x, wu, (1, 2, 2), compute='f32')
+    assert rel(yu, oo.upconv3d(x, wu, (1, 2, 2))) <= TOL['f32']
+    dyu = r.randn(*yu.shape).astype(np.float32)
+    assert rel(F.upconv3d_grad_input(dyu, wu, x.shape, (1, 2, 2), compute='f32'), oo.upconv3d_dgrad(dyu, wu, (1, 2, 2))) <= TOL['f32']
+    assert rel(F.upconv3d_grad_weights(x, dyu, wu.shape, (1, 2, 2), compute='f32'), oo.upconv3d_wgrad(dyu, x, (1, 2, 2))) <= TOL['f32']
+    xp = np.maximum(r.rand(1, 5, 4, 6, 8).astype(np.float32) - 0.3, 0)
+    yp, idx = F.maxpool3d(xp, (2, 2, 2), return_argmax=True)
+    assert np.array_equal(yp, oo.pooling(xp, (2, 2, 2))) and np.array_equal(idx, oo.pooling_argmax(xp, (2, 2, 2)))
+    dyp = r.randn(*yp.shape).astype(np.float32)
+    for tie in ('first', 'all'):
+        assert np.array_equal(F.maxpool3d_grad(xp, dyp, (2, 2, 2), tie), oo.pooling_bwd(dyp, xp, (2, 2, 2), tie).astype(np.float32))
+    xm = r.rand(1, 3, 7, 9, 11).astype(np.float32)
+    ref, off, st = oo.fragmentpool(xm, (2, 2, 2), [[0, 0, 0]], [1, 1, 1])
+    fr = F.fragmentpool(xm, (2, 2, 2))
+    assert np.array_equal(fr, ref)
+    assert np.array_equal(F.fragments2dense(fr, off, st), oo.fragments2dense(ref, off, st))
+    # Theano Op.perform() through the stand-in package
+    sys.path.insert(0, HERE)
+    import theano_stub
+    theano_stub.install()
+    try:
+        import importlib
+        tops = importlib.import_module('elektronn2_b200.theano_ops')
+        out = [[None]]
+        tops.B200Conv3d('f32').perform(None, [x, w], out)
+        assert out[0][0].shape == y.shape and rel(out[0][0], oo.conv3d(x, w)) <= TOL['f32']
+        tops.B200MaxPool3d((2, 2, 2)).perform(None, [xp], out)
+        assert np.array_equal(out[0][0], yp)
+        tops.B200Conv3dGradW('f32').perform(None, [x, dy, np.array(w.shape)], out)
+        assert rel(out[0][0], oo.conv3d_wgrad(dy, x, w.shape)) <= TOL['f32']
+    finally:
+        theano_stub.uninstall()

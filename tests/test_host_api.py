@@ -8,6 +8,7 @@ import json
 import os
 import re
 import runpy
+import sys
 
 import numpy as np
 import pytest
@@ -268,3 +269,36 @@ def test_mdl_round_trip_uses_reference_module_paths(tmp_path):
         assert np.array_equal(a.get_value(), b.get_value())
     with pytest.raises(NotImplementedError):
         nm.modelload(fn2, make_weights_constant=True)
+
+
+def test_theano_op_wiring_against_a_stub_theano():
+    """The Theano Ops of INTEGRATION.md §4 follow the reference's Op convention (malis/malisop.py:19-123):
+    __props__, make_node -> Apply, grad -> sibling Ops, infer_shape.  Theano is not installable here, so the wiring
+    runs against tests/theano_stub.py (perform() is exercised on the GPU in tests/test_gpu_ops.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import theano_stub
+    theano_stub.install()
+    try:
+        import importlib
+        ops = importlib.import_module('elektronn2_b200.theano_ops')
+        x, w = theano_stub.Variable(5, 'x'), theano_stub.Variable(5, 'w')
+        y = ops.B200Conv3d()(x, w)
+        assert isinstance(y.owner.op, ops.B200Conv3d) and y.owner.inputs == [x, w]
+        gx, gw = y.owner.op.grad([x, w], [theano_stub.Variable(5, 'dy')])
+        assert isinstance(gx.owner.op, ops.B200Conv3dGradI) and isinstance(gw.owner.op, ops.B200Conv3dGradW)
+        assert ops.B200Conv3d().infer_shape(None, [(1, 32, 10, 20, 20), (64, 32, 3, 3, 3)]) == [(1, 64, 8, 18, 18)]
+        assert ops.B200Conv3d('tf32') == ops.B200Conv3d('tf32') and ops.B200Conv3d('f32') != ops.B200Conv3d('tf32')
+        u = ops.B200UpConv3d((2, 2, 2))
+        assert u.infer_shape(None, [(1, 8, 3, 4, 5), (6, 8, 2, 2, 2)]) == [(1, 6, 6, 8, 10)]
+        gi, gwt = u.grad([x, w], [theano_stub.Variable(5)])
+        assert isinstance(gi.owner.op, ops.B200UpConv3dGradI) and gi.owner.op.pool == (2, 2, 2)
+        assert isinstance(gwt.owner.op, ops.B200UpConv3dGradW)
+        p = ops.B200MaxPool3d((1, 2, 2))
+        assert p.infer_shape(None, [(2, 4, 6, 8, 10)]) == [(2, 4, 6, 4, 5)]
+        g, = p.grad([x], [theano_stub.Variable(5)])
+        assert isinstance(g.owner.op, ops.B200MaxPool3dGrad) and g.owner.op.tie_mode == 'first'
+        assert hash(ops.B200Frag2Dense([[0, 0, 0], [0, 0, 1]], (1, 1, 2))) == hash(ops.B200Frag2Dense([[0, 0, 0], [0, 0, 1]], (1, 1, 2)))
+        with pytest.raises(TypeError):
+            ops.B200Conv3d()(theano_stub.Variable(4), w)
+    finally:
+        theano_stub.uninstall()
