@@ -6,5 +6,5 @@ from .node_basic import Node, Input, Input_like, Concat, model_manager, choose_n
 from .neural import Conv, UpConv, Pool, Crop, FragmentsToDense, AutoMerge, UpConvMerge  # noqa: F401
 from .loss import Softmax, MultinoulliNLL, AggregateLoss, Classification, Errors  # noqa: F401
 from .model import Model, rebuild_model, kernel_lists_from_node_descr, modelload  # noqa: F401
-from . import graphmanager, model  # noqa: F401
+from . import graphmanager, model, computations  # noqa: F401
 from . import optimiser  # noqa: F401

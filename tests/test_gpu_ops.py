@@ -653,3 +653,33 @@ def test_functional_layer_and_theano_perform(h):
         assert rel(out[0][0], oo.conv3d_wgrad(dy, x, w.shape)) <= TOL['f32']
     finally:
         theano_stub.uninstall()
+
+
+def test_computations_seam_values(h):
+    """neuromancer.computations (the reference's five functions, same signatures) on the GPU: conv == np.convolve along
+    every axis (the reference's own known answer, tests/test_conv.py:89-104), upconv with the reference's swapped
+    weight layout, pooling, fragmentpool (+ offsets / strides bookkeeping) and fragments2dense against the oracle."""
+    from elektronn2_b200.neuromancer import computations as cp
+    from elektronn2_b200.config import config
+    r = np.random.RandomState(17)
+    old = config.compute
+    config.compute = 'f32'
+    try:
+        sig, ker = r.rand(24).astype(np.float32), r.rand(5).astype(np.float32)
+        for ax in range(3):
+            xs, ks = [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]
+            xs[2 + ax], ks[2 + ax] = 24, 5
+            y = cp.conv(sig.reshape(xs), ker.reshape(ks), axis_order='dnn', conv_dim=3)
+            assert np.allclose(y.ravel(), np.convolve(sig, ker, mode='valid'), rtol=1e-5, atol=1e-6)
+        x = r.rand(1, 6, 4, 5, 6).astype(np.float32)
+        w = (r.randn(4, 6, 2, 2, 2) * 0.3).astype(np.float32)                # node layout (f_out, f_in, p...)
+        yu = cp.upconv(x, np.swapaxes(w, 0, 1), (2, 2, 2))                    # the reference passes (f_in, f_out, p...)
+        assert rel(yu, oo.upconv3d(x, w, (2, 2, 2))) <= TOL['f32']
+        xp = r.rand(1, 3, 7, 9, 11).astype(np.float32)
+        assert np.array_equal(cp.pooling(xp[:, :, :6, :8, :10], (2, 2, 2), [2, 3, 4]), oo.pooling(xp[:, :, :6, :8, :10], (2, 2, 2)))
+        fr, off, st = cp.fragmentpool(xp, (2, 2, 2), [[0, 0, 0]], [1, 1, 1], [2, 3, 4])
+        ref, roff, rst = oo.fragmentpool(xp, (2, 2, 2), [[0, 0, 0]], [1, 1, 1])
+        assert np.array_equal(fr, ref) and np.array_equal(off, roff) and np.array_equal(st, rst)
+        assert np.array_equal(cp.fragments2dense(fr, off, st, [2, 3, 4]), oo.fragments2dense(ref, roff, rst))
+    finally:
+        config.compute = old

@@ -302,3 +302,31 @@ def test_theano_op_wiring_against_a_stub_theano():
             ops.B200Conv3d()(theano_stub.Variable(4), w)
     finally:
         theano_stub.uninstall()
+
+
+def test_computations_seam_error_behaviour():
+    """neuromancer.computations keeps the reference's signatures and exception types (computations.py:259-260, 216,
+    538, 652, 681); the value checks run on the GPU (tests/test_gpu_ops.py)."""
+    from elektronn2_b200.neuromancer import computations as cp
+    x, w = np.zeros((1, 2, 4, 6, 6), np.float32), np.zeros((3, 2, 3, 3, 3), np.float32)
+    with pytest.raises(ValueError):
+        cp.conv(x, w[..., 0], conv_dim=3)                        # computations.py:315-318
+    with pytest.raises(ValueError):
+        cp.conv(x, w[..., 0])                                    # :322-325
+    with pytest.raises(NotImplementedError):
+        cp.conv(x, w, axis_order='dnn', stride=(2, 2, 2))        # :375-376
+    with pytest.raises(NotImplementedError):
+        cp.conv(x, w, axis_order='dnn', border_mode='full')
+    with pytest.raises(ValueError):
+        cp.upconv(x, np.zeros((2, 3, 2, 2, 2), np.float32), (2, 2, 2), axis_order='theano')   # :243-244
+    with pytest.raises(NotImplementedError):
+        cp.pooling(x, (2, 2, 2), [2, 3, 4], stride=(1, 1, 1))    # :612-613
+    with pytest.raises(ValueError):
+        cp.pooling(x, (3, 2, 2), [2, 3, 4])
+    assert cp.pooling(x, (1, 1, 1), [2, 3, 4]) is x             # :569-570 short circuit
+    out = cp.fragmentpool(x, (1, 1, 1), [[0, 0, 0]], [1, 1, 1], [2, 3, 4])
+    assert out[0] is x                                           # :653-654
+    with pytest.raises(ValueError):
+        cp.fragmentpool(x, (2, 2, 2), [[0, 0, 0]], [1, 1, 1], [2, 3, 4])    # (4-2+1) % 2 != 0
+    with pytest.raises(ValueError):
+        cp.fragments2dense(np.zeros((3, 2, 2, 2, 2), np.float32), [[0, 0, 0]] * 3, (1, 2, 2), [2, 3, 4])
