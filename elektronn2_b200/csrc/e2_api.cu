@@ -32,7 +32,7 @@ extern "C" int e2_destroy(e2_handle* h) {
 }
 
 extern "C" const char* e2_last_error(const e2_handle* h) { return h ? h->err : "null handle"; }
-extern "C" int64_t e2_launch_count(const e2_handle* h) { return h ? h->launches : -1; }
+extern "C" int64_t e2_launch_count(const e2_handle* h) { return h ? __atomic_load_n(&h->launches, __ATOMIC_RELAXED) : -1; }
 
 // ---------------------------------------------------------------- NCDHW <-> NDHWC
 // A [C][P] <-> [P][c_pitch] transpose per batch item through a padded 32x32 smem tile;
@@ -85,7 +85,7 @@ static int layout_launch(e2_handle* h, const e2_tensor* t, const float* src, flo
   dim3 grid((unsigned)((P + 31) / 32), (unsigned)((t->c + 31) / 32), (unsigned)t->n);
   E2_REQUIRE(h, grid.y <= 65535 && grid.z <= 65535, "layout_convert: too many channels / batch items");
   k_layout<TO_CL><<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, t->c, P, t->c_pitch);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "layout_convert");
   return E2_OK;
 }
@@ -120,7 +120,7 @@ extern "C" int e2_repitch(e2_handle* h, const e2_tensor* src_t, const float* src
   const int64_t P = e2_positions(src_t);
   k_repitch<<<e2_grid_1d(P * dst_t->c_pitch, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(
       src, dst, P, src_t->c, src_t->c_pitch, dst_t->c_pitch, round_tf32);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "repitch");
   return E2_OK;
 }
@@ -156,7 +156,7 @@ extern "C" int e2_u8_to_f32(e2_handle* h, const uint8_t* src, float* dst, int64_
   E2_REQUIRE(h, src && dst && count >= 0 && scale != 0.f, "u8_to_f32: bad arguments");
   if (count == 0) return E2_OK;
   k_u8_to_f32<<<e2_grid_1d((count + 3) / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(src, dst, count, scale);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "u8_to_f32");
   return E2_OK;
 }
@@ -165,7 +165,7 @@ extern "C" int e2_f32_to_u8(e2_handle* h, const float* src, uint8_t* dst, int64_
   E2_REQUIRE(h, src && dst && count >= 0, "f32_to_u8: bad arguments");
   if (count == 0) return E2_OK;
   k_f32_to_u8<<<e2_grid_1d(count, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(src, dst, count, scale);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "f32_to_u8");
   return E2_OK;
 }

@@ -16,6 +16,9 @@ struct e2_handle {
   void* tmap_cache;  // tcgen05 path: host-side tensor-map cache (opaque)
 };
 
+// launch counter (e2_launch_count): atomic, a handle may be driven from several host threads / streams
+static inline void e2_count_launch(e2_handle* h) { __atomic_fetch_add(&h->launches, (int64_t)1, __ATOMIC_RELAXED); }
+
 static inline int e2_fail(e2_handle* h, int code, const char* fmt, ...) {
   if (h) {
     va_list ap;

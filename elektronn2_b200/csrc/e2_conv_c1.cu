@@ -450,7 +450,7 @@ int launch_wgrad(e2_handle* h, const ReduceGemm& g, cudaStream_t s) {
   const int gx = std::max(1, std::min(lines, per_sm * h->sm_count));
   dim3 grid((unsigned)gx, (unsigned)((g.R + 31) / 32));
   k_c1_wgrad_line<KY><<<grid, 32 * rows, smem, s>>>(g, lines);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_wgrad_line");
   return E2_OK;
 }
@@ -479,7 +479,7 @@ int e2_launch_conv_c1_fwd_line(e2_handle* h, const GatherGemm& g, cudaStream_t s
   const int gx = std::max(1, std::min(lines, 8 * h->sm_count));
   dim3 grid((unsigned)gx, (unsigned)((g.N + 31) / 32));
   k_c1_fwd_line<<<grid, 256, smem, s>>>(g, lines);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_fwd_line");
   return E2_OK;
 }
@@ -528,7 +528,7 @@ int e2_launch_conv_c1_fwd_reg(e2_handle* h, const GatherGemm& g, cudaStream_t s)
     case 3: k_c1_fwd_reg<1, 4, 4><<<grid, 256, 0, s>>>(g, ntx, nty, tiles); break;
     default: return e2_fail(h, E2_ERR_UNSUPPORTED, "conv c_in==1 fwd: no register-tiled variant");
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_fwd_reg");
   return E2_OK;
 }
@@ -553,7 +553,7 @@ int e2_launch_conv_c1_wgrad_reg(e2_handle* h, const ReduceGemm& g, float* db, cu
     case 3: k_c1_wgrad_reg<1, 4, 4><<<grid, 256, 0, s>>>(g, ntx, nty, tiles, db); break;
     default: return e2_fail(h, E2_ERR_UNSUPPORTED, "conv c_in==1 wgrad: no register-tiled variant");
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_wgrad_reg");
   return E2_OK;
 }

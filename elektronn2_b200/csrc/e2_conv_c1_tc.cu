@@ -319,7 +319,7 @@ int e2_launch_conv_c1_fwd_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     k_c1_fwd_tc<true><<<grid, C1_THREADS, smem, s>>>(p);
   else
     k_c1_fwd_tc<false><<<grid, C1_THREADS, smem, s>>>(p);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_fwd_tc");
   return E2_OK;
 }

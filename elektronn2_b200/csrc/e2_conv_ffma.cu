@@ -159,16 +159,16 @@ extern "C" int e2_conv3d_pack_weights(e2_handle* h, const e2_conv_desc* d, const
       }
       k_pack_conv_wf<<<grid, 256, slab_bytes, s>>>(w, wf, d->x.c, d->kz, d->kx, d->ky, cp, tf32,
                                                   e2_fastdiv((uint32_t)T, (uint64_t)WF_CH * T));
-      h->launches++;
+      e2_count_launch(h);
     }
     if (wd) {
       dim3 grid((unsigned)((M + 31) / 32), (unsigned)((d->y.c + 31) / 32));
       k_pack_conv_wd<<<grid, 256, 0, s>>>(w, wd, d->y.c, M, op, tf32);
-      h->launches++;
+      e2_count_launch(h);
     }
   } else {
     k_pack_conv<<<e2_grid_1d(total, 256, h->sm_count), 256, 0, s>>>(w, wf, wd, d->y.c, d->x.c, d->kz, d->kx, d->ky, cp, op, tf32);
-    h->launches++;
+    e2_count_launch(h);
   }
   E2_CUDA_CHECK(h, "conv3d_pack_weights");
   return E2_OK;
@@ -204,7 +204,7 @@ extern "C" int e2_upconv3d_pack_weights(e2_handle* h, const e2_upconv_desc* d, c
   int64_t total = (int64_t)d->y.c * d->x.c * T;
   k_pack_upconv<<<e2_grid_1d(total, 256, h->sm_count), 256, 0, s>>>(w, wf, wd, d->y.c, d->x.c, T, cp, np,
                                                                     d->compute == E2_COMPUTE_TF32);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "upconv3d_pack_weights");
   return E2_OK;
 }
@@ -318,7 +318,7 @@ int e2_launch_gather_gemm_ffma(e2_handle* h, const GatherGemm& g, cudaStream_t s
   int64_t M = (int64_t)g.On * g.Oz * g.Ox * g.Oy;
   dim3 grid((unsigned)((M + GBM - 1) / GBM), (unsigned)((g.N + GBN - 1) / GBN));
   k_gather_gemm<<<grid, 256, 0, s>>>(g);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "gather_gemm_ffma");
   return E2_OK;
 }
@@ -378,7 +378,7 @@ int e2_launch_conv_c1_fwd(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
   size_t smem = sizeof(float) * T * NB;
   if (smem > 48 * 1024) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv c_in==1: filter too large");
   k_conv_c1_fwd<NB><<<grid, 128, smem, s>>>(g);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_fwd");
   return E2_OK;
 }
@@ -473,7 +473,7 @@ int e2_launch_reduce_gemm_ffma(e2_handle* h, const ReduceGemm& g, cudaStream_t s
   cudaMemsetAsync(g.W, 0, sizeof(float) * (size_t)g.R * g.S * T, s);
   dim3 grid((unsigned)tiles, (unsigned)T, (unsigned)splits);
   k_reduce_gemm<<<grid, 256, 0, s>>>(g);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "reduce_gemm_ffma");
   return E2_OK;
 }
@@ -551,7 +551,7 @@ int e2_launch_conv_c1_wgrad(e2_handle* h, const ReduceGemm& g, cudaStream_t s) {
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)((g.R + 31) / 32));
   k_conv_c1_wgrad<<<grid, 256, 0, s>>>(g);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_c1_wgrad");
   return E2_OK;
 }
@@ -596,7 +596,7 @@ int e2_launch_bias_grad(e2_handle* h, const float* dy, int64_t M, int C, int pit
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)((C + 31) / 32));
   k_bias_grad<<<grid, 256, 0, s>>>(dy, M, C, pitch, db);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "bias_grad");
   return E2_OK;
 }
@@ -630,18 +630,16 @@ extern "C" int e2_act_bwd(e2_handle* h, const e2_tensor* t, int32_t act, const f
   int64_t P = e2_positions(t);
   k_act_bwd<<<e2_grid_1d(P * t->c, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(y, dy, dpre, P, t->c, t->c_pitch,
                                                                                       act);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "act_bwd");
   return E2_OK;
 }
 
 // ------------------------------------------------------------------- op front-ends
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s) {
-  static const bool no_plane = getenv("E2_DISABLE_PLANE") != nullptr;   // A/B switch for profiling
   static const bool no_zstack = getenv("E2_DISABLE_ZSTACK") != nullptr;
   if (compute == E2_COMPUTE_TF32) {
     if (!no_zstack && e2_gather_gemm_tc_ok(h, g) && e2_conv_zstack_tc_ok(h, g)) return e2_launch_conv_zstack_tc(h, g, s);
-    if (!no_plane && e2_gather_gemm_tc_ok(h, g) && e2_conv_plane_tc_ok(h, g)) return e2_launch_conv_plane_tc(h, g, s);
     if (e2_gather_gemm_tc_ok(h, g)) return e2_launch_gather_gemm_tc(h, g, s);
   }
   return e2_launch_gather_gemm_ffma(h, g, s);
@@ -727,7 +725,7 @@ extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
       q->ws = dummy;                      // "a workspace will be supplied": lets the planners consider K splits
       if (e2_conv_zstack_tc_ok(&fake, *q))
         *bytes = std::max(*bytes, e2_conv_zstack_workspace_bytes(sm_count, *q));
-      else if (!e2_conv_plane_tc_ok(&fake, *q))
+      else
         *bytes = std::max(*bytes, e2_gather_gemm_tc_workspace_bytes(sm_count, *q));
     }
   }

@@ -68,15 +68,12 @@ bool e2_gather_gemm_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // scratch bytes the tap kernel wants for its split-K path (0: it will not split)
 size_t e2_gather_gemm_tc_workspace_bytes(int sm_count, const GatherGemm& g);
-// halo-reuse variant of the gather-GEMM (e2_conv_plane_tc.cu); preferred when it qualifies
-bool e2_conv_plane_tc_ok(const e2_handle* h, const GatherGemm& g);
-int e2_launch_conv_plane_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // halo planes + z-taps stacked along N (e2_conv_zstack_tc.cu); preferred over both when it qualifies
 bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // scratch bytes its split-K plan wants (0: no split); g.ws / g.ws_bytes carry the scratch at launch
 size_t e2_conv_zstack_workspace_bytes(int sm_count, const GatherGemm& g);
-// picks zstack / plane kernel / tap kernel / CUDA cores for a TF32 request
+// picks zstack / tap kernel / CUDA cores for a TF32 request
 int e2_dispatch_gather_gemm(e2_handle* h, const GatherGemm& g, int compute, cudaStream_t s);
 bool e2_reduce_gemm_tc_ok(const e2_handle* h, const ReduceGemm& g);
 // ws (nullable): per-CTA partial tiles + deterministic reduce kernel; without it fp32 atomics

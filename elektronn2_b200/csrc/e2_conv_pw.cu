@@ -150,7 +150,7 @@ int e2_launch_conv_pw_fwd(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
   const int groups = 256 / lpp;
   k_pw_fwd<<<e2_grid_1d((positions + groups - 1) / groups * 256, 256, h->sm_count, 16), 256, sizeof(float) * g.N * g.K, s>>>(
       g, positions, lpp);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_pw_fwd");
   return E2_OK;
 }
@@ -164,7 +164,7 @@ int e2_launch_conv_pw_dgrad(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
   const int64_t positions = (int64_t)g.On * g.Oz * g.Ox * g.Oy;
   const int Np = (g.N + 3) / 4 * 4;
   k_pw_dgrad<<<e2_grid_1d(positions * (Np / 4), 256, h->sm_count, 16), 256, sizeof(float) * g.K * Np, s>>>(g, positions);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_pw_dgrad");
   return E2_OK;
 }
@@ -182,7 +182,7 @@ int e2_launch_conv_pw_wgrad(e2_handle* h, const ReduceGemm& g, float* db, cudaSt
   int grid = (int)std::min<int64_t>((positions + plan - 1) / plan, (int64_t)h->sm_count * 4);
   if (grid < 1) grid = 1;
   k_pw_wgrad<<<grid, 256, 0, s>>>(g, positions, db);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_pw_wgrad");
   return E2_OK;
 }

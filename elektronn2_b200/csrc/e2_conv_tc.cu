@@ -491,11 +491,11 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   const int tiles_n = (g.N + bn - 1) / bn;
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n, (unsigned)ksplit);
   k_gather_gemm_tc<<<grid, NUM_THREADS, smem, s>>>(tmA, tmB, p);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "gather_gemm_tc");
   if (p.part) {
     k_gather_gemm_reduce<<<(unsigned)(tiles_m * tiles_n * (bn / 4)), BM, 0, s>>>(p, ksplit, tiles_m, tiles_n);
-    h->launches++;
+    e2_count_launch(h);
     E2_CUDA_CHECK(h, "gather_gemm_reduce");
   }
   return E2_OK;

@@ -722,7 +722,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     fprintf(stderr, "zstack trace (CTA 0, %d tiles): mma warp total %lld  wait acc_empty %lld  wait w_full %lld  issue %lld | epi0 total %lld wait acc_full %lld work %lld | epi4 total %lld wait %lld work %lld\n",
             tiles0, tr[0], tr[1], tr[2], tr[3], tr[8], tr[9], tr[10], tr[12], tr[13], tr[14]);
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "conv_zstack_tc");
   if (split) {
     const int64_t positions = (int64_t)g.On * g.Oz * g.Ox * g.Oy;
@@ -730,7 +730,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     k_zstack_reduce<<<e2_grid_1d(positions * (Np / 4), 256, h->sm_count, 16), 256, 0, s>>>(
         static_cast<const float*>(g.ws), p.ksplit, positions, Np, g.N, g.C, g.c_pitch, g.bias, g.gate,
         g.act, g.accumulate, g.round_tf32);
-    h->launches++;
+    e2_count_launch(h);
     E2_CUDA_CHECK(h, "zstack_reduce");
   }
   return E2_OK;

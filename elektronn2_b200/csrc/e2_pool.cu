@@ -319,7 +319,7 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
     const int rowlen = p.Yo * p.C;
     k_maxpool_fwd<1, 0, 0, 0><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "maxpool3d_fwd");
   return E2_OK;
 }
@@ -352,7 +352,7 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
     k_maxpool_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, x, dx,
                                                                                            relu_gate);
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "maxpool3d_bwd");
   return E2_OK;
 }
@@ -506,7 +506,7 @@ extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, co
     const int rowlen = p.Yo * p.C;
     k_mfp_fwd<1><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv(p.C, rowlen), x, bias, y, argmax);
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "mfp_fwd");
   return E2_OK;
 }
@@ -522,7 +522,7 @@ extern "C" int e2_mfp_bwd(e2_handle* h, const e2_mfp_desc* d, const float* dy, c
     k_mfp_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx);
   else
     k_mfp_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, dy, argmax, dx);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "mfp_bwd");
   return E2_OK;
 }
@@ -580,7 +580,7 @@ static int f2d_launch(e2_handle* h, const e2_f2d_desc* d, const float* src, cons
     if (v4) k_f2d<4, false><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
     else k_f2d<1, false><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, s>>>(p, src, offs, dst);
   }
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "frag2dense");
   return E2_OK;
 }
@@ -708,7 +708,7 @@ extern "C" int e2_crop_concat_fwd(e2_handle* h, const e2_crop_desc* d, const flo
     k_crop_fwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, src, dst);
   else
     k_crop_fwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, src, dst);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "crop_concat_fwd");
   return E2_OK;
 }
@@ -724,7 +724,7 @@ extern "C" int e2_crop_concat_bwd(e2_handle* h, const e2_crop_desc* d, const flo
     k_crop_bwd<4><<<e2_grid_1d(work / 4, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc, relu_gate);
   else
     k_crop_bwd<1><<<e2_grid_1d(work, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(p, ddst, dsrc, relu_gate);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "crop_concat_bwd");
   return E2_OK;
 }

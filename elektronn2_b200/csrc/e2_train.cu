@@ -75,7 +75,7 @@ extern "C" int e2_softmax_nll_fwd(e2_handle* h, const e2_tensor* t, const float*
   cudaMemsetAsync(out_scalars, 0, 4 * sizeof(float), s);
   int64_t P = e2_positions(t);
   k_softmax_nll_fwd<<<e2_grid_1d(P, 256, h->sm_count, 8), 256, 0, s>>>(x, target, probs, out_scalars, P, t->c, t->c_pitch);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "softmax_nll_fwd");
   return E2_OK;
 }
@@ -87,7 +87,7 @@ extern "C" int e2_softmax_nll_bwd(e2_handle* h, const e2_tensor* t, const float*
   k_softmax_nll_bwd<<<e2_grid_1d(P, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(probs, target, scalars,
                                                                                          grad_scale, dlogits, P, t->c,
                                                                                          t->c_pitch);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "softmax_nll_bwd");
   return E2_OK;
 }
@@ -114,7 +114,7 @@ extern "C" int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, fl
   double factor = sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)mom, (double)t));  // optimiser.py:304
   k_adam<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, lr, mom, beta2, wd,
                                                                                   apply_wd, (float)factor);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "adam_step");
   return E2_OK;
 }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
 extern "C" int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void* stream) {
   E2_REQUIRE(h, hyper && t_dev, "adam_prepare: null pointer");
   k_adam_prepare<<<1, 32, 0, (cudaStream_t)stream>>>(hyper, t_dev);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "adam_prepare");
   return E2_OK;
 }
@@ -158,7 +158,7 @@ extern "C" int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m
   E2_REQUIRE(h, p && g && m && s && hyper && count >= 0, "adam_step_dev: bad arguments");
   if (count == 0) return E2_OK;
   k_adam_dev<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, hyper, apply_wd);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "adam_step_dev");
   return E2_OK;
 }
@@ -179,7 +179,7 @@ extern "C" int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_d
   if (count == 0) return E2_OK;
   k_sgd<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, last_dir, count, lr, mom, wd,
                                                                                  apply_wd);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "sgd_step");
   return E2_OK;
 }

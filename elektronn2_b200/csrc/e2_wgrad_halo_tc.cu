@@ -554,7 +554,7 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t 
     return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
   dim3 grid((unsigned)units, (unsigned)splits);
   fn<<<grid, WH_THREADS, smem, s>>>(tmP, tmQ, p);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "wgrad_halo_tc");
   if (p.ws) {
     const int db_blocks = p.db_ws ? (p.n_rc * p.n_cols + 127) / 128 : 0;
@@ -566,12 +566,12 @@ int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t 
       const int dbb = p.db_ws ? (p.n_rc * p.n_cols + 128 * p.kz - 1) / (128 * p.kz) : 0;
       k_wgrad_halo_reduce_rows<<<(unsigned)(w_blocks + dbb), 128 * p.kz, (size_t)4 * 32 * T * sizeof(float), s>>>(
           p, units, splits, w_blocks);
-      h->launches++;
+      e2_count_launch(h);
       E2_CUDA_CHECK(h, "wgrad_halo_reduce_rows");
     } else {
       const int w_blocks = units * p.n_acc * (p.n_cols / 4);
       k_wgrad_halo_reduce<<<(unsigned)(w_blocks + db_blocks), 128, 0, s>>>(p, units, splits, w_blocks);
-      h->launches++;
+      e2_count_launch(h);
       E2_CUDA_CHECK(h, "wgrad_halo_reduce");
     }
   }

@@ -392,11 +392,11 @@ int e2_launch_reduce_gemm_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t
   }
   dim3 grid((unsigned)units, (unsigned)splits);
   k_wgrad_tc<<<grid, WG_THREADS, smem, s>>>(tmP, tmQ, p);
-  h->launches++;
+  e2_count_launch(h);
   E2_CUDA_CHECK(h, "wgrad_tc");
   if (p.part) {
     k_wgrad_tc_reduce<<<(unsigned)(units * p.gpc * (ncols / 4)), 128, 0, s>>>(p, splits, units);
-    h->launches++;
+    e2_count_launch(h);
     E2_CUDA_CHECK(h, "wgrad_tc_reduce");
   }
   return E2_OK;

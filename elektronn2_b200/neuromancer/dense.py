@@ -62,6 +62,9 @@ class _TileRunner(object):
         self.node = node
         inp = node.input_nodes[0]
         b = inp.shape['b'] or 1
+        if int(b) != 1:
+            # the reference feeds raw_img[None] (node_basic.py:825): one tile per call
+            raise ValueError("predict_dense needs an input node with batch size 1 or None (got %d)" % int(b))
         self.plan = node._plans.get(int(b)) or Plan(node.model, [node], b)
         node._plans[int(b)] = self.plan
         self.h = self.plan.h

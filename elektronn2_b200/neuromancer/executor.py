@@ -75,6 +75,15 @@ class ParamStore(object):
     def __init__(self, named_params, device):
         # reverse graph order inside each region; weights (regularised) first, then the rest
         plist = list(named_params)[::-1]
+        seen = {}
+        for k, p in plist:
+            if id(p) in seen:
+                # the reference shares weights by passing one VariableParam to several nodes; the flat buffer gives
+                # every entry its own region and each wgrad kernel OVERWRITES its gradient view, so a shared
+                # parameter would silently lose contributions
+                raise NotImplementedError("parameter %s is shared by '%s' and '%s': shared parameters are not "
+                                          "supported on the B200 path" % (p.name, seen[id(p)], k))
+            seen[id(p)] = k
         reg = [(k, p) for k, p in plist if p.apply_reg]
         noreg = [(k, p) for k, p in plist if not p.apply_reg]
         self.entries = []  # (key, param, offset, size)
@@ -900,9 +909,23 @@ class Plan(object):
                     self._mark_inputs_free()
                     return
             self._graph.replay()
+            if dp is not None:
+                # a replay runs the captured collectives without going through finish_step(): tell the simple
+                # all-reduce (non-fused optimisers call it after execute()) that this step is already summed
+                dp._step_reduced = True
         else:
             body()
         self._mark_inputs_free()
+
+    def release_graphs(self):
+        """Drop every captured CUDA graph of this plan (they hold references to streams, scratch buffers and -- with
+        data parallelism -- the NCCL communicator).  Called before an orderly process teardown; the next step
+        re-captures."""
+        torch.cuda.synchronize(self.device)
+        self._opt_graphs.clear()
+        self._graph = None
+        self._pack_graph = None
+        gc.collect()
 
     def _mark_inputs_free(self):
         if self._inputs_free is None:

@@ -14,6 +14,20 @@ from . import ops, shapes, loss as oloss
 F64 = np.float64
 
 
+def rna_tf32(v):
+    """float64 -> float32 (nearest even) -> tf32 with ``cvt.rna`` (nearest, ties away from zero), in a float64
+    container: what a TF32-mode kernel of libe2b200 stores (csrc/e2_common.cuh e2_round_tf32)."""
+    a = np.ascontiguousarray(np.asarray(v, np.float32)).view(np.uint32)
+    return ((a + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32).astype(F64)
+
+
+def trunc_tf32(v):
+    """What ``tcgen05.mma.kind::tf32`` does to an fp32 operand that was not rounded by its producer: the low 13
+    mantissa bits are ignored."""
+    a = np.ascontiguousarray(np.asarray(v, np.float32)).view(np.uint32)
+    return (a & np.uint32(0xFFFFE000)).view(np.float32).astype(F64)
+
+
 def glorot_normal(w_sh, pool, rng):
     """initweights(scale='glorot', mode='normal') for conv weights
     (variables.py:219-240): std = sqrt(2 / ((n_in + n_out/prod(pool)) * prod(k)))."""
@@ -43,6 +57,24 @@ class Net(object):
     def __init__(self, seed=2):
         self.nodes = []
         self.rng = np.random.RandomState(seed)
+        # tf32=True: emulate the operand roundings of libe2b200's TF32 mode (tests pin "the end-to-end tf32
+        # deviation is the network's conditioning, not kernel error"): stored activations / gradients are
+        # rounded with cvt.rna by their producer, packed weights likewise, tensor-core operands that were not
+        # rounded by their producer (sums of two gradient contributions) are truncated by the MMA; the
+        # CUDA-core kernels (F_in == 1 wgrad, 1x1x1 layers with <= 4 outputs) multiply exact fp32 values.
+        self.tf32 = False
+
+    def _q(self, v):
+        return rna_tf32(v) if self.tf32 else v
+
+    def _use(self, v, exact=False):
+        return trunc_tf32(v) if (self.tf32 and not exact) else v
+
+    @staticmethod
+    def _cuda_core_layer(n):
+        """Layers libe2b200 runs on CUDA cores in fp32 even in TF32 mode (csrc/e2_conv_pw.cu)."""
+        w = n.params['w']
+        return n.op == 'conv' and tuple(w.shape[2:]) == (1, 1, 1) and w.shape[0] <= 4
 
     # -- node constructors ---------------------------------------------------
     def input(self, shape, name='raw'):
@@ -126,6 +158,26 @@ class Net(object):
             p = [self.val[q] for q in n.parents]
             if n.op == 'input':
                 v = np.asarray(x, F64)
+            elif n.op == 'conv' and self.tf32:
+                w = n.params['w']
+                xin = p[0]
+                if w.shape[1] == 1:
+                    # first layer: the tcgen05 kernel (>= 16 taps) rounds its input halo, the CUDA-core one does not
+                    xin = rna_tf32(xin) if int(np.prod(w.shape[2:])) >= 16 else np.asarray(xin, np.float32).astype(F64)
+                else:
+                    xin = self._use(xin, self._cuda_core_layer(n))
+                lin = (ops.conv3d_dot if tuple(w.shape[2:]) == (1, 1, 1) else ops.conv3d)(xin, rna_tf32(w))
+                if n.kw['mfp'] or any(q > 1 for q in n.kw['pool']):
+                    lin = rna_tf32(lin)            # the conv kernel stores the raw accumulators rounded, the pool kernel
+                    if n.kw['mfp']:                # applies max -> +bias -> act and rounds again
+                        pooled = ops.fragmentpool(lin, n.kw['pool'], n.parents[0].sh.mfp_offsets, n.parents[0].sh.strides)[0]
+                    else:
+                        pooled = ops.pooling(lin, n.kw['pool'])
+                else:
+                    pooled = lin
+                pre = pooled + np.asarray(n.params['b'], F64).reshape(1, -1, 1, 1, 1)
+                v = rna_tf32(ops.activation(pre, n.kw['act']))
+                self.aux[n] = (lin, pre)
             elif n.op == 'conv':
                 v, (lin, pre), _ = ops.conv_node_fwd(p[0], n.params['w'], n.params['b'], n.kw['pool'],
                                                      n.kw['act'], n.kw['mfp'], n.parents[0].sh.mfp_offsets,
@@ -134,7 +186,9 @@ class Net(object):
             elif n.op == 'pool':
                 v = ops.pooling(p[0], n.kw['pool'])
             elif n.op == 'upconv':
-                v, pre = ops.upconv_node_fwd(p[0], n.params['w'], n.params['b'], n.kw['pool'], n.kw['act'])
+                v, pre = ops.upconv_node_fwd(self._use(p[0]), self._q(n.params['w']), n.params['b'], n.kw['pool'],
+                                             n.kw['act'])
+                v = self._q(v)
                 self.aux[n] = pre
             elif n.op == 'crop':
                 v = ops.crop(p[0], n.kw['crop'])
@@ -171,16 +225,19 @@ class Net(object):
                     dlin = ops.pooling_bwd(dpre, lin, n.kw['pool'], tie_mode)
                 else:
                     dlin = dpre
-                grads[(n, 'w')] = ops.conv3d_wgrad(dlin, xin, n.params['w'].shape)
+                exact = self._cuda_core_layer(n) or n.params['w'].shape[1] == 1
+                grads[(n, 'w')] = ops.conv3d_wgrad(self._use(dlin, exact), self._use(xin, exact), n.params['w'].shape)
                 if par[0].op != 'input':
-                    self._acc(g, par[0], ops.conv3d_dgrad(dlin, n.params['w'], xin.shape))
+                    self._acc(g, par[0], ops.conv3d_dgrad(self._use(dlin, self._cuda_core_layer(n)),
+                                                          self._q(n.params['w']), xin.shape), rounded=True)
             elif n.op == 'pool':
                 self._acc(g, par[0], ops.pooling_bwd(dy, self.val[par[0]], n.kw['pool'], tie_mode))
             elif n.op == 'upconv':
                 dpre = ops.activation_bwd(dy, self.aux[n], n.kw['act'])
                 grads[(n, 'b')] = ops.bias_grad(dpre)
-                grads[(n, 'w')] = ops.upconv3d_wgrad(dpre, self.val[par[0]], n.kw['pool'])
-                self._acc(g, par[0], ops.upconv3d_dgrad(dpre, n.params['w'], n.kw['pool']))
+                grads[(n, 'w')] = ops.upconv3d_wgrad(self._use(dpre), self._use(self.val[par[0]]), n.kw['pool'])
+                self._acc(g, par[0], ops.upconv3d_dgrad(self._use(dpre), self._q(n.params['w']), n.kw['pool']),
+                          rounded=True)
             elif n.op == 'crop':
                 self._acc(g, par[0], ops.crop_bwd(dy, n.kw['crop'], self.val[par[0]].shape))
             elif n.op == 'concat':
@@ -192,9 +249,11 @@ class Net(object):
                 self._acc(g, par[0], ops.fragments2dense_bwd(dy, par[0].sh.mfp_offsets, par[0].sh.strides))
         return loss, grads, probs, g
 
-    @staticmethod
-    def _acc(g, node, val):
-        g[node] = val if node not in g else g[node] + val
+    def _acc(self, g, node, val, rounded=False):
+        """``rounded``: the contribution comes from a dgrad kernel, whose epilogue rounds (accumulated sum included)
+        in TF32 mode; pool / crop / concat backward kernels add without rounding."""
+        v = val if node not in g else g[node] + val
+        g[node] = self._q(v) if rounded else v
 
 
 # ---------------------------------------------------------------- the four configs

@@ -16,7 +16,7 @@ FAMILY = [
     ('k_wgrad_halo_tc', 'conv_wgrad'), ('k_wgrad_halo_reduce', 'conv_wgrad'), ('k_c1_wgrad', 'conv_wgrad'),
     ('k_reduce_gemm', 'conv_wgrad'),
     ('k_wgrad_tc_reduce', 'upconv_wgrad'), ('k_wgrad_tc', 'upconv_wgrad'), ('k_bias_grad', 'upconv_wgrad'),
-    ('k_conv_zstack_tc', 'conv_fwd+dgrad'), ('k_zstack_reduce', 'conv_fwd+dgrad'), ('k_conv_plane_tc', 'conv_fwd+dgrad'),
+    ('k_conv_zstack_tc', 'conv_fwd+dgrad'), ('k_zstack_reduce', 'conv_fwd+dgrad'),
     ('k_c1_fwd', 'conv_fwd+dgrad'), ('k_gather_gemm_tc', 'conv/upconv tap kernel'), ('k_gather_gemm_reduce', 'conv/upconv tap kernel'),
     ('k_gather_gemm', 'conv_fwd+dgrad'),
     ('k_maxpool_fwd', 'pool_fwd'), ('k_maxpool_bwd', 'pool_bwd'), ('k_crop_fwd', 'crop_concat_fwd'), ('k_crop_bwd', 'crop_concat_bwd'),
