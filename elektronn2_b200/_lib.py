@@ -18,7 +18,8 @@ lib = C.CDLL(LIB_PATH)
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4
 ACT = {'lin': 0, 'linear': 0, 'relu': 1, 'tanh': 2, 'sig': 3, 'sigmoid': 3, 'logistic': 3, 'abs': 4, 'soft+': 5, 'elu': 6,
-       'selu': 7}
+       'selu': 7, 'prelu': 8}
+POOL_MODE = {'max': 0, 'average': 1, 'average_inc_pad': 1, 'average_exc_pad': 1, 'sum': 2}
 COMPUTE = {'f32': 0, 'tf32': 1, 'bf16': 2}
 TIE = {'first': 0, 'all': 1}
 
@@ -70,12 +71,17 @@ class UpConvDesc(C.Structure):
 
 class PoolDesc(C.Structure):
     _fields_ = [('x', Tensor), ('y', Tensor), ('pz', i32), ('px', i32), ('py', i32), ('act', i32),
-                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32), ('round_tf32', i32), ('gate_pooled', i32)]
+                ('has_bias', i32), ('tie_mode', i32), ('accumulate', i32), ('round_tf32', i32), ('gate_pooled', i32),
+                ('mode', i32)]
 
 
 class MfpDesc(C.Structure):
     _fields_ = [('x', Tensor), ('y', Tensor), ('pz', i32), ('px', i32), ('py', i32), ('act', i32),
                 ('has_bias', i32), ('round_tf32', i32)]
+
+
+class AffineDesc(C.Structure):
+    _fields_ = [('t', Tensor), ('act', i32), ('batch_stats', i32), ('round_tf32', i32), ('param_stride', i32)]
 
 
 class F2DDesc(C.Structure):
@@ -125,10 +131,17 @@ SIGNATURES = {
     'e2_crop_concat_bwd': (C.c_int, [vp, P(CropDesc), vp, vp, vp, vp]),
     'e2_softmax_nll_fwd': (C.c_int, [vp, P(Tensor), vp, vp, vp, vp, vp]),
     'e2_softmax_nll_bwd': (C.c_int, [vp, P(Tensor), vp, vp, vp, C.c_float, vp, vp]),
-    'e2_adam_step': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i32, i32, vp]),
-    'e2_sgd_step': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, i32, vp]),
+    'e2_adam_step': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp]),
+    'e2_sgd_step': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     'e2_adam_prepare': (C.c_int, [vp, vp, vp, vp]),
-    'e2_adam_step_dev': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, i32, vp]),
+    'e2_adam_step_dev': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, C.c_float, vp]),
+    'e2_bn_batch_stats': (C.c_int, [vp, P(Tensor), vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp]),
+    'e2_bn_fold': (C.c_int, [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'e2_affine_act_fwd': (C.c_int, [vp, P(AffineDesc), vp, vp, vp, vp, vp, vp]),
+    'e2_affine_act_bwd': (C.c_int, [vp, P(AffineDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'e2_affine_scratch_bytes': (C.c_int, [i32, P(sz)]),
+    'e2_maxout_fwd': (C.c_int, [vp, vp, vp, C.c_int64, i32, C.c_int64, i32, vp]),
+    'e2_maxout_bwd': (C.c_int, [vp, vp, vp, vp, C.c_int64, i32, C.c_int64, i32, vp]),
     'e2_debug_zstack_plan': (C.c_int, [C.c_int] * 10 + [P(C.c_int)]),
 }
 

@@ -92,5 +92,9 @@ __device__ __forceinline__ float e2_round_tf32(float v) {
   return __uint_as_float(r);
 }
 
+// average / sum pooling (e2_epilogue.cu), reached through e2_maxpool3d_fwd / _bwd with d->mode != E2_POOL_MAX
+int e2_launch_avgpool_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, float* y, cudaStream_t s);
+int e2_launch_avgpool_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, float* dx, cudaStream_t s);
+
 // internal launchers shared between translation units
 int e2_conv_tc_supported(const e2_handle* h, int c_in, int c_out, int c_in_pitch, int c_out_pitch);

@@ -301,6 +301,11 @@ extern "C" int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float
   int rc = fill_pool(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, x && y && (!d->has_bias || bias), "maxpool3d_fwd: null pointer");
+  if (d->mode != E2_POOL_MAX) {
+    E2_REQUIRE(h, d->mode == E2_POOL_AVERAGE || d->mode == E2_POOL_SUM, "pool3d_fwd: unknown mode %d", d->mode);
+    E2_REQUIRE(h, !d->has_bias && d->act == E2_ACT_LIN && !argmax, "pool3d_fwd: average / sum pooling has no fused epilogue or argmax");
+    return e2_launch_avgpool_fwd(h, d, x, y, (cudaStream_t)stream);
+  }
   const int64_t rows = (int64_t)p.n * p.Zo * p.Xo;
   E2_REQUIRE(h, rows < (1ll << 31), "maxpool3d_fwd: too many rows");
   if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
@@ -330,6 +335,11 @@ extern "C" int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float
   int rc = fill_pool(h, d, &p);
   if (rc) return rc;
   E2_REQUIRE(h, dy && dx, "maxpool3d_bwd: null pointer");
+  if (d->mode != E2_POOL_MAX) {
+    E2_REQUIRE(h, d->mode == E2_POOL_AVERAGE || d->mode == E2_POOL_SUM, "pool3d_bwd: unknown mode %d", d->mode);
+    E2_REQUIRE(h, !relu_gate, "pool3d_bwd: average / sum pooling takes no ReLU gate");
+    return e2_launch_avgpool_bwd(h, d, dy, dx, (cudaStream_t)stream);
+  }
   E2_REQUIRE(h, d->tie_mode == E2_TIE_FIRST ? argmax != nullptr : x != nullptr,
              "maxpool3d_bwd: tie_mode FIRST needs argmax, tie_mode ALL needs x");
   E2_REQUIRE(h, !d->gate_pooled || (d->tie_mode == E2_TIE_FIRST && !d->has_bias && d->act == E2_ACT_LIN),

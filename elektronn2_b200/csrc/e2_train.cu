@@ -95,25 +95,25 @@ extern "C" int e2_softmax_nll_bwd(e2_handle* h, const e2_tensor* t, const float*
 // ------------------------------------------------------------------------ optimisers
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                               float* __restrict__ s, int64_t n, float lr, float mom, float beta2, float wd,
-                                              int apply_wd, float factor) {
+                                              float wd_mult, float factor) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
     float nm = mom * m[i] + (1.0f - mom) * gi;             // optimiser.py:306
     float ns = beta2 * s[i] + (1.0f - beta2) * gi * gi;    // :307
     float dir = factor * nm / sqrtf(ns + 1e-5f);           // :309, epsilon inside the sqrt (:283)
     float pi = p[i];
-    pi = apply_wd ? pi - lr * (dir + wd * pi) : pi - lr * dir;  // :310-319
+    pi = wd_mult != 0.f ? pi - lr * (dir + wd * wd_mult * pi) : pi - lr * dir;  // :310-319
     m[i] = nm, s[i] = ns, p[i] = pi;
   }
 }
 
 extern "C" int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, float lr,
-                            float mom, float beta2, float wd, int32_t apply_wd, int32_t t, void* stream) {
+                            float mom, float beta2, float wd, float wd_mult, int32_t t, void* stream) {
   E2_REQUIRE(h, p && g && m && s && count >= 0 && t >= 1, "adam_step: bad arguments");
   if (count == 0) return E2_OK;
   double factor = sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)mom, (double)t));  // optimiser.py:304
   k_adam<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, lr, mom, beta2, wd,
-                                                                                  apply_wd, (float)factor);
+                                                                                  wd_mult, (float)factor);
   e2_count_launch(h);
   E2_CUDA_CHECK(h, "adam_step");
   return E2_OK;
@@ -132,7 +132,7 @@ __global__ void k_adam_prepare(float* __restrict__ hyper, int* __restrict__ t_de
 
 __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                   float* __restrict__ s, int64_t n, const float* __restrict__ hyper,
-                                                  int apply_wd) {
+                                                  float wd_mult) {
   const float lr = hyper[0], mom = hyper[1], beta2 = hyper[2], wd = hyper[3], factor = hyper[4];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
     float ns = beta2 * s[i] + (1.0f - beta2) * gi * gi;
     float dir = factor * nm / sqrtf(ns + 1e-5f);
     float pi = p[i];
-    pi = apply_wd ? pi - lr * (dir + wd * pi) : pi - lr * dir;
+    pi = wd_mult != 0.f ? pi - lr * (dir + wd * wd_mult * pi) : pi - lr * dir;
     m[i] = nm, s[i] = ns, p[i] = pi;
   }
 }
@@ -154,31 +154,31 @@ extern "C" int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void*
 }
 
 extern "C" int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count,
-                                const float* hyper, int32_t apply_wd, void* stream) {
+                                const float* hyper, float wd_mult, void* stream) {
   E2_REQUIRE(h, p && g && m && s && hyper && count >= 0, "adam_step_dev: bad arguments");
   if (count == 0) return E2_OK;
-  k_adam_dev<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, hyper, apply_wd);
+  k_adam_dev<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, s, count, hyper, wd_mult);
   e2_count_launch(h);
   E2_CUDA_CHECK(h, "adam_step_dev");
   return E2_OK;
 }
 
 __global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ d,
-                                             int64_t n, float lr, float mom, float wd, int apply_wd) {
+                                             int64_t n, float lr, float mom, float wd, float wd_mult) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float nd = g[i] + mom * d[i];  // optimiser.py:148
     float pi = p[i];
-    pi = apply_wd ? pi - lr * (nd + wd * pi) : pi - lr * nd;
+    pi = wd_mult != 0.f ? pi - lr * (nd + wd * wd_mult * pi) : pi - lr * nd;
     d[i] = nd, p[i] = pi;
   }
 }
 
 extern "C" int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom,
-                           float wd, int32_t apply_wd, void* stream) {
+                           float wd, float wd_mult, void* stream) {
   E2_REQUIRE(h, p && g && last_dir && count >= 0, "sgd_step: bad arguments");
   if (count == 0) return E2_OK;
   k_sgd<<<e2_grid_1d(count, 256, h->sm_count, 8), 256, 0, (cudaStream_t)stream>>>(p, g, last_dir, count, lr, mom, wd,
-                                                                                 apply_wd);
+                                                                                 wd_mult);
   e2_count_launch(h);
   E2_CUDA_CHECK(h, "sgd_step");
   return E2_OK;

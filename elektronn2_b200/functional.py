@@ -109,12 +109,80 @@ def upconv3d_grad_weights(x, dy, w_shape, pool, compute='tf32'):
     return dw.cpu().numpy()
 
 
-def _pool_op(x, pool, tie_mode='first'):
+def _pool_op(x, pool, tie_mode='first', mode='max'):
     h = _lib.get_handle()
     pool = tuple(int(p) for p in pool)
     xd = DevTensor.from_numpy(x, h)
     yd = DevTensor(x.shape[0], x.shape[2] // pool[0], x.shape[3] // pool[1], x.shape[4] // pool[2], x.shape[1])
-    return h, PoolOp(h, xd, yd, pool, tie_mode=tie_mode), xd, yd
+    return h, PoolOp(h, xd, yd, pool, tie_mode=tie_mode, mode=mode), xd, yd
+
+
+def pool3d(x, pool, mode='average_inc_pad'):
+    """computations.pooling with dnn_pool's other modes (computations.py:556-561, 589-590, 600):
+    'average_inc_pad' / 'average_exc_pad' (identical without padding) and 'sum'; stride == pool."""
+    x = _f32(x)
+    h, op, xd, yd = _pool_op(x, pool, mode=mode)
+    op.fwd()
+    return yd.numpy(h)
+
+
+def pool3d_grad(x_shape, dy, pool, mode='average_inc_pad'):
+    dy = _f32(dy)
+    h, op, xd, yd = _pool_op(np.zeros(tuple(int(v) for v in x_shape), np.float32), pool, mode=mode)
+    dyd = DevTensor.from_numpy(dy, h)
+    dxd = xd.like()
+    op.bwd(dyd, dxd)
+    return dxd.numpy(h)
+
+
+def maxout(x, factor=2, axis=1):
+    """computations.maxout (computations.py:455-495): max over groups of ``factor`` consecutive entries of ``axis``."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    factor, axis = int(factor), int(axis)
+    if x.shape[axis] % factor:
+        raise ValueError("maxout: axis %d of length %d is not divisible by %d" % (axis, x.shape[axis], factor))
+    h = _lib.get_handle()
+    outer = int(np.prod(x.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(x.shape[axis + 1:], dtype=np.int64))
+    fo = x.shape[axis] // factor
+    xd = _t(x)
+    yd = torch.empty(x.shape[:axis] + (fo,) + x.shape[axis + 1:], dtype=torch.float32, device='cuda')
+    h.call('e2_maxout_fwd', _lib.ptr(xd), _lib.ptr(yd), outer, fo, inner, factor, h.stream())
+    return yd.cpu().numpy()
+
+
+def maxout_grad(x, dy, factor=2, axis=1):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    dy = np.ascontiguousarray(dy, dtype=np.float32)
+    factor, axis = int(factor), int(axis)
+    h = _lib.get_handle()
+    outer = int(np.prod(x.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(x.shape[axis + 1:], dtype=np.int64))
+    fo = x.shape[axis] // factor
+    xd, dyd = _t(x), _t(dy)
+    dxd = torch.empty_like(xd)
+    h.call('e2_maxout_bwd', _lib.ptr(xd), _lib.ptr(dyd), _lib.ptr(dxd), outer, fo, inner, factor, h.stream())
+    return dxd.cpu().numpy()
+
+
+def affine_act(v, act='lin', b=None, gamma=None, mean=None, std=None, alpha=None):
+    """y = act((gamma / std) * v + b - gamma * mean / std) (neural.py:711-712) on a (b,f,z,x,y) array; 'prelu' takes
+    its slope in ``alpha`` (= b[:,1] of the reference's (f,2) bias, neural.py:655-657)."""
+    from .ops import AffineActOp
+    v = _f32(v)
+    h = _lib.get_handle()
+    vd = DevTensor.from_numpy(v, h)
+    yd = vd.like()
+    c = v.shape[1]
+    bb = np.zeros(c, np.float32) if b is None else np.asarray(b, np.float32)
+    if act == 'prelu':
+        bb = np.stack([bb, np.asarray(alpha, np.float32)], 1)
+    bn = 'predict' if (gamma is not None or mean is not None or std is not None) else False
+    one, zero = np.ones(c, np.float32), np.zeros(c, np.float32)
+    op = AffineActOp(h, vd, yd, act, _t(bb), bn, _t(one if gamma is None else gamma) if bn else None,
+                     _t(zero if mean is None else mean) if bn else None, _t(one if std is None else std) if bn else None)
+    op.fwd()
+    return yd.numpy(h)
 
 
 def maxpool3d(x, pool, return_argmax=False):

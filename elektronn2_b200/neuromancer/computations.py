@@ -5,8 +5,10 @@ signatures, argument meaning and error behaviour, evaluated eagerly on the B200 
 equivalent of the seam -- what ``config.backend == 'b200'`` dispatches to inside an existing install,
 and what the parity tests read like.
 
-Only what the BASELINE configs use is on the B200 path: 3-D, ``axis_order='dnn'`` (tags ``b,f,z,x,y``), ``'valid'``
-borders, stride 1 convs, ``pool == stride`` max-pooling.  Everything else raises the reference's own exception type.
+On the B200 path: 1-D / 2-D / 3-D (``axis_order='dnn'``, tags ``b,f[,z],x[,y]``; the lower-dimensional forms,
+computations.py:337-362, run as 3-D with leading unit axes), ``'valid'`` borders, stride 1 convs, ``pool == stride``
+pooling in every dnn_pool mode, ``apply_activation`` and ``maxout``.  Everything else raises the reference's own
+exception type.
 """
 from itertools import product
 
@@ -31,12 +33,20 @@ def conv(x, w, axis_order=None, conv_dim=None, x_shape=None, w_shape=None, borde
                              "filter, but got%id" % (conv_dim, x.ndim, x.ndim, w.ndim))
         if conv_dim > 3:
             raise ValueError("Input tensor dim to big. No conv for dim>5.")       # :327
-    if conv_dim != 3 or axis_order not in ('dnn', None):
-        raise NotImplementedError("b200 backend: 3-D convolution in 'dnn' axis order (b,f,z,x,y) only")
+    if axis_order not in ('dnn', None):
+        raise NotImplementedError("b200 backend: 'dnn' axis order (b,f,z,x,y) only")
     if stride is not None and not np.all(np.equal(stride, 1)):
-        raise NotImplementedError("Cannot use strided conv with 3d conv")         # :375-376
+        if conv_dim == 3:
+            raise NotImplementedError("Cannot use strided conv with 3d conv")     # :375-376
+        raise NotImplementedError("b200 backend: strided 1-D / 2-D convolution is not on the path")
     if border_mode != 'valid':
         raise NotImplementedError("b200 backend: border_mode 'valid' only (no BASELINE config uses another)")
+    if conv_dim < 3:
+        # 1-D (:337-349, conv2d on an added axis) and 2-D (:351-362): the same true convolution with kz (= kx) = 1
+        lead = (1,) * (3 - conv_dim)
+        y = F.conv3d(x.reshape(x.shape[:2] + lead + x.shape[2:]), w.reshape(w.shape[:2] + lead + w.shape[2:]),
+                     compute=config.compute)
+        return y.reshape(y.shape[:2] + y.shape[2 + len(lead):])
     return F.conv3d(x, w, compute=config.compute)
 
 
@@ -63,13 +73,49 @@ def pooling(x, pool, spatial_axes, mode='max', stride=None):
     x = np.asarray(x)
     if stride is not None and tuple(stride) != pool:
         raise NotImplementedError("pool != stride is not implemented for 3d")     # :612-613
-    if len(pool) != 3 or list(spatial_axes) != [2, 3, 4]:
-        raise NotImplementedError("b200 backend: 3-D pooling over axes (2,3,4) only")
-    if mode != 'max':
-        raise NotImplementedError("b200 backend: pooling mode 'max' only (the BASELINE configs' mode)")
-    if any(x.shape[2 + i] % pool[i] for i in range(3)):
+    nd = len(pool)
+    if nd not in (1, 2, 3):
+        raise NotImplementedError("Only 1/2/3-dim maxpooling with this function.")   # :646-647
+    if list(spatial_axes) != list(range(2, 2 + nd)):
+        if nd == 3:
+            raise ValueError("Axis order not recognised, must be [2,3,4] (dnn) or [1,3,4] (theano).")   # :596-597
+        raise NotImplementedError("Can only pool on last axes %s, this input has spatial axes %s"
+                                  % (list(range(2, 2 + nd)), list(spatial_axes)))     # :634-635
+    if mode == 'average':
+        mode = 'average_inc_pad'                                                  # :591-592
+    if mode not in ('max', 'average_inc_pad', 'average_exc_pad', 'sum'):
+        raise ValueError("unknown pooling mode %r" % (mode,))
+    if any(x.shape[2 + i] % pool[i] for i in range(nd)):
         raise ValueError("Cannot pool %s by %s: the spatial axes must be divisible" % (x.shape[2:], pool))
-    return F.maxpool3d(x, pool)
+    lead = (1,) * (3 - nd)
+    x5 = x.reshape(x.shape[:2] + lead + x.shape[2:])
+    y = F.maxpool3d(x5, lead + pool) if mode == 'max' else F.pool3d(x5, lead + pool, mode)
+    return y.reshape(y.shape[:2] + y.shape[2 + len(lead):])
+
+
+def maxout(x, factor=2, axis=None):
+    """computations.maxout (computations.py:455-495).  ``axis=None`` follows the reference literally: its default
+    expression ``2 if x.ndim==5 else 2`` (:476-477) selects axis 2 for every input."""
+    x = np.asarray(x)
+    if axis is None:
+        axis = 2
+    if axis not in [1, 2]:
+        raise ValueError("Maxout only permitted on axis 1 or 2")                  # :479-480
+    return F.maxout(x, factor, axis)
+
+
+def apply_activation(x, activation_func, b1=None):
+    """computations.apply_activation (computations.py:57-134) on a (b,f,z,x,y) array; ``b1``: prelu slope per feature."""
+    x = np.asarray(x)
+    if isinstance(activation_func, str) and activation_func.startswith('maxout'):
+        import re
+        return maxout(x, factor=int(re.findall(r'\d+', activation_func)[0]))
+    from .._lib import ACT
+    if activation_func not in ACT:
+        raise NotImplementedError("%s. Permitted activation_funcs :%s" % (activation_func, sorted(ACT)))   # :125-128
+    if activation_func == 'prelu' and b1 is None:
+        raise ValueError("prelu needs the slope parameter b1")
+    return F.affine_act(x, activation_func, alpha=np.asarray(b1, np.float32).reshape(-1) if b1 is not None else None)
 
 
 def fragmentpool(conv_out, pool, offsets, strides, spatial_axes, mode='max'):

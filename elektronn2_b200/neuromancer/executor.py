@@ -84,17 +84,34 @@ class ParamStore(object):
                 raise NotImplementedError("parameter %s is shared by '%s' and '%s': shared parameters are not "
                                           "supported on the B200 path" % (p.name, seen[id(p)], k))
             seen[id(p)] = k
-        reg = [(k, p) for k, p in plist if p.apply_reg]
-        noreg = [(k, p) for k, p in plist if not p.apply_reg]
+        # grouped by weight-decay multiplier (VariableParam.apply_reg: False/0, True/1, or a factor > 1 such as the
+        # 3.0 of batch-norm gammas, neural.py:213; optimiser.py:150-153, 312-315): the plain weights first -- that
+        # region [0, n_reg) is what the backward pass completes front to back and the all-reduce buckets cover --
+        # then any other multipliers, then the unregularised rest (biases)
+        def mult(p):
+            r = p.apply_reg
+            if isinstance(r, (bool, np.bool_)):
+                return 1.0 if r else 0.0
+            r = float(r)
+            if r < 0 or (0 < r < 1):
+                raise ValueError("parameter %s: apply_reg=%r is neither a flag nor a multiplier >= 1" % (p.name, p.apply_reg))
+            return r
+        mults = sorted({mult(p) for _, p in plist} - {0.0, 1.0})
+        groups = [(m, [(k, p) for k, p in plist if mult(p) == m]) for m in [1.0] + mults + [0.0]]
         self.entries = []  # (key, param, offset, size)
+        self.regions = []  # (offset, count, weight-decay multiplier)
         off = 0
-        for group in (reg, noreg):
+        self.n_reg = 0
+        for m, group in groups:
+            start = off
             for k, p in group:
                 size = int(np.prod(p.shape))
                 self.entries.append((k, p, off, size))
                 off += (size + 3) // 4 * 4
-            if group is reg:
+            if m == 1.0:
                 self.n_reg = off
+            if off > start:
+                self.regions.append((start, off - start, m))
         self.total = off
         self.device = device
         self.P = torch.zeros(self.total, dtype=torch.float32, device=device)
@@ -130,6 +147,22 @@ def _nel(t):
     return t.desc.positions * t.desc.c
 
 
+def _sp3(v, fill=1):
+    """Spatial tuple of a 1-D / 2-D node as the 3-D (z,x,y) the library works on: leading unit axes
+    (computations.py:337-362 are the kz == 1 / kz == kx == 1 special cases of the 3-D op)."""
+    v = [int(a) for a in v]
+    return [fill] * (3 - len(v)) + v
+
+
+def _aux_dev(p, device):
+    """Device copy of a parameter that is not part of the trainable flat buffer (batch-norm mean / std, 'predict'
+    gamma).  It lives on the parameter, so every plan of the model (training, prediction) sees the same values and
+    get_value() / set_value() go through it."""
+    if p._dev is None:
+        p._dev = torch.from_numpy(np.ascontiguousarray(p._host, dtype=np.float32)).to(device)
+    return p._dev
+
+
 def _nb(node, batch):
     b = node.shape['b']
     return int(batch) if b is None else int(b)
@@ -162,9 +195,11 @@ class Plan(object):
         self.val, self.aux = {}, {}
         self.fwd_ops, self.bwd_ops, self.pack_ops = [], [], []
         self.conv_ops = {}
+        self.bn_ops = []      # batch-norm 'train' epilogues: running averages move only inside an optimiser step
         self.loss_op = None
         self.inputs = {}
         self._graph = None
+        self._graph_upd = None
         self._pack_stream = None
         self._stage_in, self._pending, self._fed = {}, {}, False
         self._opt_stream = None
@@ -194,7 +229,7 @@ class Plan(object):
         return [c for c in n.children.values() if id(c) in self._in_plan]
 
     def _new(self, node, c=None):
-        sp = node.shape.spatial_shape
+        sp = _sp3(node.shape.spatial_shape)
         return DevTensor(_nb(node, self.batch), sp[0], sp[1], sp[2], node.shape['f'] if c is None else c,
                          device=self.device)
 
@@ -243,20 +278,28 @@ class Plan(object):
                 x = self.val[n.parent]
                 y = self.val[n] if n in self.val else self._new(n)
                 self.val[n] = y
-                op = ops.UpConvOp(h, x, y, self._pdev(n.w), self._pdev(n.b), n.pool_shape, n.activation_func,
-                                  self.compute)
+                fl = 2.0 * _nel(x) * n.n_f * int(np.prod(n.pool_shape))
+                kind = 'tensor' if _tensor_shaped(x.desc.c, n.n_f) else 'hbm'
+                if self._unfused(n):
+                    d = y.desc
+                    lin = DevTensor(d.n, d.z, d.x, d.y, d.c, c_pitch=d.c_pitch, device=self.device)
+                    op = ops.UpConvOp(h, x, lin, self._pdev(n.w), None, _sp3(n.pool_shape), 'lin', self.compute)
+                    self._f('upconv_fwd:' + n.name, op.fwd, fl, 4 * (_nel(x) + _nel(lin)), kind)
+                    self._plan_affine(n, lin, None, lin, y)
+                else:
+                    op = ops.UpConvOp(h, x, y, self._pdev(n.w), self._pdev(n.b), _sp3(n.pool_shape), n.activation_func,
+                                      self.compute)
+                    self._f('upconv_fwd:' + n.name, op.fwd, fl, 4 * (_nel(x) + _nel(y)), kind)
                 self.conv_ops[n] = op
                 self.pack_ops.append(op)
-                fl = 2.0 * _nel(x) * n.n_f * int(np.prod(n.pool_shape))
-                self._f('upconv_fwd:' + n.name, op.fwd, fl, 4 * (_nel(x) + _nel(y)),
-                        'tensor' if _tensor_shaped(x.desc.c, n.n_f) else 'hbm')
             elif isinstance(n, Conv):
                 self._plan_conv(n)
             elif isinstance(n, Pool):
                 x = self.val[n.parent]
                 y = self._new(n)
                 self.val[n] = y
-                op = ops.PoolOp(h, x, y, n.pool_shape, keep_argmax=self.train, tie_mode=config.pool_tie_mode)
+                op = ops.PoolOp(h, x, y, _sp3(n.pool_shape), keep_argmax=self.train, tie_mode=config.pool_tie_mode,
+                                mode=n.mode)
                 self.aux[n] = op
                 self._f('pool_fwd:' + n.name, op.fwd, 0, 4 * (_nel(x) + _nel(y)))
             elif isinstance(n, Crop):
@@ -268,7 +311,7 @@ class Plan(object):
                 else:
                     dst, c0 = self._new(n), 0
                     self.val[n] = dst
-                op = ops.CropConcatOp(h, src, dst, n.crop, c0)
+                op = ops.CropConcatOp(h, src, dst, _sp3(n.crop, 0), c0)
                 self.aux[n] = op
                 self._f('crop_concat_fwd:' + n.name, op.fwd, 0, 8 * _nel(self.val[n]))
             elif isinstance(n, Concat):
@@ -282,7 +325,8 @@ class Plan(object):
                 x = self.val[n.parent]
                 y = self._new(n)
                 self.val[n] = y
-                op = ops.Frag2DenseOp(h, x, y, n.parent.shape.mfp_offsets, n.parent.shape.strides)
+                op = ops.Frag2DenseOp(h, x, y, [_sp3(o, 0) for o in n.parent.shape.mfp_offsets],
+                                      _sp3(n.parent.shape.strides))
                 self.aux[n] = op
                 self._f('frag2dense_fwd:' + n.name, op.fwd, 0, 8 * _nel(x))
             else:
@@ -321,32 +365,59 @@ class Plan(object):
             x = self.aux[key]
         y = self.val[n] if n in self.val else self._new(n)
         self.val[n] = y
-        pooled = any(p > 1 for p in n.pool_shape)
+        k3, p3 = _sp3(n.filter_shape), _sp3(n.pool_shape)
+        pooled = any(p > 1 for p in p3)
         w, b = self._pdev(n.w), self._pdev(n.b)
-        lsp = [s + 1 - f for s, f in zip(n.parent.shape.spatial_shape, n.filter_shape)]
+        lsp = [s + 1 - f for s, f in zip(_sp3(n.parent.shape.spatial_shape), k3)]
         flops = 2.0 * x.desc.n * int(np.prod(lsp)) * int(np.prod(n.w_sh))
         kind = 'tensor' if _tensor_shaped(x.desc.c, n.n_f) else 'hbm'
-        if not pooled:
-            op = ops.ConvOp(h, x, y, w, b, n.filter_shape, n.activation_func, self.compute)
+        rnd = self.compute == 'tf32'
+        unfused = self._unfused(n)
+        if not pooled and not unfused:
+            op = ops.ConvOp(h, x, y, w, b, k3, n.activation_func, self.compute)
             self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(y)), kind)
         else:
             # conv -> pool|MFP -> +bias -> act  (neural.py:662-712): the conv writes raw
-            # accumulators, the pooling kernel carries the bias/activation epilogue
+            # accumulators, the pooling kernel carries the bias/activation epilogue -- or, for batch
+            # normalisation / prelu / abs, a third kernel does (e2_affine_act, csrc/e2_epilogue.cu)
             lin = DevTensor(x.desc.n, lsp[0], lsp[1], lsp[2], n.n_f, device=self.device)
-            op = ops.ConvOp(h, x, lin, w, None, n.filter_shape, 'lin', self.compute)
+            op = ops.ConvOp(h, x, lin, w, None, k3, 'lin', self.compute)
             self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(lin)), kind)
-            rnd = self.compute == 'tf32'
-            if n.mfp:
-                pop = ops.MfpOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train,
-                                round_tf32=rnd)
-                self._f('mfp_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
-            else:
-                pop = ops.PoolOp(h, lin, y, n.pool_shape, bias=b, act=n.activation_func, keep_argmax=self.train,
+            pb, pact = (None, 'lin') if unfused else (b, n.activation_func)
+            v = y.like() if (unfused and pooled) else y
+            pop = None
+            if pooled and n.mfp:
+                pop = ops.MfpOp(h, lin, v, p3, bias=pb, act=pact, keep_argmax=self.train, round_tf32=rnd)
+                self._f('mfp_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(v)))
+            elif pooled:
+                pop = ops.PoolOp(h, lin, v, p3, bias=pb, act=pact, keep_argmax=self.train,
                                  tie_mode=config.pool_tie_mode, round_tf32=rnd)
-                self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(y)))
-            self.aux[n] = (lin, pop)
+                self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(v)))
+            if unfused:
+                self._plan_affine(n, lin, pop, v if pooled else lin, y)
+            else:
+                self.aux[n] = (lin, pop)
         self.conv_ops[n] = op
         self.pack_ops.append(op)
+
+    def _unfused(self, n):
+        """Does this Conv / UpConv need the separate epilogue kernel?  Batch normalisation and prelu always; 'abs'
+        only when a backward pass follows (its derivative needs the sign of the pre-activation, which the fused
+        epilogue does not keep)."""
+        return bool(n.batch_normalisation) or n.activation_func == 'prelu' or (n.activation_func == 'abs' and self.train)
+
+    def _plan_affine(self, n, lin, pop, v, y):
+        bn = n.batch_normalisation
+        gamma = mean = std = None
+        if bn:
+            gamma = self._pdev(n.gamma) if n.gamma.apply_train else _aux_dev(n.gamma, self.device)
+            mean, std = _aux_dev(n.mean, self.device), _aux_dev(n.std, self.device)
+        aff = ops.AffineActOp(self.h, v, y, n.activation_func, self._pdev(n.b), bn, gamma, mean, std,
+                              round_tf32=self.compute == 'tf32')
+        self.aux[n] = dict(lin=lin, pop=pop, v=v, aff=aff)
+        if bn == 'train':
+            self.bn_ops.append(aff)
+        self._f('affine_act_fwd:' + n.name, aff.fwd, 0, 4 * (2 * _nel(v) if bn != 'train' else 4 * _nel(v)))
 
     def _plan_loss_head(self):
         """Softmax (+ MultinoulliNLL + AggregateLoss + Errors) as one fused op."""
@@ -403,19 +474,29 @@ class Plan(object):
                 continue
             if isinstance(n, UpConv):
                 dy, op = self.grad[n], self.conv_ops[n]
-                self._emit_act_bwd(n, dy)
+                db = n.b._grad
+                if isinstance(self.aux.get(n), dict):
+                    dy, db = self._emit_affine_bwd(n, dy), None
+                else:
+                    self._emit_act_bwd(n, dy)
                 fl = 2.0 * _nel(op.x) * n.n_f * int(np.prod(n.pool_shape))
                 kind = 'tensor' if _tensor_shaped(op.x.desc.c, n.n_f) else 'hbm'
-                l = self._b('upconv_wgrad:' + n.name, lambda op=op, dy=dy, n=n: op.wgrad(dy, n.w._grad, n.b._grad),
+                l = self._b('upconv_wgrad:' + n.name, lambda op=op, dy=dy, n=n, db=db: op.wgrad(dy, n.w._grad, db),
                             fl, 4 * (_nel(op.x) + _nel(dy)), kind)
                 l.param_end = n.w._offset + int(np.prod(n.w.shape))
                 l.param_start = n.w._offset
                 self._emit_dgrad(op, dy, n.parent, written, 'upconv_dgrad:' + n.name, fl, kind)
             elif isinstance(n, Conv):
                 dy, op = self.grad[n], self.conv_ops[n]
-                self._emit_act_bwd(n, dy)
-                if n in self.aux:
-                    lin, pop = self.aux[n]
+                db = n.b._grad
+                if isinstance(self.aux.get(n), dict):
+                    a = self.aux[n]
+                    dy, db = self._emit_affine_bwd(n, dy), None       # dy is now d loss / d (pooled) conv output
+                    lin, pop = a['lin'], a['pop']
+                else:
+                    self._emit_act_bwd(n, dy)
+                    lin, pop = self.aux.get(n, (None, None))
+                if pop is not None:
                     dlin = lin.like()
                     self._b(('mfp_bwd:' if n.mfp else 'pool_bwd:') + n.name,
                             lambda pop=pop, dy=dy, dlin=dlin: pop.bwd(dy, dlin), 0, 4 * (2 * _nel(dy) + _nel(dlin)))
@@ -423,7 +504,7 @@ class Plan(object):
                     dlin = dy
                 fl = 2.0 * dlin.desc.positions * int(np.prod(n.w_sh))
                 kind = 'tensor' if _tensor_shaped(op.x.desc.c, n.n_f) else 'hbm'
-                l = self._b('conv_wgrad:' + n.name, lambda op=op, dlin=dlin, n=n: op.wgrad(dlin, n.w._grad, n.b._grad),
+                l = self._b('conv_wgrad:' + n.name, lambda op=op, dlin=dlin, n=n, db=db: op.wgrad(dlin, n.w._grad, db),
                             fl, 4 * (_nel(op.x) + _nel(dlin)), kind)
                 l.param_end = n.w._offset + int(np.prod(n.w.shape))
                 l.param_start = n.w._offset
@@ -433,7 +514,11 @@ class Plan(object):
                 if isinstance(par, Input):
                     continue
                 acc = par in written
-                gate = self._gate_for(par)
+                if n.mode == 'max':
+                    gate = self._gate_for(par)
+                else:   # average / sum pooling: no fused ReLU gate, the producer's activation backward runs on its own
+                    gate = None
+                    self._contrib.setdefault(par, []).append(False)
                 self._b('pool_bwd:' + n.name,
                         lambda op=self.aux[n], dy=self.grad[n], dx=self.grad[par], acc=acc, gate=gate:
                         op.bwd(dy, dx, acc, relu_gate=gate), 0,
@@ -503,6 +588,17 @@ class Plan(object):
         self._contrib.setdefault(parent, []).append(gate is not None)
         return gate
 
+    def _emit_affine_bwd(self, n, dy):
+        """Backward of the unfused epilogue: dy -> d loss / dv (v = the pooled conv output), bias / slope / gamma
+        gradients written straight into the flat gradient buffer."""
+        a = self.aux[n]
+        aff, v = a['aff'], a['v']
+        dv = DevTensor(v.desc.n, v.desc.z, v.desc.x, v.desc.y, v.desc.c, c_pitch=v.desc.c_pitch, device=self.device)
+        dgamma = n.gamma._grad if (n.batch_normalisation and n.gamma.apply_train) else None
+        self._b('affine_act_bwd:' + n.name,
+                lambda aff=aff, dy=dy, dv=dv, n=n, dgamma=dgamma: aff.bwd(dy, dv, n.b._grad, dgamma), 0, 4 * 5 * _nel(v))
+        return dv
+
     def _emit_act_bwd(self, n, dy):
         c = self._contrib.get(n)
         if n.activation_func == 'relu' and c and all(c):
@@ -551,6 +647,8 @@ class Plan(object):
             for n, a in values.items():
                 t, pinned, staging = self.inputs[n]
                 a = np.asarray(a, dtype=np.float32)
+                if 3 <= a.ndim < 5 and a.ndim == len(n.shape):
+                    a = a.reshape(a.shape[:2] + (1,) * (5 - a.ndim) + a.shape[2:])   # 1-D / 2-D nets: leading unit axes
                 if tuple(a.shape) != tuple(pinned.shape):
                     raise ValueError("Input '%s' expects shape %s, got %s" % (n.name, tuple(pinned.shape), a.shape))
                 src = None
@@ -711,7 +809,9 @@ class Plan(object):
         if dp is not None:
             dp.finish_step(store)
         opt.dev_step(store, S, store.n_reg - S, 1)
-        opt.dev_step(store, store.n_reg, store.total - store.n_reg, 0)
+        for off, cnt, m in store.regions:
+            if off >= store.n_reg:
+                opt.dev_step(store, off, cnt, m)
         for op in (packs_late if j is not None and S > 0 else self.pack_ops):
             op.pack(True)
 
@@ -724,12 +824,19 @@ class Plan(object):
         dp = self.model.data_parallel
         if dp is not None and dp.world <= 1:
             dp = None
+        for a in self.bn_ops:
+            a.update_running = True            # neural.py:695-698: the running averages are updates of the optimiser step
+        try:
+            self._train_step(opt, loss_async, dp)
+        finally:
+            for a in self.bn_ops:
+                a.update_running = False
+
+    def _train_step(self, opt, loss_async, dp):
         if not (self.train and self.fuse_optimiser and getattr(opt, 'fusable', False) and not opt.keep_history):
-            self.execute()
+            self.execute()                     # includes the bucketed all-reduce when data parallel
             if loss_async:
                 self.loss_op.read_async()
-            if dp is not None:
-                dp.allreduce_gradients(self.store)
             opt.step(self.store)
             self.repack()
             return
@@ -742,12 +849,16 @@ class Plan(object):
             graphs = self._opt_graphs.get(key)
             if graphs is None:
                 # eager warm-up WITHOUT the update (creates streams / communicators, touches every kernel once)
+                for a in self.bn_ops:
+                    a.update_running = False   # the warm-up pass must not move the running averages a second time
                 if dp is not None:
                     dp.begin_step(self.store)
                 self._launch_all(dp.on_gradients_ready if dp is not None else None)
                 if dp is not None:
                     dp.finish_step(self.store)
                 torch.cuda.synchronize(self.device)
+                for a in self.bn_ops:
+                    a.update_running = True
                 try:
                     g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     # captured on a high-priority stream: kernel nodes inherit it, so whenever a dgrad (critical
@@ -896,23 +1007,20 @@ class Plan(object):
         # Data parallel: the bucketed NCCL all-reduces (side stream, forked and joined with events) are captured
         # into the same CUDA graph as the kernels: one graph launch per step on every rank.  If this torch/NCCL
         # build refuses the capture the step stays eager (E2_DP_GRAPH=0 forces that).
+        # one captured graph per value of the batch-norm running-average switch (graph nodes bake their arguments)
+        gkey = '_graph_upd' if (self.bn_ops and self.bn_ops[0].update_running) else '_graph'
         if self.use_graph and (dp is None or dp.graph_ok):
-            if self._graph is None:
+            if getattr(self, gkey) is None:
                 body()                      # eager warm-up (also creates the communicators outside the capture)
                 torch.cuda.synchronize(self.device)
-                self._graph = _try_capture(body, self.device, 'the training pass')
-                if self._graph is None:     # refused / invalidated: this plan stays eager
+                setattr(self, gkey, _try_capture(body, self.device, 'the training pass'))
+                if getattr(self, gkey) is None:     # refused / invalidated: this plan stays eager
                     self.use_graph = False
                     if dp is not None:
                         dp.graph_ok = False
-                    body()
-                    self._mark_inputs_free()
-                    return
-            self._graph.replay()
-            if dp is not None:
-                # a replay runs the captured collectives without going through finish_step(): tell the simple
-                # all-reduce (non-fused optimisers call it after execute()) that this step is already summed
-                dp._step_reduced = True
+                self._mark_inputs_free()
+                return
+            getattr(self, gkey).replay()
         else:
             body()
         self._mark_inputs_free()
@@ -924,6 +1032,7 @@ class Plan(object):
         torch.cuda.synchronize(self.device)
         self._opt_graphs.clear()
         self._graph = None
+        self._graph_upd = None
         self._pack_graph = None
         gc.collect()
 
@@ -980,7 +1089,11 @@ class Plan(object):
             return np.argmax(self.val[node.pred].numpy(self.h), axis=1)[:, None].astype(np.int16)
         if isinstance(node, loss_nodes.MultinoulliNLL):
             raise NotImplementedError("the per-voxel NLL tensor is not materialised on the B200 path")
-        return self.val[node].numpy(self.h)
+        out = self.val[node].numpy(self.h)
+        nd = len(node.shape)
+        if 3 <= nd < 5:
+            out = out.reshape(out.shape[:2] + out.shape[2 + (5 - nd):])
+        return out
 
     def run(self, values):
         self.feed(values)

@@ -5,10 +5,16 @@ signatures, shape / stride / fov / MFP arithmetic, parameter creation and error
 behaviour follow the reference (cited per method); the numeric work each node stands
 for is launched through libe2b200 by ``executor.Plan``.
 
-Supported on the B200 path: 3-D nets with tags 'b,f,z,x,y' ('dnn' axis order,
-neural.py:618-620), conv_mode 'valid', batch normalisation off, dropout off -- what
-all four BASELINE configs use.  Anything else raises NotImplementedError at
-construction, never silently computes something different.
+Supported on the B200 path: tags 'b,f,z,x,y' ('dnn' axis order, neural.py:618-620) and
+the 2-D / 1-D forms 'b,f,x,y' / 'b,f,x' (computations.py:337-362; executed as 3-D with
+leading unit axes), conv_mode 'valid', every activation of apply_activation
+(computations.py:57-134) except 'maxout' (see ``_check_supported``), batch
+normalisation 'train' / 'predict' (neural.py:681-709), max / average / sum pooling.
+The four BASELINE configs (relu / lin, no BN) run through the fused conv / pool
+epilogues; BN, 'prelu' and 'abs' in training go through the unfused epilogue kernels
+(csrc/e2_epilogue.cu).  Dropout, gradnet_mode, BN 'fadeout' and the 'theano' axis
+order raise NotImplementedError at construction -- never silently compute something
+different.
 """
 import logging
 
@@ -21,7 +27,7 @@ from .shapecalc import mfp_bookkeeping
 
 logger = logging.getLogger('elektronn2log')
 
-_ACTS = ('relu', 'lin', 'linear', 'tanh', 'sig', 'sigmoid', 'logistic', 'abs', 'soft+', 'elu', 'selu')
+_ACTS = ('relu', 'lin', 'linear', 'tanh', 'sig', 'sigmoid', 'logistic', 'abs', 'soft+', 'elu', 'selu', 'prelu')
 
 
 class NeuralLayer(Node):
@@ -44,17 +50,44 @@ class NeuralLayer(Node):
         setattr(self, name, p)
         self.params[name] = p
 
-    def _setup_params(self, w_sh, w, b, pool_shape):
-        """neural.py:146-204: glorot-normal weights (pool-aware fan), bias by activation."""
+    def _setup_params(self, w_sh, w, b, pool_shape, gamma=None, mean=None, std=None):
+        """neural.py:146-239: glorot-normal weights (pool-aware fan), bias by activation ((f,2) for prelu: bias and
+        slope, slope initialised to 1), batch-normalisation parameters."""
         w_init = dict(scale='glorot', mode='normal', pool=pool_shape, spatial_axes=self.spatial_axes)
         self._register_param(w, w_sh, 'w', init_kwargs=w_init, apply_train=True, apply_reg=True)
+        b_sh = (self.n_f,)
+        fov = float(np.prod([w_sh[i] for i in self.spatial_axes]))
         if self.activation_func == 'relu':
-            b_init = dict(scale=1.0 / float(np.prod([w_sh[i] for i in self.spatial_axes])), mode='const')
+            b_init = dict(scale=1.0 / fov, mode='const')
         elif self.activation_func == 'sigmoid':
             b_init = dict(scale=0.5, mode='const')
+        elif self.activation_func == 'prelu':
+            b_init = dict(scale=1.0 / fov, mode='prelu')
+            b_sh = (self.n_f, 2)
         else:
             b_init = dict(scale=1e-6, mode='fix-uni')
-        self._register_param(b, (self.n_f,), 'b', init_kwargs=b_init, apply_train=True, apply_reg=False)
+        self._register_param(b, b_sh, 'b', init_kwargs=b_init, apply_train=True, apply_reg=False)
+        sh = (self.n_f,)
+        bn = self.batch_normalisation
+        if bn == 'train':   # neural.py:208-228
+            self._register_param(gamma, sh, 'gamma', init_kwargs=dict(scale=1.0, mode='const'), apply_train=True,
+                                 apply_reg=3.0)
+            if mean is not None or std is not None:
+                raise ValueError("Cannot pass mean and std for training, they are computed in the theano graph.")
+            self._register_param(None, sh, 'mean', init_kwargs=dict(scale=0.0, mode='const'), apply_train=False)
+            self._register_param(None, sh, 'std', init_kwargs=dict(scale=1.0, mode='const'), apply_train=False)
+        elif bn == 'predict':   # neural.py:230-242
+            self._register_param(gamma, sh, 'gamma', init_kwargs=dict(scale=1.0, mode='const'), apply_train=False)
+            self._register_param(mean, sh, 'mean', init_kwargs=dict(scale=0.0, mode='const'), apply_train=False)
+            self._register_param(std, sh, 'std', init_kwargs=dict(scale=1.0, mode='const'), apply_train=False)
+        elif bn is not False:
+            raise ValueError("Unknown value %s for batchnormalisation" % (bn,))
+
+    @property
+    def unfused_epilogue(self):
+        """True when the bias / activation cannot ride in the conv or pool kernel's epilogue (BN scale and batch
+        statistics, prelu's slope, abs' sign): the executor then runs conv -> pool -> e2_affine_act."""
+        return bool(self.batch_normalisation) or self.activation_func in ('prelu', 'abs')
 
 
 class Conv(NeuralLayer):
@@ -88,25 +121,36 @@ class Conv(NeuralLayer):
             raise ValueError("The filter_shape dimensionality (%i), the number of spatial dimensions in the input "
                              "(%i) and the dimensionality of pool_shape (%i) differ! Use filter size 1 on axes "
                              "which should not be convolved." % (len(self.filter_shape), conv_dim, len(self.pool_shape)))
-        if conv_dim != 3 or len(parent.shape) != 5 or self.spatial_axes != [2, 3, 4]:
-            raise NotImplementedError("The B200 path convolves 3-D 'b,f,z,x,y' tensors only (got tags %s)"
-                                      % (parent.shape.tags,))
-        self.axis_order = 'dnn'
+        # neural.py:604-633: 1-D 'b,f,x', 2-D 'b,f,x,y' (any two spatial tags on axes 2,3), 3-D 'b,f,z,x,y' ('dnn')
+        ok = {1: (3, [2]), 2: (4, [2, 3]), 3: (5, [2, 3, 4])}.get(conv_dim)
+        if ok is None or len(parent.shape) != ok[0] or self.spatial_axes != ok[1]:
+            raise NotImplementedError("Cannot convolve non-standard shapes / axis orders (got tags %s; the 'theano' "
+                                      "order 'b,z,f,x,y' is not on the B200 path). Implement reshaping before conv "
+                                      "and re-reshaping after!" % (parent.shape.tags,))
+        self.axis_order = 'dnn' if conv_dim == 3 else None
         self.conv_dim = conv_dim
         n_in = parent.shape['f']
         self.w_sh = [n_f, n_in] + list(self.filter_shape)
-        self._setup_params(self.w_sh, w, b, self.pool_shape)
+        self._setup_params(self.w_sh, w, b, self.pool_shape, gamma, mean, std)
 
     @staticmethod
     def _check_supported(conv_mode, activation_func, batch_normalisation, dropout_rate, gradnet_mode):
         if conv_mode != 'valid':
             raise NotImplementedError("conv_mode '%s': only 'valid' is supported on the B200 path "
                                       "(3-D 'same'/'full' exist only on the reference's cuDNN path)" % conv_mode)
+        if isinstance(activation_func, str) and activation_func.startswith('maxout'):
+            # the reference cannot build this either: Conv._make_output does ``self.filter_shape /= r``
+            # (neural.py:650-653), a TypeError for the tuple / list filter shapes every caller passes, and
+            # computations.maxout pools axis 2 (z in the 'b,f,z,x,y' layout, computations.py:476-477) instead of f
+            raise NotImplementedError("'%s' as a layer activation is broken in the reference (neural.py:650-653); "
+                                      "use computations.maxout(x, factor, axis) on the layer output" % activation_func)
         if activation_func not in _ACTS:
             raise NotImplementedError("%s. Permitted activation_funcs on the B200 path: %s"
                                       % (activation_func, list(_ACTS)))
-        if batch_normalisation:
-            raise NotImplementedError("batch_normalisation is not supported on the B200 path yet (SURVEY 8f-4)")
+        if batch_normalisation == 'fadeout':
+            raise NotImplementedError("batch_normalisation='fadeout' needs gradnet_mode, which is not on the B200 path")
+        if batch_normalisation not in (False, 'train', 'predict'):
+            raise ValueError("Unknown value %s for batchnormalisation" % (batch_normalisation,))
         if dropout_rate:
             raise NotImplementedError("dropout is not supported on the B200 path")
         if gradnet_mode:
@@ -188,13 +232,14 @@ class UpConv(Conv):
         pool_shape = tuple(int(p) for p in pool_shape)
         super(UpConv, self).__init__(parent, n_f, pool_shape, pool_shape, 'valid', activation_func, mfp=False,
                                      batch_normalisation=batch_normalisation, dropout_rate=dropout_rate, name=name,
-                                     print_repr=print_repr, w=w, b=b, gradnet_mode=gradnet_mode)
+                                     print_repr=print_repr, w=w, b=b, gamma=gamma, mean=mean, std=std,
+                                     gradnet_mode=gradnet_mode)
         if identity_init:  # neural.py:977-986
             w_val = self.w.get_value() * 0.1
             s = np.arange(min(w_val.shape[0], w_val.shape[1]))
             w_val[s, s] = 1.0
             self.w.set_value(w_val)
-            self.b.set_value(self.b.get_value() * 0.0)
+            self.b.set_value(self.b.get_value() * 0.0)   # prelu: zeroes the slope too, like the reference (:984)
 
     def _calc_shape(self):
         """neural.py:1074-1097: S*p per axis, strides / p, fov flagged -1."""
@@ -288,8 +333,10 @@ class Pool(Node):
         if stride is not None and tuple(stride) != pool_shape:
             raise NotImplementedError("Stride!=Pool is not supported (neither by the reference's CPU path, "
                                       "computations.py:612-613)")
-        if mode != 'max':
-            raise NotImplementedError("Pooling mode '%s': only 'max' is on the B200 path" % mode)
+        if mode == 'average':
+            mode = 'average_inc_pad'  # Theano's internal name (neural.py:1451-1452)
+        if mode not in ('max', 'average_inc_pad', 'average_exc_pad', 'sum'):
+            raise ValueError("Unknown pooling mode '%s' (computations.py:556-561)" % mode)
         self.pool_shape = pool_shape
         self.pool_stride = pool_shape
         self.mfp = mfp
@@ -297,8 +344,10 @@ class Pool(Node):
         self.strides = parent.shape.strides
         self.mfp_offsets = parent.shape.mfp_offsets
         self.spatial_axes = parent.shape.spatial_axes
-        if len(pool_shape) != 3 or len(parent.shape) != 5 or self.spatial_axes != [2, 3, 4]:
-            raise NotImplementedError("The B200 path pools 3-D 'b,f,z,x,y' tensors only")
+        nd = len(pool_shape)
+        if nd not in (1, 2, 3) or len(parent.shape) != nd + 2 or self.spatial_axes != list(range(2, 2 + nd)):
+            raise NotImplementedError("The B200 path pools 'b,f,x' / 'b,f,x,y' / 'b,f,z,x,y' tensors over all their "
+                                      "spatial axes (got pool %s for tags %s)" % (pool_shape, parent.shape.tags))
 
     def _calc_shape(self):
         """neural.py:1528-1559."""

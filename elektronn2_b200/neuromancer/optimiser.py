@@ -8,6 +8,7 @@ The reference additionally rotates three full parameter copies per step for
 ``repair()`` (optimiser.py:71-72, 103-118) -- kept here as an optional, off-by-default
 snapshot because it is pure overhead on the hot path.
 """
+import numpy as np
 import torch
 
 from .. import _lib
@@ -44,12 +45,13 @@ class Optimiser(object):
             self.meta_params[k].set_value(v)
 
     def _hyper(self):
-        return (float(self.global_lr.get_value()), float(self.global_mom.get_value()),
-                float(self.global_weight_decay.get_value()))
+        return (float(np.asarray(self.global_lr.get_value()).reshape(-1)[0]),
+                float(np.asarray(self.global_mom.get_value()).reshape(-1)[0]),
+                float(np.asarray(self.global_weight_decay.get_value()).reshape(-1)[0]))
 
     def _regions(self, store):
-        """(offset, count, apply_wd) per contiguous region of the flat buffer."""
-        return [(0, store.n_reg, 1), (store.n_reg, store.total - store.n_reg, 0)]
+        """(offset, count, weight-decay multiplier) per contiguous region of the flat buffer."""
+        return list(store.regions)
 
     def _alloc(self, store, n):
         return [torch.zeros(store.total, dtype=torch.float32, device=store.device) for _ in range(n)]
@@ -86,7 +88,7 @@ class SGD(Optimiser):
         for off, cnt, awd in self._regions(store):
             if cnt:
                 h.call('e2_sgd_step', _slice_ptr(store.P, off), _slice_ptr(store.G, off),
-                       _slice_ptr(self._state[0], off), cnt, lr, mom, wd, awd, h.stream())
+                       _slice_ptr(self._state[0], off), cnt, lr, mom, wd, float(awd), h.stream())
         self._after_step(store)
 
 
@@ -102,7 +104,7 @@ class Adam(Optimiser):
         if self._state is None:
             self._state = self._alloc(store, 2)  # momentum, squared_accum
         lr, mom, wd = self._hyper()
-        beta2 = float(self.beta2.get_value())
+        beta2 = float(np.asarray(self.beta2.get_value()).reshape(-1)[0])
         self.t += 1
         if self.keep_history:
             self._snapshot = store.P.clone()
@@ -110,7 +112,7 @@ class Adam(Optimiser):
             if cnt:
                 h.call('e2_adam_step', _slice_ptr(store.P, off), _slice_ptr(store.G, off),
                        _slice_ptr(self._state[0], off), _slice_ptr(self._state[1], off), cnt, lr, mom, beta2, wd,
-                       awd, self.t, h.stream())
+                       float(awd), self.t, h.stream())
         self._after_step(store)
 
     # -- in-graph form (executor.Plan.train_step): hyper-parameters and step counter in device memory ----------
@@ -126,7 +128,7 @@ class Adam(Optimiser):
             self._t_dev = torch.zeros(1, dtype=torch.int32, device=store.device)
             self._hyper_host, self._t_host = None, None
         lr, mom, wd = self._hyper()
-        cur = (lr, mom, float(self.beta2.get_value()), wd)
+        cur = (lr, mom, float(np.asarray(self.beta2.get_value()).reshape(-1)[0]), wd)
         if cur != self._hyper_host:
             self._hyper_dev[:4].copy_(torch.tensor(cur, dtype=torch.float32))
             self._hyper_host = cur
@@ -144,7 +146,7 @@ class Adam(Optimiser):
             return
         h = _lib.get_handle()
         h.call('e2_adam_step_dev', _slice_ptr(store.P, off), _slice_ptr(store.G, off), _slice_ptr(self._state[0], off),
-               _slice_ptr(self._state[1], off), cnt, _lib.ptr(self._hyper_dev), int(apply_wd), h.stream())
+               _slice_ptr(self._state[1], off), cnt, _lib.ptr(self._hyper_dev), float(apply_wd), h.stream())
 
     def dev_after(self, store):
         """Host bookkeeping after a fused step has been submitted."""

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT, COMPUTE, TIE
+from ._lib import ACT, COMPUTE, TIE, POOL_MODE
 from .devtensor import DevTensor
 
 
@@ -126,12 +126,16 @@ class PoolOp(object):
     """computations.pooling 3-D max (computations.py:538-649) with optional fused
     +bias -> act (Conv nodes that carry a pool, neural.py:678, 711-712)."""
 
-    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, tie_mode='first', round_tf32=False):
+    def __init__(self, h, x, y, pool, bias=None, act='lin', keep_argmax=True, tie_mode='first', round_tf32=False,
+                 mode='max'):
         self.h, self.x, self.y, self.bias = h, x, y, bias
         self.pool = tuple(int(v) for v in pool)
+        if mode not in POOL_MODE:
+            raise ValueError("unknown pooling mode %r (computations.py:556-561)" % (mode,))
         self.d = _lib.PoolDesc(x.desc, y.desc, self.pool[0], self.pool[1], self.pool[2], ACT[act],
-                               1 if bias is not None else 0, TIE[tie_mode], 0, int(bool(round_tf32)))
-        self.argmax = y.like(dtype=torch.int32) if keep_argmax else None
+                               1 if bias is not None else 0, TIE[tie_mode], 0, int(bool(round_tf32)), 0, POOL_MODE[mode])
+        self.is_max = POOL_MODE[mode] == 0
+        self.argmax = y.like(dtype=torch.int32) if (keep_argmax and self.is_max) else None
 
     def fwd(self):
         self.h.call('e2_maxpool3d_fwd', C.byref(self.d), self.x.ptr(), _lib.ptr(self.bias), self.y.ptr(),
@@ -142,12 +146,73 @@ class PoolOp(object):
         C.memmove(C.byref(d), C.byref(self.d), C.sizeof(d))
         d.x, d.y, d.accumulate = dx.desc, dy.desc, int(accumulate)
         gate = relu_gate
+        if not self.is_max:
+            # average / sum pooling: no argmax, no fused gate (the executor emits the activation backward separately)
+            assert relu_gate is None
+            self.h.call('e2_maxpool3d_bwd', C.byref(d), dy.ptr(), None, None, dx.ptr(), None, self.h.stream())
+            return
         if (relu_gate is self.x and self.argmax is not None and not d.has_bias and d.act == ACT['lin']
                 and d.tie_mode == TIE['first']):
             # the gate is this pool's own (post-ReLU) input: gate[argmax] == pooled value, read y instead of x
             gate, d.gate_pooled = self.y, 1
         self.h.call('e2_maxpool3d_bwd', C.byref(d), dy.ptr(), self.argmax.ptr() if self.argmax is not None else None,
                     self.x.ptr(), dx.ptr(), gate.ptr() if gate is not None else None, self.h.stream())
+
+
+class AffineActOp(object):
+    """The unfused epilogue y = act((gamma/std) * v + b - gamma*mean/std) of Conv / UpConv (neural.py:681-712) for
+    batch normalisation, 'prelu' and activations whose derivative needs the pre-activation.
+
+    bn: False | 'train' | 'predict'.  Parameters are device views: b (f,) or (f,2) for prelu; gamma / mean / std (f,).
+    In 'train' mode ``fwd`` computes the batch statistics and, when ``update_running`` is set, the running averages
+    mean <- 0.9995 mean + 0.0005 batch_mean (same for std), which the reference applies as Theano updates of the
+    optimiser step (neural.py:695-698)."""
+
+    KEEP = 0.9995
+
+    def __init__(self, h, v, y, act, b, bn=False, gamma=None, mean=None, std=None, round_tf32=False):
+        self.h, self.v, self.y, self.act, self.b, self.bn = h, v, y, act, b, bn
+        self.gamma, self.mean, self.std = gamma, mean, std
+        self.prelu = act == 'prelu'
+        stride = 2 if self.prelu else 1
+        self.d = _lib.AffineDesc(v.desc, ACT[act], 1 if bn == 'train' else 0, int(bool(round_tf32)), stride)
+        c = v.desc.c
+        dev = v.buf.device
+        self.scale = _dev_f32(c, dev)
+        self.shift = _dev_f32(c, dev)
+        self.bmean = _dev_f32(c, dev)          # batch statistics ('train')
+        self.bstd = _dev_f32(c, dev)
+        nb = C.c_size_t()
+        _lib.lib.e2_affine_scratch_bytes(c, C.byref(nb))
+        self.scratch = torch.zeros((nb.value + 7) // 8, dtype=torch.float64, device=dev)
+        self.update_running = False
+        self.alpha = None
+        if self.prelu:
+            self.alpha = C.c_void_p(b.data_ptr() + 4)       # b[:, 1]
+
+    def fwd(self):
+        h, s = self.h, self.h.stream()
+        if self.bn == 'train':
+            upd = self.update_running
+            h.call('e2_bn_batch_stats', C.byref(self.v.desc), self.v.ptr(), _lib.ptr(self.gamma), _lib.ptr(self.b),
+                   self.d.param_stride, _lib.ptr(self.bmean), _lib.ptr(self.bstd), _lib.ptr(self.scale),
+                   _lib.ptr(self.shift), _lib.ptr(self.mean) if upd else None, _lib.ptr(self.std) if upd else None,
+                   C.c_float(self.KEEP), _lib.ptr(self.scratch), s)
+        else:
+            h.call('e2_bn_fold', self.v.desc.c, _lib.ptr(self.gamma) if self.bn else None, _lib.ptr(self.b),
+                   self.d.param_stride, _lib.ptr(self.mean) if self.bn else None, _lib.ptr(self.std) if self.bn else None,
+                   _lib.ptr(self.scale), _lib.ptr(self.shift), s)
+        h.call('e2_affine_act_fwd', C.byref(self.d), self.v.ptr(), _lib.ptr(self.scale), _lib.ptr(self.shift), self.alpha,
+               self.y.ptr(), s)
+
+    def bwd(self, dy, dv, db, dgamma=None):
+        """dv, db (and dgamma, and for prelu the slope gradient interleaved in db) from dy."""
+        m = self.bmean if self.bn == 'train' else (self.mean if self.bn else None)
+        sd = self.bstd if self.bn == 'train' else (self.std if self.bn else None)
+        dalpha = C.c_void_p(db.data_ptr() + 4) if self.prelu else None
+        self.h.call('e2_affine_act_bwd', C.byref(self.d), self.v.ptr(), dy.ptr(), _lib.ptr(self.scale), _lib.ptr(self.shift),
+                    self.alpha, _lib.ptr(m), _lib.ptr(sd), dv.ptr(), _lib.ptr(dgamma), _lib.ptr(db), dalpha,
+                    _lib.ptr(self.scratch), self.h.stream())
 
 
 class MfpOp(object):

@@ -15,12 +15,14 @@
  *  - return value: E2_OK or a negative e2_status; e2_last_error(h) holds the text;
  *  - activations are channels-last "NDHWC": element (n,z,x,y,c) lives at
  *    ((((n*Z + z)*X + x)*Y + y) * c_pitch + c), c_pitch >= c.  The reference's
- *    (b,f,z,x,y) arrays enter/leave through e2_layout_convert;
+ *    (b,f,z,x,y) arrays enter/leave through e2_ncdhw_to_ndhwc / e2_ndhwc_to_ncdhw;
  *  - conv weights are exchanged in the reference's own layout
  *    (f_out, f_in, kz, kx, ky) float32 (neural.py:618-620) and re-packed on the
  *    device by e2_conv3d_pack_weights;
  *  - a handle is bound to one device; calls on different handles are independent;
- *    there is no global mutable state.
+ *    the library keeps no mutable state outside the handle.  The only process-wide inputs are read-once
+ *    E2_* environment switches for A/B profiling (kernel selection, split plans); they never change results
+ *    beyond fp32 summation order and are listed in DESIGN.md.
  */
 #ifndef E2B200_H
 #define E2B200_H
@@ -47,7 +49,9 @@ typedef enum {
 /* apply_activation, computations.py:57-134 (the parameter-free subset) */
 /* apply_activation, computations.py:57-134: 'soft+' = log(1+exp(x)), 'elu' = T.nnet.elu(x, 1), 'selu' = scale * elu(x, alpha) */
 typedef enum { E2_ACT_LIN = 0, E2_ACT_RELU = 1, E2_ACT_TANH = 2, E2_ACT_SIGMOID = 3, E2_ACT_ABS = 4,
-               E2_ACT_SOFTPLUS = 5, E2_ACT_ELU = 6, E2_ACT_SELU = 7 } e2_act;
+               E2_ACT_SOFTPLUS = 5, E2_ACT_ELU = 6, E2_ACT_SELU = 7,
+               E2_ACT_PRELU = 8 /* T.nnet.relu(x, alpha): only through e2_affine_act_* (needs the slope parameter) */
+} e2_act;
 
 /* arithmetic used inside the conv GEMMs (accumulation is always fp32) */
 typedef enum {
@@ -57,6 +61,9 @@ typedef enum {
 } e2_compute;
 
 typedef enum { E2_TIE_FIRST = 0, E2_TIE_ALL = 1 } e2_tie_mode;
+/* computations.pooling modes (computations.py:556-561, 589-590): dnn_pool's 'average_inc_pad' and 'average_exc_pad'
+ * coincide because the path never pads */
+typedef enum { E2_POOL_MAX = 0, E2_POOL_AVERAGE = 1, E2_POOL_SUM = 2 } e2_pool_mode;
 
 typedef struct {
   int32_t n, z, x, y, c; /* logical extents */
@@ -167,6 +174,7 @@ typedef struct {
                           * for a pool without bias/activation whose input is a post-ReLU tensor: the only
                           * element of a window that receives gradient is the argmax, whose value IS the
                           * pooled value, so gate(x)[argmax] == y -- one eighth of the gate traffic */
+  int32_t mode;          /* e2_pool_mode; AVERAGE / SUM take no bias / activation / argmax / gate */
 } e2_pool_desc;
 
 int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,
@@ -175,6 +183,47 @@ int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const 
  * semantics) needs x and the pooled pre-bias maximum is recomputed from it. */
 int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax, const float* x,
                      float* dx, const float* relu_gate, void* stream);
+
+/* ------------------------------------------------- unfused epilogue (next-row 8f-4)
+ * Conv._make_output / UpConv._make_output between pooling and dropout, neural.py:681-712:
+ *     y = act((gamma / std) * v + b - gamma * mean / std)
+ * for the configurations the fused conv / pool epilogues do not cover: batch normalisation ('train': batch
+ * statistics over all axes but f, std = T.std + 1e-6, running averages 0.9995/0.0005, neural.py:681-698;
+ * 'predict': stored mean / std / gamma, :700-703), 'prelu' (b is (f_out, 2): bias b[:,0], slope b[:,1],
+ * neural.py:655-657), and activations whose derivative needs the pre-activation ('abs').
+ * scale / shift / mean / std are DEVICE float[c]; NULL scale == 1, NULL shift == 0. */
+typedef struct {
+  e2_tensor t;          /* geometry shared by v, y, dy, dv                                   */
+  int32_t act;          /* e2_act, E2_ACT_PRELU included                                    */
+  int32_t batch_stats;  /* bwd: scale / shift were derived from the batch statistics of v   */
+  int32_t round_tf32;   /* round y (fwd) / dv (bwd) to tf32                                 */
+  int32_t param_stride; /* floats between consecutive channels of alpha / dbias / dalpha (2 for prelu's (f,2) b) */
+} e2_affine_desc;
+
+/* batch statistics of v -> mean, std (= sqrt(mean((v-mean)^2)) + 1e-6), scale = gamma/std, shift = b - gamma*mean/std;
+ * run_mean / run_std (nullable) <- keep * run + (1-keep) * batch.  scratch: DEVICE double[2*c]. */
+int e2_bn_batch_stats(e2_handle* h, const e2_tensor* t, const float* v, const float* gamma, const float* bias,
+                      int32_t bias_stride, float* mean, float* std_out, float* scale, float* shift, float* run_mean,
+                      float* run_std, float keep, double* scratch, void* stream);
+/* scale = gamma/std, shift = b - gamma*mean/std from stored parameters (any pointer may be NULL: gamma=1, b=0, mean=0, std=1) */
+int e2_bn_fold(e2_handle* h, int32_t c, const float* gamma, const float* bias, int32_t bias_stride, const float* mean,
+               const float* std_in, float* scale, float* shift, void* stream);
+int e2_affine_act_fwd(e2_handle* h, const e2_affine_desc* d, const float* v, const float* scale, const float* shift,
+                      const float* alpha, float* y, void* stream);
+/* dv and the parameter gradients (each nullable): dbias = sum dpre, dgamma = sum dpre * (v-mean)/std,
+ * dalpha = sum dy * min(pre, 0).  With batch_stats the gradient flows through mean and std as T.grad derives it.
+ * scratch: e2_affine_scratch_bytes(c) DEVICE bytes, 8-byte aligned. */
+int e2_affine_act_bwd(e2_handle* h, const e2_affine_desc* d, const float* v, const float* dy, const float* scale,
+                      const float* shift, const float* alpha, const float* mean, const float* std_in, float* dv,
+                      float* dgamma, float* dbias, float* dalpha, double* scratch, void* stream);
+int e2_affine_scratch_bytes(int32_t c, size_t* bytes);
+
+/* computations.maxout, computations.py:455-495: y[o, f, i] = max_k x[o, f*factor + k, i] on a dense
+ * (outer, f_out*factor, inner) array; the backward routes dy to the first maximal slice. */
+int e2_maxout_fwd(e2_handle* h, const float* x, float* y, int64_t outer, int32_t f_out, int64_t inner, int32_t factor,
+                  void* stream);
+int e2_maxout_bwd(e2_handle* h, const float* x, const float* dy, float* dx, int64_t outer, int32_t f_out, int64_t inner,
+                  int32_t factor, void* stream);
 
 /* ------------------------------------------------------ max-fragment-pooling
  * computations.fragmentpool, computations.py:652-678.  Output batch = prod(p) * n,
@@ -239,19 +288,20 @@ int e2_softmax_nll_bwd(e2_handle* h, const e2_tensor* logits, const float* probs
 
 /* ---------------------------------------------------- optimiser (next-row 8f-2)
  * Adam exactly as optimiser.py:301-324: eps=1e-5 inside the sqrt, factor =
- * sqrt(1-beta2^t)/(1-mom^t), L2 term wd*p when apply_wd.  t is the 1-based step. */
+ * sqrt(1-beta2^t)/(1-mom^t), L2 term wd*wd_mult*p where wd_mult is the parameter's apply_reg (0: none, 1, or a
+ * multiplier > 1 such as batch-norm gamma's 3.0, neural.py:213; optimiser.py:312-318).  t is the 1-based step. */
 int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, float lr, float mom,
-                 float beta2, float wd, int32_t apply_wd, int32_t t, void* stream);
+                 float beta2, float wd, float wd_mult, int32_t t, void* stream);
 /* The same update with its hyper-parameters in DEVICE memory, so that the step can live inside a CUDA graph
  * (graph nodes bake their scalar arguments): hyper = float[8] {lr, mom, beta2, wd, factor, -, -, -}, t_dev = the
  * number of steps taken so far.  e2_adam_prepare increments *t_dev and refreshes hyper[4] = factor(t); it is the
  * first node of a training-step graph, e2_adam_step_dev may then run on any stream ordered behind it. */
 int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void* stream);
 int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, const float* hyper,
-                     int32_t apply_wd, void* stream);
+                     float wd_mult, void* stream);
 /* SGD with momentum, optimiser.py:146-160 */
 int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom, float wd,
-                int32_t apply_wd, void* stream);
+                float wd_mult, void* stream);
 
 /* ---------------------------------------------------------------- introspection
  * Host-only (no GPU needed): the tile plan the z-stack conv kernel would use for a conv of K input / N output

@@ -81,16 +81,25 @@ class Net(object):
         b, f = shape[0], shape[1]
         return N(self, 'input', [], shapes.Sh(1 if b is None else b, f, shape[2:]), name=name)
 
-    def conv(self, parent, n_f, k, pool=(1, 1, 1), act='relu', mfp=False, name=None):
+    def conv(self, parent, n_f, k, pool=(1, 1, 1), act='relu', mfp=False, name=None, bn=False):
+        """bn: False | 'train' | 'predict' (neural.py:206-242: gamma=1, running mean=0 / std=1)."""
         sh = shapes.conv_shape(parent.sh, n_f, k, pool, mfp)
-        n = N(self, 'conv', [parent], sh, k=tuple(k), pool=tuple(pool), act=act, mfp=mfp, name=name)
+        n = N(self, 'conv', [parent], sh, k=tuple(k), pool=tuple(pool), act=act, mfp=mfp, name=name, bn=bn)
         w_sh = (n_f, parent.sh.f) + tuple(k)
         n.params['w'] = glorot_normal(w_sh, pool, self.rng)
-        n.params['b'] = bias_init(n_f, k, act, self.rng)
+        if act == 'prelu':      # neural.py:186-200, variables.py:209-213: (f,2): bias 1/prod(k), slope 1
+            b = np.ones((n_f, 2), np.float32) / np.prod(k)
+            b[:, 1] = 1.0
+            n.params['b'] = b
+        else:
+            n.params['b'] = bias_init(n_f, k, act, self.rng)
+        if bn:
+            n.params['gamma'] = np.ones(n_f, np.float32)
+            n.state = dict(mean=np.zeros(n_f, F64), std=np.ones(n_f, F64))
         return n
 
-    def pool(self, parent, pool, name=None):
-        return N(self, 'pool', [parent], shapes.pool_shape(parent.sh, pool), pool=tuple(pool), name=name)
+    def pool(self, parent, pool, name=None, mode='max'):
+        return N(self, 'pool', [parent], shapes.pool_shape(parent.sh, pool), pool=tuple(pool), name=name, mode=mode)
 
     def upconv(self, parent, n_f, pool, act='relu', name=None):
         sh = shapes.upconv_shape(parent.sh, n_f, pool)
@@ -147,8 +156,8 @@ class Net(object):
         """(node, key) in graph order: w then b per layer."""
         out = []
         for n in self.nodes:
-            for k in ('w', 'b'):
-                if k in n.params:
+            for k in ('w', 'b', 'gamma'):
+                if k in n.params and not (k == 'gamma' and n.kw.get('bn') != 'train'):
                     out.append((n, k))
         return out
 
@@ -178,13 +187,32 @@ class Net(object):
                 pre = pooled + np.asarray(n.params['b'], F64).reshape(1, -1, 1, 1, 1)
                 v = rna_tf32(ops.activation(pre, n.kw['act']))
                 self.aux[n] = (lin, pre)
+            elif n.op == 'conv' and (n.kw.get('bn') or n.kw['act'] == 'prelu'):
+                # Conv._make_output with batch normalisation / prelu (neural.py:655-712)
+                w = n.params['w']
+                lin = (ops.conv3d_dot if tuple(w.shape[2:]) == (1, 1, 1) else ops.conv3d)(p[0], w)
+                pooled = ops.pooling(lin, n.kw['pool'])
+                b = np.asarray(n.params['b'], F64)
+                b0, b1 = (b[:, 0], b[:, 1]) if n.kw['act'] == 'prelu' else (b, None)
+                bn = n.kw.get('bn')
+                if bn == 'train':
+                    mean, std = ops.batchnorm_stats(pooled)
+                    n.batch = dict(mean=mean, std=std)
+                elif bn == 'predict':
+                    mean, std = n.state['mean'], n.state['std']
+                else:
+                    mean, std = np.zeros(len(b0)), np.ones(len(b0))
+                gamma = n.params['gamma'] if bn else np.ones(len(b0))
+                pre = ops.batchnorm_affine(pooled, gamma, b0, mean, std)
+                v = ops.prelu(pre, b1) if b1 is not None else ops.activation(pre, n.kw['act'])
+                self.aux[n] = (lin, pre, pooled, mean, std)
             elif n.op == 'conv':
                 v, (lin, pre), _ = ops.conv_node_fwd(p[0], n.params['w'], n.params['b'], n.kw['pool'],
                                                      n.kw['act'], n.kw['mfp'], n.parents[0].sh.mfp_offsets,
                                                      n.parents[0].sh.strides)
                 self.aux[n] = (lin, pre)
             elif n.op == 'pool':
-                v = ops.pooling(p[0], n.kw['pool'])
+                v = ops.pooling_mode(p[0], n.kw['pool'], n.kw.get('mode', 'max'))
             elif n.op == 'upconv':
                 v, pre = ops.upconv_node_fwd(self._use(p[0]), self._q(n.params['w']), n.params['b'], n.kw['pool'],
                                              n.kw['act'])
@@ -214,7 +242,24 @@ class Net(object):
                 continue
             dy = g[n]
             par = n.parents
-            if n.op == 'conv':
+            if n.op == 'conv' and len(self.aux[n]) == 5:
+                lin, pre, pooled, mean, std = self.aux[n]
+                bn = n.kw.get('bn')
+                if n.kw['act'] == 'prelu':
+                    dpre, dalpha = ops.prelu_bwd(dy, pre, np.asarray(n.params['b'], F64)[:, 1])
+                else:
+                    dpre, dalpha = ops.activation_bwd(dy, pre, n.kw['act']), None
+                gamma = n.params['gamma'] if bn else np.ones(pre.shape[1])
+                dpooled, dgamma, db = ops.batchnorm_bwd(dpre, pooled, gamma, mean, std, bn == 'train')
+                grads[(n, 'b')] = np.stack([db, dalpha], 1) if dalpha is not None else db
+                if bn == 'train':
+                    grads[(n, 'gamma')] = dgamma
+                xin = self.val[par[0]]
+                dlin = ops.pooling_bwd(dpooled, lin, n.kw['pool'], tie_mode) if any(q > 1 for q in n.kw['pool']) else dpooled
+                grads[(n, 'w')] = ops.conv3d_wgrad(dlin, xin, n.params['w'].shape)
+                if par[0].op != 'input':
+                    self._acc(g, par[0], ops.conv3d_dgrad(dlin, n.params['w'], xin.shape))
+            elif n.op == 'conv':
                 lin, pre = self.aux[n]
                 dpre = ops.activation_bwd(dy, pre, n.kw['act'])
                 grads[(n, 'b')] = ops.bias_grad(dpre)
@@ -230,6 +275,8 @@ class Net(object):
                 if par[0].op != 'input':
                     self._acc(g, par[0], ops.conv3d_dgrad(self._use(dlin, self._cuda_core_layer(n)),
                                                           self._q(n.params['w']), xin.shape), rounded=True)
+            elif n.op == 'pool' and n.kw.get('mode', 'max') != 'max':
+                self._acc(g, par[0], ops.pooling_mode_bwd(dy, self.val[par[0]].shape, n.kw['pool'], n.kw['mode']))
             elif n.op == 'pool':
                 self._acc(g, par[0], ops.pooling_bwd(dy, self.val[par[0]], n.kw['pool'], tie_mode))
             elif n.op == 'upconv':

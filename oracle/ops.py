@@ -402,3 +402,102 @@ def upconv_node_fwd(x, w, b, pool, act='relu'):
     lin = upconv3d(x, w, pool)
     pre = lin + np.asarray(b, F64).reshape(1, -1, 1, 1, 1)
     return activation(pre, act), pre
+
+
+# ----------------------------------------------------- pooling modes, prelu, maxout, batch norm
+def pooling_mode(x, pool, mode='max'):
+    """computations.pooling with dnn_pool's other modes (computations.py:556-561, 589-590, 600): 'average_inc_pad',
+    'average_exc_pad' (identical here: the path never pads) and 'sum'; stride == pool, ignore_border."""
+    if mode == 'average':
+        mode = 'average_inc_pad'
+    if mode == 'max':
+        return pooling(x, pool)
+    x = np.asarray(x, F64)
+    pool = tuple(int(p) for p in pool)
+    if all(p == 1 for p in pool):
+        return x
+    b, c, Z, X, Y = x.shape
+    pz, px, py = pool
+    Zo, Xo, Yo = Z // pz, X // px, Y // py
+    v = x[:, :, :Zo * pz, :Xo * px, :Yo * py].reshape(b, c, Zo, pz, Xo, px, Yo, py)
+    if mode in ('average_inc_pad', 'average_exc_pad'):
+        return v.mean(axis=(3, 5, 7))
+    if mode == 'sum':
+        return v.sum(axis=(3, 5, 7))
+    raise ValueError(mode)
+
+
+def pooling_mode_bwd(dy, x_shape, pool, mode):
+    """Backward of average / sum pooling: dy spread evenly over (or copied to) the window."""
+    dy = np.asarray(dy, F64)
+    pz, px, py = pool
+    up = np.repeat(np.repeat(np.repeat(dy, pz, 2), px, 3), py, 4)
+    if mode in ('average', 'average_inc_pad', 'average_exc_pad'):
+        up = up / float(pz * px * py)
+    dx = np.zeros(x_shape, F64)
+    dx[:, :, :up.shape[2], :up.shape[3], :up.shape[4]] = up
+    return dx
+
+
+def prelu(pre, alpha):
+    """T.nnet.relu(x, alpha) as Theano writes it: 0.5*(1+alpha)*x + 0.5*(1-alpha)*|x|
+    (apply_activation 'prelu', computations.py:83-85; alpha = b[:,1] broadcast over f, neural.py:655-657)."""
+    pre = np.asarray(pre, F64)
+    a = np.asarray(alpha, F64).reshape(1, -1, 1, 1, 1)
+    return 0.5 * (1 + a) * pre + 0.5 * (1 - a) * np.abs(pre)
+
+
+def prelu_bwd(dy, pre, alpha):
+    """(d/dpre, d/dalpha): slope 1 where pre > 0, alpha where pre < 0; d/dalpha = sum dy * min(pre, 0)."""
+    pre = np.asarray(pre, F64)
+    a = np.asarray(alpha, F64).reshape(1, -1, 1, 1, 1)
+    dpre = dy * np.where(pre > 0, 1.0, a)
+    dalpha = (dy * np.minimum(pre, 0.0)).sum(axis=(0, 2, 3, 4))
+    return dpre, dalpha
+
+
+def maxout(x, factor=2, axis=1):
+    """computations.maxout (computations.py:455-495): y = max_i x[..., i::factor, ...] along ``axis``.  (The
+    reference's default picks axis 2 for every input, :476-477 -- callers here pass the axis explicitly.)"""
+    x = np.asarray(x)
+    sl = [slice(None)] * x.ndim
+    sl[axis] = slice(0, None, factor)
+    y = x[tuple(sl)]
+    for i in range(1, factor):
+        sl[axis] = slice(i, None, factor)
+        y = np.maximum(y, x[tuple(sl)])
+    return y
+
+
+BN_EPS = 1e-6
+
+
+def batchnorm_stats(v):
+    """neural.py:681-685: mean and T.std (population) over all axes but f, std + 1e-6."""
+    v = np.asarray(v, F64)
+    return v.mean(axis=(0, 2, 3, 4)), v.std(axis=(0, 2, 3, 4)) + BN_EPS
+
+
+def batchnorm_affine(v, gamma, b, mean, std):
+    """neural.py:711: (gamma / std) * v + b - gamma * mean / std."""
+    r = lambda a: np.asarray(a, F64).reshape(1, -1, 1, 1, 1)
+    return (r(gamma) / r(std)) * np.asarray(v, F64) + r(b) - r(gamma) * r(mean) / r(std)
+
+
+def batchnorm_bwd(dpre, v, gamma, mean, std, batch_stats):
+    """Gradients of ``batchnorm_affine`` w.r.t. v, gamma, b.  With ``batch_stats`` mean and std are functions of v
+    (std = sigma + eps): dv = (gamma/std) [dpre - mean(dpre) - vhat (std/sigma) mean(dpre * vhat)]."""
+    r = lambda a: np.asarray(a, F64).reshape(1, -1, 1, 1, 1)
+    v = np.asarray(v, F64)
+    dpre = np.asarray(dpre, F64)
+    vhat = (v - r(mean)) / r(std)
+    ax = (0, 2, 3, 4)
+    db = dpre.sum(axis=ax)
+    dgamma = (dpre * vhat).sum(axis=ax)
+    if batch_stats:
+        n = v.size / v.shape[1]
+        sigma = np.asarray(std, F64) - BN_EPS
+        dv = (r(gamma) / r(std)) * (dpre - r(db) / n - vhat * r(np.asarray(std, F64) / sigma) * r(dgamma) / n)
+    else:
+        dv = (r(gamma) / r(std)) * dpre
+    return dv, dgamma, db

@@ -37,14 +37,21 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.e2_version() == 100
 
 
-def test_descriptor_structs_match_header_sizes():
+def test_descriptor_structs_match_header_sizes(tmp_path):
+    """sizeof of every POD descriptor as gcc sees include/e2b200.h == the ctypes mirror in _lib.py."""
+    import subprocess
     from elektronn2_b200 import _lib
-    assert ctypes.sizeof(_lib.Tensor) == 24
-    assert ctypes.sizeof(_lib.ConvDesc) == 48 + 7 * 4
-    assert ctypes.sizeof(_lib.PoolDesc) == 48 + 9 * 4
-    assert ctypes.sizeof(_lib.MfpDesc) == 48 + 6 * 4
-    assert ctypes.sizeof(_lib.F2DDesc) == 48 + 3 * 4
-    assert ctypes.sizeof(_lib.CropDesc) == 48 + 5 * 4
+    pairs = [('e2_tensor', _lib.Tensor), ('e2_conv_desc', _lib.ConvDesc), ('e2_upconv_desc', _lib.UpConvDesc),
+             ('e2_pool_desc', _lib.PoolDesc), ('e2_mfp_desc', _lib.MfpDesc), ('e2_f2d_desc', _lib.F2DDesc),
+             ('e2_crop_desc', _lib.CropDesc), ('e2_affine_desc', _lib.AffineDesc)]
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include "e2b200.h"\nint main(void){%s return 0;}\n'
+                   % ''.join('printf("%%zu\\n", sizeof(%s));' % n for n, _ in pairs))
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(c) for _, c in pairs]
+    assert ctypes.sizeof(_lib.Tensor) == 24 and ctypes.sizeof(_lib.PoolDesc) == 48 + 10 * 4
 
 
 def test_no_gpu_fails_loudly():

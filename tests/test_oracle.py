@@ -222,3 +222,75 @@ def test_tiling_oracle_identity_net():
     assert np.allclose(pred, raw[:, 2:-2, 2:-2, 2:-2].astype(np.float32) / 255)
     pred8 = tiling.predict_dense(fwd, raw, patch, out_sp, strides, offsets, 1, as_uint8=True)
     assert np.array_equal(pred8, (raw[:, 2:-2, 2:-2, 2:-2].astype(np.float32) / 255 * 255).astype(np.uint8))
+
+
+# ---------------------------------------------------------------- SURVEY 8f-4 restatements vs torch-CPU float64
+def test_f4_batchnorm_prelu_pool_modes_maxout_match_torch():
+    torch = pytest.importorskip("torch")
+    import torch.nn.functional as TF
+    rs = np.random.RandomState(0)
+    v = rs.randn(2, 5, 4, 6, 6)
+    gamma, b, dy = rs.rand(5) + 0.5, rs.randn(5), rs.randn(2, 5, 4, 6, 6)
+    r = lambda a: a.reshape(1, -1, 1, 1, 1)
+    tv = torch.tensor(v, requires_grad=True)
+    tg = torch.tensor(gamma, requires_grad=True)
+    tb = torch.tensor(b, requires_grad=True)
+    mean = tv.mean(dim=(0, 2, 3, 4))
+    std = tv.std(dim=(0, 2, 3, 4), unbiased=False) + 1e-6            # T.std + 1e-6, neural.py:683-684
+    pre = (r(tg) / r(std)) * tv + r(tb) - r(tg) * r(mean) / r(std)      # neural.py:711
+    (pre * torch.tensor(dy)).sum().backward()
+    m, s = ops.batchnorm_stats(v)
+    assert np.allclose(ops.batchnorm_affine(v, gamma, b, m, s), pre.detach().numpy(), atol=1e-12)
+    dv, dg, db = ops.batchnorm_bwd(dy, v, gamma, m, s, True)
+    assert np.allclose(dv, tv.grad.numpy(), atol=1e-12) and np.allclose(dg, tg.grad.numpy(), atol=1e-11)
+    assert np.allclose(db, tb.grad.numpy(), atol=1e-11)
+    # prelu == T.nnet.relu(x, alpha) == leaky relu with a per-feature slope
+    alpha = rs.uniform(-0.5, 0.9, 5)
+    ta = torch.tensor(alpha, requires_grad=True)
+    tp = torch.tensor(v, requires_grad=True)
+    y = torch.where(tp > 0, tp, r(ta) * tp)
+    (y * torch.tensor(dy)).sum().backward()
+    assert np.allclose(ops.prelu(v, alpha), y.detach().numpy(), atol=1e-12)
+    dpre, dalpha = ops.prelu_bwd(dy, v, alpha)
+    assert np.allclose(dpre, tp.grad.numpy(), atol=1e-12) and np.allclose(dalpha, ta.grad.numpy(), atol=1e-11)
+    # pooling modes
+    x = torch.tensor(v)
+    assert np.allclose(ops.pooling_mode(v, (2, 3, 2), 'average_inc_pad'), TF.avg_pool3d(x, (2, 3, 2)).numpy(), atol=1e-12)
+    assert np.allclose(ops.pooling_mode(v, (2, 3, 2), 'sum'), TF.avg_pool3d(x, (2, 3, 2)).numpy() * 12, atol=1e-12)
+    assert np.array_equal(ops.pooling_mode(v, (2, 3, 2), 'max'), ops.pooling(v, (2, 3, 2)))
+    d = rs.randn(2, 5, 2, 2, 3)
+    xg = torch.tensor(v, requires_grad=True)
+    (TF.avg_pool3d(xg, (2, 3, 2)) * torch.tensor(d)).sum().backward()
+    assert np.allclose(ops.pooling_mode_bwd(d, v.shape, (2, 3, 2), 'average'), xg.grad.numpy(), atol=1e-12)
+    # maxout: max over strided feature slices (computations.py:481-493)
+    z = rs.randn(2, 6, 3, 4, 4)
+    assert np.array_equal(ops.maxout(z, 3, 1), z.reshape(2, 2, 3, 3, 4, 4).max(axis=2))
+    assert np.array_equal(ops.maxout(z, 3, 2), np.maximum(np.maximum(z[:, :, 0::3], z[:, :, 1::3]), z[:, :, 2::3]))
+
+
+def test_f4_oracle_net_gradients_by_finite_differences():
+    """The oracle network with batch norm / prelu / abs / average pooling: analytic gradients == central differences."""
+    o = nets.Net(3)
+    n = o.input((2, 1, 4, 10, 10))
+    a = o.conv(n, 3, (1, 3, 3), (1, 2, 2), bn='train')
+    a = o.conv(a, 4, (2, 3, 3), act='prelu')
+    a = o.pool(a, (1, 2, 2), mode='average_inc_pad')
+    a = o.conv(a, 3, (1, 1, 1), act='abs', bn='train')
+    o.conv(a, 2, (1, 1, 1), act='lin')
+    rs = np.random.RandomState(1)
+    for node, k in o.param_list():
+        node.params[k] = (node.params[k].astype(np.float64) + 0.1 * rs.randn(*node.params[k].shape))
+    x = rs.rand(2, 1, 4, 10, 10)
+    t = rs.randint(0, 2, (2, 1, 3, 1, 1)).astype(np.float64)
+    L, grads, _, _ = o.loss_and_grads(x, t)
+    for node, k in o.param_list():
+        p = node.params[k]
+        idx = tuple(rs.randint(0, s) for s in p.shape)
+        old = p[idx]
+        p[idx] = old + 1e-6
+        Lp = o.loss_and_grads(x, t)[0]
+        p[idx] = old - 1e-6
+        Lm = o.loss_and_grads(x, t)[0]
+        p[idx] = old
+        num = (Lp - Lm) / 2e-6
+        assert abs(num - grads[(node, k)][idx]) <= 1e-5 * max(1.0, abs(num)), (node.name, k, num, grads[(node, k)][idx])
