@@ -337,3 +337,28 @@ def test_computations_seam_error_behaviour():
         cp.fragmentpool(x, (2, 2, 2), [[0, 0, 0]], [1, 1, 1], [2, 3, 4])    # (4-2+1) % 2 != 0
     with pytest.raises(ValueError):
         cp.fragments2dense(np.zeros((3, 2, 2, 2, 2), np.float32), [[0, 0, 0]] * 3, (1, 2, 2), [2, 3, 4])
+
+
+def test_modelload_reads_a_file_written_by_the_reference_serialiser():
+    """tests/golden/ref_written_small.mdl was written by the REFERENCE's own graphmanager.py (NodeDescriptor pointer
+    replacement, GraphManager.serialise) and picklesave (tests/golden/make_mdl_fixture.py) -- not by this package's
+    writer.  ``modelload`` (model.py:623-729) must rebuild the graph, the designations and every weight from it."""
+    from elektronn2_b200 import neuromancer as nm
+    golden = os.path.join(ROOT, 'tests', 'golden')
+    z = np.load(os.path.join(golden, 'ref_written_small.npz'))
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = nm.modelload(os.path.join(golden, 'ref_written_small.mdl'))
+    assert [type(n).__name__ for n in m.nodes.values()] == ['Input', 'Conv', 'Conv', 'Conv', 'Conv', 'Softmax', 'Input',
+                                                            'MultinoulliNLL', 'AggregateLoss']
+    assert (m.input_node.name, m.target_node.name, m.loss_node.name, m.prediction_node.name) == ('raw', 'target', 'loss', 'softmax')
+    assert [n.name for n in m.prediction_ext] == ['loss', 'softmax'] and m.error_node is None
+    assert m.prediction_node.shape.shape == [None, 2, 4, 10, 10]
+    assert list(m.prediction_node.shape.strides) == [2, 2, 2]
+    assert m.nodes['conv2'].activation_func == 'tanh' and m.nodes['conv1'].pool_shape == (2, 1, 1)
+    ps = m.prediction_node.all_trainable_params
+    assert len(ps) == 8
+    for k, p in ps.items():
+        assert np.array_equal(p.get_value(), z['p_' + k]), k
+    # the stream carries the reference's module paths, none of this package's
+    raw = open(os.path.join(golden, 'ref_written_small.mdl'), 'rb').read()
+    assert b'elektronn2.neuromancer.graphmanager' in raw and b'elektronn2_b200' not in raw
