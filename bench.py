@@ -38,6 +38,15 @@ WORKLOADS = {
 }
 
 
+# BASELINE.json configs 4 and 5: tiled dense prediction of a uint8 EM volume with examples/neuro3d.py re-built with MFP
+DENSE = {
+    'predict_dense_512': dict(volume=(512, 512, 512), patch=(54, 400, 400), seed=3, uint8_out=False,
+                              cpu_patch=(23, 185, 185)),
+    'predict_dense_2048': dict(volume=(2048, 2048, 2048), patch=(54, 400, 400), seed=4, uint8_out=True,
+                               cpu_patch=(23, 185, 185)),
+}
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -146,12 +155,14 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='unet3d', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='unet3d', choices=sorted(WORKLOADS) + sorted(DENSE))
     ap.add_argument('--compute', default=None, choices=['tf32', 'f32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-launch timing table (JSON) here')
     args = ap.parse_args()
+    if args.workload in DENSE:
+        return dense_main(args)
     W = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     K = max(args.steps, 1)
     rank = int(os.environ.get('RANK', '0'))
@@ -312,6 +323,199 @@ def main():
     return 0
 
 
+def cpu_dense_reference(spec, steps, budget_s=240.0):
+    """The reference's CPU way to predict one dense tile (no MFP: prod(strides) shifted passes, node_basic.py:832-856)
+    on all host cores; a step = one tile of the (23,185,185) training patch (10x84x84 output voxels)."""
+    import torch
+    from oracle import nets as onets, theano_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    r = theano_cpu.time_dense_tile(onets.neuro3d, spec['cpu_patch'], (2, 4, 4))
+    first = time.perf_counter() - t0
+    n = max(0, min(steps - 1, int((budget_s - first) / max(r['seconds'], 1e-9))))
+    secs = [r['seconds']]
+    for i in range(n):
+        secs.append(theano_cpu.time_dense_tile(onets.neuro3d, spec['cpu_patch'], (2, 4, 4), seed=i + 1)['seconds'])
+    vox = float(np.prod(r['out_spatial']))
+    per = float(np.mean(secs))
+    return dict(value=vox / per, unit='voxels/s', cores=r['cores'], kind='port', ms_per_step=per * 1e3, steps_timed=len(secs),
+                sample='%d tile(s) of %s output voxels each, %d shifted forward passes of examples/neuro3d.py at patch %s per '
+                       'tile (the reference\'s non-MFP dense path, node_basic.py:832-856), conv3d2d/pool_2d decomposition on '
+                       'torch-CPU float32 (Theano-equivalent restatement, not Theano)'
+                       % (len(secs), r['out_spatial'], r['passes'], list(spec['cpu_patch'])))
+
+
+def dense_main(args):
+    """``--workload predict_dense_512 | predict_dense_2048``: a step = one (54,400,400) tile through the MFP graph."""
+    spec = DENSE[args.workload]
+    K = max(args.steps, 1)
+    W = max(args.warmup, 3)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    config = dict(workload='predict_dense, examples/neuro3d.py + MFP (override_mfp_to_active), uint8 volume %s, tile patch '
+                           '(1,1,%d,%d,%d), %s output' % ((list(spec['volume']),) + tuple(spec['patch']) +
+                                                          ('uint8' if spec['uint8_out'] else 'float32',)),
+                  parallelism='tiles sharded over %d rank(s) in contiguous blocks, no collective' % world,
+                  l2_policy='activations of one tile (~6 GB) exceed the 126 MB L2')
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        r = cpu_dense_reference(spec, K)
+        line = dict(metric='predict_dense voxels/sec', value=r['value'], unit='voxels/s', n_gpus=world, steps=K,
+                    warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic', config=config, impl='reference',
+                    steps_timed=r['steps_timed'],
+                    cpu_baseline=dict(value=r['value'], unit='voxels/s', cores=r['cores'], kind=r['kind'], sample=r['sample']),
+                    e2e=dict(value=r['value'], unit='voxels/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return 0
+
+    import ctypes as C
+    import torch
+    from elektronn2_b200 import _lib, examples, parallel, neuromancer as nm
+    from elektronn2_b200.config import config as e2cfg
+    from elektronn2_b200.neuromancer import dense
+    if args.compute:
+        e2cfg.compute = args.compute
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dist = torch.distributed
+    sampler = ClockSampler(local)
+    sampler.start()
+    np.random.seed(2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        base = examples.neuro3d()
+        model = nm.rebuild_model(base, override_mfp_to_active=True, imposed_patch_size=tuple(spec['patch']))
+    node = model.prediction_node
+    vol_sp = spec['volume']
+    tile_sh, prob_sh, pred_sh, n_tiles = dense.tile_geometry(node, vol_sp)
+    tiles = dense.tile_list(n_tiles)
+    per = (len(tiles) + world - 1) // world
+    lo = rank * per
+    hi = min(len(tiles), lo + per, lo + K)          # bounded sample: the first K tiles of this rank's contiguous block
+    mine = tiles[lo:hi]
+    # the volume: zero pages are never touched; only the z-slab(s) this rank's tiles read get synthetic uint8 data
+    vol = np.zeros((1,) + tuple(vol_sp), dtype=np.uint8)
+    for z_t in sorted(set(t[0] for t in mine)):
+        z0, z1 = z_t * int(prob_sh[0]), min(vol_sp[0], z_t * int(prob_sh[0]) + int(tile_sh[0]))
+        vol[0, z0:z1] = np.random.RandomState(spec['seed'] * 1000 + z_t).randint(0, 256, vol[0, z0:z1].shape, dtype=np.uint8)
+    as_u8 = spec['uint8_out']
+    # output buffer: only the rows this rank writes are touched
+    out = np.zeros([node.shape['f']] + [int(v) for v in pred_sh], dtype=np.uint8 if as_u8 else np.float32)
+
+    def placed_voxels(ts):
+        n = 0
+        for t in ts:
+            n += int(np.prod([min(int(prob_sh[i]), int(pred_sh[i]) - t[i] * int(prob_sh[i])) for i in range(3)]))
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up through the public API (plan build, CUDA-graph capture) ---------------------------------------
+    dense.predict_dense(node, vol, as_uint8=as_u8, tile_range=(lo, lo + 1), out=out)
+    runner = dense._TileRunner(node, as_u8, True)
+    h = runner.h
+    n_in = runner.dev_u8.numel()
+
+    def device_tile():
+        s = h.stream()
+        h.call('e2_u8_to_f32', _lib.ptr(runner.dev_u8), runner.t_in.ptr(), n_in, C.c_float(255.0), s)
+        runner.plan.execute()
+        h.call('e2_ndhwc_to_ncdhw', C.byref(runner.out.desc), runner.out.ptr(), _lib.ptr(runner.out_ncdhw), s)
+        if as_u8:
+            h.call('e2_f32_to_u8', _lib.ptr(runner.out_ncdhw), _lib.ptr(runner.out_u8), runner.out_ncdhw.numel(),
+                   C.c_float(255.0), s)
+
+    # ---- value: the tile already resident in HBM (full tile of random uint8) ------------------------------------
+    runner.dev_u8.copy_(torch.randint(0, 256, runner.in_shape, dtype=torch.uint8))
+    before = h.launches
+    device_tile()                                   # the plan replays its CUDA graph: only the boundary kernels count here
+    torch.cuda.synchronize()
+    edge = h.launches - before
+    before = h.launches
+    runner.plan.pack()
+    packs = h.launches - before
+    launches_per_tile = edge + runner.plan.launches_per_step() - packs     # eager pass of the launch list, counted by the library
+    for _ in range(W):
+        device_tile()
+    barrier()
+    sampler.mark_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        device_tile()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    # ---- e2e: Node.predict_dense on the host volume (uint8 in over PCIe, probabilities back, host-side assembly) ----
+    barrier()
+    t0 = time.perf_counter()
+    _, st = dense.predict_dense(node, vol, as_uint8=as_u8, tile_range=(lo, hi), out=out, return_stats=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    vox_tile = float(np.prod(prob_sh))
+    dev_vox, e2e_vox, n_done = vox_tile * K, float(placed_voxels(mine)), float(len(mine))
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(tt[0]), float(tt[1])
+        ss = torch.tensor([dev_vox, e2e_vox, n_done], device='cuda', dtype=torch.float64)
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        dev_vox, e2e_vox, n_done = float(ss[0]), float(ss[1]), float(ss[2])
+    if rank != 0:
+        _finish(dist, world, model)
+        return 0
+    peaks = load_peaks()
+    prof = runner.plan.profile(repeats=3)
+    tile_ms = sum(p[4] for p in prof)
+    fam = {}
+    for label, kind, flops, nbytes, ms in prof:
+        f = fam.setdefault(label.split(':')[0], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        f['ms'] += ms
+        f['flops'] += flops if kind == 'tensor' else 0.0
+        f['bytes'] += nbytes
+        f['n'] += 1
+    top = max(fam, key=lambda k: fam[k]['ms'])
+    tf = fam[top]
+    tensor_peak = peaks['bf16'] / 2.0
+    ach = tf['flops'] / (tf['ms'] * 1e-3) / 1e12
+    roof = dict(bound='tensor', kernel=top, achieved=ach, peak=tensor_peak, unit='TFLOP/s', frac=ach / tensor_peak, traffic=None,
+                launches=tf['n'], avg_launch_ms=tf['ms'] / tf['n'], share_of_step=tf['ms'] / tile_ms,
+                peak_source='%s cuBLAS bf16 %.1f TFLOP/s (burst) / 2 for TF32' % (peaks['source'], peaks['bf16']))
+    if 'mfp_fwd' in fam:
+        m = fam['mfp_fwd']
+        gbs = m['bytes'] / (m['ms'] * 1e-3) / 1e9
+        roof['mfp_fwd'] = dict(bound='hbm', achieved=gbs, peak=peaks['hbm'], unit='GB/s', frac=gbs / peaks['hbm'],
+                               launches=m['n'], ms=m['ms'], share_of_step=m['ms'] / tile_ms)
+    if args.profile_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        json.dump(dict(tile_ms_eager=tile_ms, families=fam,
+                       launches=[dict(label=p[0], kind=p[1], flops=p[2], bytes=p[3], ms=p[4]) for p in prof]),
+                  open(args.profile_out, 'w'), indent=1)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_dense_reference(spec, 1, budget_s=30.0)
+        cpu = dict(value=r['value'], unit='voxels/s', cores=r['cores'], kind=r['kind'], sample=r['sample'])
+    tiles_e2e = int(n_done)
+    line = dict(metric='predict_dense voxels/sec', value=dev_vox / (dev_ms * 1e-3), unit='voxels/s', n_gpus=world, steps=K,
+                warmup=W, ms_per_step=dev_ms / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=e2cfg.compute, data='synthetic', config=config, roofline=roof, cpu_baseline=cpu,
+                e2e=dict(value=e2e_vox / e2e_s, unit='voxels/s', h2d_bytes_per_step=st['h2d_bytes'] / max(len(mine), 1),
+                         d2h_bytes_per_step=st['d2h_bytes'] / max(len(mine), 1), seconds=e2e_s, tiles=tiles_e2e,
+                         tiles_total=len(tiles), tiles_per_rank=len(mine),
+                         api='Node.predict_dense(raw_img uint8 host array) -> host array'),
+                gpu_launches=int(launches_per_tile * K), clocks=clocks, tile_output_voxels=[int(v) for v in prob_sh],
+                cuda_graph=runner.plan._graph is not None)
+    print(json.dumps(line))
+    _finish(dist, world, model)
+    return 0
+
+
 def _finish(dist, world, model=None):
     """Orderly teardown, so that interpreter exit hooks run: drop the CUDA graphs (they reference the NCCL
     communicators and the streams), drain the device, destroy the process group, return normally."""
@@ -320,7 +524,10 @@ def _finish(dist, world, model=None):
     sys.stdout.flush()
     sys.stderr.flush()
     if model is not None:
-        for plan in list(getattr(model, '_train_plans', {}).values()) + list(getattr(model, '_ext_plans', {}).values()):
+        plans = list(getattr(model, '_train_plans', {}).values()) + list(getattr(model, '_ext_plans', {}).values())
+        for n in getattr(model, 'nodes', {}).values():
+            plans += list(getattr(n, '_plans', {}).values())
+        for plan in plans:
             plan.release_graphs()
     gc.collect()
     torch.cuda.synchronize()

@@ -716,6 +716,7 @@ extern "C" int e2_conv3d_workspace_size(const e2_conv_desc* d, size_t* bytes) {
     conv_wgrad_problem(d, dummy, dummy, dummy, &g);
     if (e2_wgrad_halo_tc_ok(&fake, g)) *bytes = e2_wgrad_halo_workspace_bytes(sm_count, g);
     else if (e2_reduce_gemm_tc_ok(&fake, g)) *bytes = e2_reduce_gemm_tc_workspace_bytes(sm_count, g);
+    if (e2_wgrad_zs_tc_ok(&fake, g)) *bytes = std::max(*bytes, e2_wgrad_zs_workspace_bytes(sm_count, g));
     // forward / dgrad on the tap kernel: split-K partial tiles for layers with few output positions
     GatherGemm f, b;
     conv_fwd_problem(d, dummy, dummy, nullptr, dummy, &f);
@@ -790,6 +791,9 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
     rc = e2_launch_conv_c1_wgrad_line(h, g, s);
   else if (d->x.c == 1 && d->kz * d->kx * d->ky <= 64)
     rc = e2_launch_conv_c1_wgrad(h, g, s);
+  else if (d->compute == E2_COMPUTE_TF32 && ws && !(reinterpret_cast<uintptr_t>(ws) & 15) && e2_wgrad_zs_tc_ok(h, g) &&
+           ws_bytes >= e2_wgrad_zs_workspace_bytes(h->sm_count, g))
+    rc = e2_launch_wgrad_zs_tc(h, g, ws, ws_bytes, db, &db_done, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_wgrad_halo_tc_ok(h, g))
     rc = e2_launch_wgrad_halo_tc(h, g, ws, ws_bytes, db, &db_done, s);
   else if (d->compute == E2_COMPUTE_TF32 && e2_reduce_gemm_tc_ok(h, g))

@@ -85,3 +85,10 @@ bool e2_wgrad_halo_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_wgrad_halo_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
                             cudaStream_t s);
 size_t e2_wgrad_halo_workspace_bytes(int sm_count, const ReduceGemm& g);
+
+// z-taps stacked along MMA N (e2_wgrad_zs_tc.cu): for few dy channels (R <= 64), where the halo kernel's N = R MMA
+// is operand-fetch-bound.  Needs the workspace (partial tiles + deterministic reduce).
+bool e2_wgrad_zs_tc_ok(const e2_handle* h, const ReduceGemm& g);
+int e2_launch_wgrad_zs_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
+                          cudaStream_t s);
+size_t e2_wgrad_zs_workspace_bytes(int sm_count, const ReduceGemm& g);

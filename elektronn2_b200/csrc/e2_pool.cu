@@ -3,6 +3,7 @@
 // All tensors are channels-last; one thread owns V consecutive channels of one output
 // position, so a warp reads/writes 32*V contiguous floats (V=4: 512 B) per window tap.
 #include <initializer_list>
+#include <stdlib.h>
 #include "e2_common.cuh"
 
 template <int V>
@@ -375,14 +376,19 @@ template <int V>
 __global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, E2FastDiv dcv, const float* __restrict__ x,
                                                  const float* __restrict__ bias, float* __restrict__ y,
                                                  int* __restrict__ amax) {
-  // one block per output row (fragment, zo, xo), see k_maxpool_fwd
+  // one block per output row (fragment, zo, xo), see k_maxpool_fwd.  The fragment offset is the FASTEST block
+  // coordinate: the prod(p) blocks that read the same input rows are neighbours in launch order, so those rows cross
+  // HBM once and are shared through L2 (fragment-major order re-read the input prod(p) times: 1.4 TB/s algorithmic)
   const int cv = (p.C + V - 1) / V;
+  const int nfr = p.pz * p.px * p.py;
   int r = blockIdx.x;
+  const int off = r % nfr;
+  r /= nfr;
   const int xo = r % p.Xo;
   r /= p.Xo;
   const int zo = r % p.Zo;
-  const int fr = r / p.Zo;
-  const int n = fr % p.n, off = fr / p.n;
+  const int n = r / p.Zo;
+  const int fr = off * p.n + n;
   const int iy = off % p.py, ix = (off / p.py) % p.px, iz = off / (p.py * p.px);
   const int rowlen = p.Yo * cv;
   const float* xn = x + (int64_t)n * p.Z * p.X * p.Y * p.xp;
@@ -427,6 +433,111 @@ __global__ void __launch_bounds__(256) k_mfp_fwd(PoolP p, E2FastDiv dcv, const f
     o.store(y + oofs);
     if (amax) oi.store(amax + oofs);
   }
+}
+
+// Shared-memory form of the forward pass.  k_mfp_fwd above launches one block per OUTPUT row, fragment-major: the
+// prod(p) fragments read the same input rows at launch positions far apart, so for a tensor larger than L2 every input
+// byte crosses HBM prod(p) times (measured 1.4 - 2.4 TB/s of algorithmic traffic on the dense-prediction tile).
+// Here a block owns the outputs (zo, xo, y chunk) of ALL fragments: it stages the (2pz-1) x (2px-1) input rows those
+// windows touch once (coalesced float4), computes every fragment's maxima from shared memory and writes each
+// fragment row with full-line stores.  Neighbouring blocks share input rows through L2 (adjacent in launch order).
+struct MfpTile {
+  int rows_z, rows_x;      // staged input rows: 2pz-1, 2px-1
+  int yc, n_chunks;        // output positions per fragment and chunk, chunks per row
+  int in_pos;              // staged positions per row: yc*py + py - 1
+};
+
+__global__ void __launch_bounds__(256) k_mfp_fwd_tile(PoolP p, MfpTile m, E2FastDiv dcv, const float* __restrict__ x,
+                                                      const float* __restrict__ bias, float* __restrict__ y,
+                                                      int* __restrict__ amax) {
+  extern __shared__ float4 tile[];                 // [rows_z*rows_x][in_pos][cv]
+  const int cv = (p.C + 3) / 4;
+  int b = blockIdx.x;
+  const int ch = b % m.n_chunks;
+  b /= m.n_chunks;
+  const int xo = b % p.Xo;
+  b /= p.Xo;
+  const int zo = b % p.Zo;
+  const int n = b / p.Zo;
+  const int yo0 = ch * m.yc;
+  const int nyo = min(m.yc, p.Yo - yo0);           // output positions of this chunk
+  const int y_in0 = yo0 * p.py;
+  const int npos = nyo * p.py + p.py - 1;          // input positions needed (<= in_pos, inside the row by the MFP rule)
+  const int nrows = m.rows_z * m.rows_x;
+  const float* xn = x + (int64_t)n * p.Z * p.X * p.Y * p.xp;
+  // ---- stage: a row segment is npos * cv consecutive float4 in HBM (pitch == 4 * cv on this path)
+  const int per_row = npos * cv;
+  for (int r = 0; r < nrows; ++r) {
+    const int rz = r / m.rows_x, rx = r - rz * m.rows_x;
+    const int64_t lin = ((int64_t)(zo * p.pz + rz) * p.X + xo * p.px + rx) * p.Y + y_in0;
+    const float4* src = reinterpret_cast<const float4*>(xn + lin * p.xp);
+    float4* dst = tile + r * m.in_pos * cv;
+    for (int q = threadIdx.x; q < per_row; q += blockDim.x) dst[q] = __ldg(src + q);
+  }
+  __syncthreads();
+  // ---- compute: for each fragment offset, item = (yo, channel group), channel group fastest
+  const int nfr = p.pz * p.px * p.py;
+  const int per_frag = nyo * cv;
+  for (int off = 0; off < nfr; ++off) {
+    const int iy = off % p.py, ix = (off / p.py) % p.px, iz = off / (p.py * p.px);
+    const int fr = off * p.n + n;
+    const int64_t obase = ((((int64_t)fr * p.Zo + zo) * p.Xo + xo) * p.Yo + yo0) * p.yp;
+    for (int q = threadIdx.x; q < per_frag; q += blockDim.x) {
+      const int yl = (int)dcv.div((uint32_t)q);
+      const int c4 = q - yl * cv;
+      float best[4];
+      int bi[4];
+      bool first = true;
+      for (int dz = 0; dz < p.pz; ++dz)
+        for (int dx = 0; dx < p.px; ++dx) {
+          const int r = (iz + dz) * m.rows_x + ix + dx;
+          const int lin0 = ((zo * p.pz + iz + dz) * p.X + xo * p.px + ix + dx) * p.Y + y_in0 + iy + yl * p.py;
+          const float4* src = tile + (r * m.in_pos + iy + yl * p.py) * cv + c4;
+          for (int dy = 0; dy < p.py; ++dy) {
+            const float4 v4 = src[dy * cv];
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (first || v[j] > best[j]) best[j] = v[j], bi[j] = lin0 + dy;     // strict '>': FIRST maximum in scan order
+            first = false;
+          }
+        }
+      const int c = c4 * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float r2 = best[j];
+        if (c + j < p.C) {
+          if (p.has_bias) r2 += __ldg(bias + c + j);
+          r2 = e2_apply_act(r2, p.act);
+          o[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
+        } else {
+          o[j] = 0.f;
+        }
+      }
+      const int64_t oofs = obase + (int64_t)q * 4;      // (yl * cv + c4) * 4 == yl * pitch + c
+      *reinterpret_cast<float4*>(y + oofs) = make_float4(o[0], o[1], o[2], o[3]);
+      if (amax) *reinterpret_cast<int4*>(amax + oofs) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+    }
+  }
+}
+
+// plan the shared-memory tile; false: rows too long even for one output position per chunk
+static bool plan_mfp_tile(const PoolP& p, MfpTile* m, size_t* smem) {
+  const int cv = (p.C + 3) / 4;
+  m->rows_z = 2 * p.pz - 1, m->rows_x = 2 * p.px - 1;
+  const size_t budget = 64 * 1024;                 // <= 3 blocks per SM
+  const size_t per_pos = (size_t)m->rows_z * m->rows_x * cv * 16;
+  const int64_t max_pos = (int64_t)(budget / per_pos);
+  int64_t yc = (max_pos - (p.py - 1)) / p.py;
+  if (yc < 1) return false;
+  if (yc > p.Yo) yc = p.Yo;
+  m->n_chunks = (int)((p.Yo + yc - 1) / yc);
+  yc = (p.Yo + m->n_chunks - 1) / m->n_chunks;     // even chunks
+  m->yc = (int)yc;
+  m->in_pos = m->yc * p.py + p.py - 1;
+  *smem = per_pos * m->in_pos;
+  return true;
 }
 
 // Gather form (no atomics, deterministic): each input element checks the prod(p) windows
@@ -509,7 +620,17 @@ extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, co
   E2_REQUIRE(h, x && y && (!d->has_bias || bias), "mfp_fwd: null pointer");
   const int64_t rows = (int64_t)p.n * p.pz * p.px * p.py * p.Zo * p.Xo;
   E2_REQUIRE(h, rows < (1ll << 31), "mfp_fwd: too many rows");
-  if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
+  MfpTile mt;
+  size_t smem = 0;
+  static const bool use_tile = getenv("E2_MFP_TILE") != nullptr;      // A/B switch for profiling (default: row kernel)
+  if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp) && use_tile &&
+      p.xp == 4 * ((p.C + 3) / 4) && p.yp == p.xp && plan_mfp_tile(p, &mt, &smem) && (int64_t)p.n * p.Zo * p.Xo * mt.n_chunks < (1ll << 31)) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_mfp_fwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return e2_fail(h, E2_ERR_CUDA, "mfp_fwd: cudaFuncSetAttribute(max dynamic smem) failed");
+    k_mfp_fwd_tile<<<(unsigned)((int64_t)p.n * p.Zo * p.Xo * mt.n_chunks), 256, smem, (cudaStream_t)stream>>>(
+        p, mt, e2_fastdiv((p.C + 3) / 4, (uint64_t)mt.yc * ((p.C + 3) / 4)), x, bias, y, argmax);
+  } else if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
     const int rowlen = p.Yo * ((p.C + 3) / 4);
     k_mfp_fwd<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv((p.C + 3) / 4, rowlen), x, bias, y, argmax);
   } else {

@@ -35,6 +35,10 @@ def init_from_env(backend=None):
         if backend == 'nccl':
             torch.cuda.set_device(local)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('E2_NCCL_MAX_CTAS'):
+            # every NCCL channel is a CTA that occupies an SM for the duration of a collective; the persistent conv
+            # kernels size their grids to the SM count, so SMs taken by NCCL cost them a second wave
+            os.environ.setdefault('NCCL_MAX_CTAS', os.environ['E2_NCCL_MAX_CTAS'])
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 
@@ -61,6 +65,7 @@ class DataParallel(object):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.bucket_floats = int(bucket_mb * 1024 * 1024 / 4)
+        self.tail_entries = int(os.environ.get('E2_DP_TAIL', '4'))   # layers (from the input side) with a bucket of their own
         self.overlap = overlap
         self.comm_stream = None
         self.producer_streams = []            # set by the executor: the streams its wgrad kernels run on
@@ -93,14 +98,25 @@ class DataParallel(object):
         those buckets are reduced)."""
         if getattr(self, '_buckets', None) is None or getattr(self, '_split', None) != split:
             self._split = split
-            # weight region in buckets, the (tiny) bias tail as the last bucket
+            # weight region in buckets; the layers nearest the input -- whose gradients the backward pass produces
+            # LAST -- get a bucket each, so that when the final wgrad kernel ends only its own few KB (merged with the
+            # bias region, which is contiguous with it) are still to be reduced: the exposed tail of the step is one
+            # latency-bound collective instead of a multi-MB one
             w_entries = [e for e in store.entries if e[2] < store.n_reg]
             self._buckets = [(s, e) for s, e, _ in bucket_ranges(w_entries, store.n_reg, self.bucket_floats)]
+            cuts = set()
             if split:
-                self._buckets = [r for (s, e) in self._buckets
-                                 for r in ([(s, split), (split, e)] if s < split < e else [(s, e)])]
+                cuts.add(int(split))
+            for e in w_entries[-self.tail_entries:] if self.tail_entries else []:
+                cuts.add(int(e[2]))
+            for c in sorted(cuts):
+                self._buckets = [r for (s, e) in self._buckets for r in ([(s, c), (c, e)] if s < c < e else [(s, e)])]
             if store.total > store.n_reg:
-                self._buckets.append((store.n_reg, store.total))
+                if self._buckets and self.tail_entries:
+                    s_last, _ = self._buckets.pop()
+                    self._buckets.append((s_last, store.total))
+                else:
+                    self._buckets.append((store.n_reg, store.total))
             if torch.cuda.is_available() and store.G.is_cuda:
                 self.comm_stream = torch.cuda.Stream(device=store.G.device)
         self._next, self._works = 0, []

@@ -154,3 +154,31 @@ def time_training(net_builder, in_sp, steps=1, warmup=0, threads=None, direct=Fa
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return dict(seconds_per_step=dt, voxels_per_s=float(np.prod(ish)) / dt, cores=torch.get_num_threads(),
                 loss=loss, input_shape=ish)
+
+
+def time_dense_tile(net_builder, in_sp, strides, threads=None, seed=0):
+    """Seconds for ONE tile of ``Node._predict_densetile`` on the host cores, the way the reference does it without
+    MFP (node_basic.py:832-856): prod(strides) forward passes of the strided net on shifted crops of a
+    (patch + strides - 1) tile, interleaved into the dense output.  Returns dict(seconds, voxels_per_s, cores)."""
+    if threads:
+        torch.set_num_threads(int(threads))
+    net = net_builder(tuple(in_sp))
+    tn = TorchNet(net)
+    osh = net.nodes[-1].sh
+    st = [int(s) for s in strides]
+    tile = [p + s - 1 for p, s in zip(in_sp, st)]
+    r = np.random.RandomState(seed)
+    raw = torch.tensor(r.rand(1, 1, *tile).astype(np.float32))
+    out_sp = [int(o) * s for o, s in zip(osh.spatial, st)]
+    prob = torch.zeros([2] + out_sp)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for xo in range(st[1]):
+            for yo in range(st[2]):
+                for zo in range(st[0]):
+                    cut = raw[:, :, zo:zo + in_sp[0], xo:xo + in_sp[1], yo:yo + in_sp[2]]
+                    p = torch.softmax(tn.forward(cut), 1)[0]
+                    prob[:, zo::st[0], xo::st[1], yo::st[2]] = p
+    dt = time.perf_counter() - t0
+    return dict(seconds=dt, voxels_per_s=float(np.prod(out_sp)) / dt, cores=torch.get_num_threads(),
+                out_spatial=out_sp, passes=int(np.prod(st)))

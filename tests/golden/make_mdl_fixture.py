@@ -125,9 +125,9 @@ def main():
     # the graph, written the way examples/neuro3d_lite.py writes one (positional parents, keyword options)
     rs = np.random.RandomState(12)
     spec = [
-        ('raw', 'node_basic', 'Input', [(None, 1, 9, 30, 30), 'b,f,z,x,y'], dict(name='raw'), {}),
-        ('conv', 'neural', 'Conv', ['@raw', 6, (1, 3, 3), (1, 2, 2)], dict(name='conv'),
-         dict(w=(6, 1, 1, 3, 3), b=(6,))),
+        ('raw', 'node_basic', 'Input', [(None, 1, 9, 31, 31), 'b,f,z,x,y'], dict(name='raw'), {}),
+        ('conv', 'neural', 'Conv', ['@raw', 6, (1, 4, 4), (1, 2, 2)], dict(name='conv'),
+         dict(w=(6, 1, 1, 4, 4), b=(6,))),
         ('conv1', 'neural', 'Conv', ['@conv', 8, (2, 3, 3), (2, 1, 1)], dict(name='conv1'),
          dict(w=(8, 6, 2, 3, 3), b=(8,))),
         ('conv2', 'neural', 'Conv', ['@conv1', 9, (1, 3, 3)], dict(name='conv2', activation_func='tanh'),
@@ -136,7 +136,7 @@ def main():
          dict(w=(2, 9, 1, 1, 1), b=(2,))),
         ('softmax', 'loss', 'Softmax', ['@conv3'], dict(name='softmax'), {}),
         ('target', 'node_basic', 'Input', [(None, 1, 4, 10, 10), 'b,f,z,x,y'],
-         dict(name='target', strides=np.array([2, 2, 2]), fov=np.array([3, 9, 9]), dtype='float32', hardcoded_shape=False), {}),
+         dict(name='target', strides=np.array([2, 2, 2]), fov=np.array([3, 13, 13]), dtype='float32', hardcoded_shape=False), {}),
         ('nll', 'loss', 'MultinoulliNLL', ['@softmax', '@target'], dict(name='nll', target_is_sparse=True), {}),
         ('loss', 'loss', 'AggregateLoss', ['@nll'], dict(name='loss'),
          dict(mixing_weights=None)),
@@ -176,15 +176,15 @@ def main():
     # oracle prediction with these weights (float64), for the GPU test
     from oracle import nets as onets, loss as ol
     o = onets.Net(0)
-    n = o.input((1, 1, 9, 30, 30))
-    n = o.conv(n, 6, (1, 3, 3), (1, 2, 2))
+    n = o.input((1, 1, 9, 31, 31))
+    n = o.conv(n, 6, (1, 4, 4), (1, 2, 2))
     n = o.conv(n, 8, (2, 3, 3), (2, 1, 1))
     n = o.conv(n, 9, (1, 3, 3), act='tanh')
     n = o.conv(n, 2, (1, 1, 1), act='lin')
     for (node, k), key in zip(o.param_list(), [k for k in params_out if not k.startswith('loss')]):
         assert node.params[k].shape == params_out[key].shape, (key, node.params[k].shape, params_out[key].shape)
         node.params[k] = params_out[key]
-    x = np.random.RandomState(0).rand(1, 1, 9, 30, 30).astype(np.float32)
+    x = np.random.RandomState(0).rand(1, 1, 9, 31, 31).astype(np.float32)
     probs = ol.softmax(o.forward(x), 1)
     np.savez_compressed(os.path.join(HERE, 'ref_written_small.npz'), x=x, probs=probs,
                         **dict(('p_' + k, v) for k, v in params_out.items()))

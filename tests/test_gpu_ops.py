@@ -89,6 +89,12 @@ CONV_CASES = [
     (1, 128, (4, 6, 6), 256, (3, 3, 3)),
     (1, 256, (5, 16, 16), 128, (3, 3, 3)),   # few tiles, long K: the z-stack kernel splits K over channel blocks
     (1, 200, (4, 15, 14), 72, (3, 3, 3)),    # same with ragged channel counts and edges
+    # the z-stacked wgrad kernel (e2_wgrad_zs_tc.cu: <= 64 output channels, kz >= 2, batch 1)
+    (1, 40, (7, 11, 13), 32, (3, 3, 3)),     # one r block (N = 96), second s block partial, ragged tiles
+    (1, 24, (6, 9, 9), 20, (2, 3, 3)),       # fewer than 32 output channels (clipped r block), kz = 2
+    (1, 32, (9, 12, 12), 64, (4, 4, 4)),     # kz = 4: N = 256, ky = 4 fills all four M chunks
+    (1, 48, (5, 10, 21), 64, (2, 4, 4)),     # kz = 2: N = 128
+    (1, 32, (20, 19, 25), 64, (3, 3, 3)),    # several z / x / y tiles per split, z halo across tiles
 ]
 
 

@@ -62,7 +62,9 @@ def _worker(rank, world, port, q):
     dp.broadcast_parameters(store)
     assert float(store.P.abs().max()) == 0.0                                    # rank 0's values everywhere
     dp.begin_step(store)
-    assert dp._buckets[0][0] == 0 and dp._buckets[-1] == (store.n_reg, store.total)
+    # the layer nearest the input has a bucket of its own, merged with the (contiguous) bias region
+    assert dp._buckets[0][0] == 0 and dp._buckets[-1] == (store.entries[4][2], store.total)
+    assert all(any(s == e[2] for s, _ in dp._buckets) for e in store.entries[1:5])   # E2_DP_TAIL=4: one bucket per tail layer
     assert all(a[1] == b[0] for a, b in zip(dp._buckets, dp._buckets[1:]))      # contiguous, no gaps
     launched = []
     for _, _, off, size in store.entries:
@@ -70,7 +72,7 @@ def _worker(rank, world, port, q):
             break
         dp.on_gradients_ready(off + size)      # what executor.Plan calls after each wgrad launch
         launched.append(dp._next)
-    assert launched[0] == 0 and launched[-1] >= len(dp._buckets) - 2 and sorted(launched) == launched
+    assert launched[0] <= 1 and launched[-1] == len(dp._buckets) - 1 and sorted(launched) == launched
     dp.finish_step(store)
     expect = torch.arange(store.total, dtype=torch.float32) * sum(range(1, world + 1))
     ok = bool(torch.equal(store.G, expect)) and dp.bytes_reduced == store.total * 4
