@@ -44,7 +44,7 @@ struct ZsParams {
   int tiles_total, tiles_per_split;
   float* W;
   float* ws;                 // partial tiles [split][unit][col/4][lane][4]
-  float* db_ws;              // fused bias gradient [split][rc][n_rb*32] (NULL: off)
+  float* db_ws;              // fused bias gradient [split][rc][sc*kx + j][n_rb*32] (NULL: off)
   float* db;
   int out_mode;
   uint32_t idesc;
@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(ZS_THREADS) k_wgrad_zs_tc(const __grid_constan
   const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
   const int ntiles = max(t_end - t_begin, 0);
-  const bool do_db = p.db_ws && j3 == 0 && sc == 0;
+  // fused bias gradient: every CTA of an r chunk sums its share of the dy planes (plane index mod #CTAs): the extra
+  // work is the same for all CTAs, so they keep walking the tile list in step and share the dy / x tiles through L2
+  const bool do_db = p.db_ws != nullptr;
+  const int db_grp = p.n_sc * p.kx, db_idx = sc * p.kx + j3;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmP);
@@ -173,11 +176,13 @@ __global__ void __launch_bounds__(ZS_THREADS) k_wgrad_zs_tc(const __grid_constan
       int st = 0;
       uint32_t par = 0;
       for (int ti = 0; ti < ntiles; ++ti) {
+        const int q0 = ((t_begin + ti) / (p.nty * p.ntx)) * p.TQ;
         wait_bar(&full[st], par);
         if (et < nch) {
           const uint8_t* dyb = smem + st * p.stage_bytes + p.x_stride + (size_t)(et >> 5) * p.box_bytes;
-          for (int pl = p.kz - 1; pl < p.kz - 1 + p.TQ; ++pl) {
-            const uint8_t* bx = dyb + (size_t)pl * p.n_rb * p.box_bytes;
+          for (int o = 0; o < p.TQ; ++o) {
+            if ((q0 + o) % db_grp != db_idx) continue;       // dy plane q0 + o is summed by exactly one CTA of the group
+            const uint8_t* bx = dyb + (size_t)(p.kz - 1 + o) * p.n_rb * p.box_bytes;
 #pragma unroll 8
             for (int r = 0; r < rows; ++r)
               sum += *reinterpret_cast<const float*>(bx + r * 128 + ((a ^ (uint32_t)(r & 3)) << 5) + w);
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(ZS_THREADS) k_wgrad_zs_tc(const __grid_constan
         if (et == 0) tc::mbar_arrive(&empty[st]);
         if (++st == p.stages) st = 0, par ^= 1u;
       }
-      if (et < nch) p.db_ws[((size_t)blockIdx.y * p.n_rc + rc) * nch + et] = sum;
+      if (et < nch) p.db_ws[(((size_t)blockIdx.y * p.n_rc + rc) * db_grp + db_idx) * nch + et] = sum;
     }
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
@@ -225,7 +230,9 @@ __global__ void __launch_bounds__(128) k_wgrad_zs_reduce(const ZsParams p, int u
     const int r = rc * nch + c;
     if (r >= p.R) return;
     float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += __ldcg(p.db_ws + ((size_t)sp * p.n_rc + rc) * nch + c);
+    const int grp = p.n_sc * p.kx;
+    for (int sp = 0; sp < splits; ++sp)
+      for (int gi = 0; gi < grp; ++gi) acc += __ldcg(p.db_ws + (((size_t)sp * p.n_rc + rc) * grp + gi) * nch + c);
     p.db[r] = acc;
     return;
   }
@@ -357,7 +364,7 @@ size_t e2_wgrad_zs_workspace_bytes(int sm_count, const ReduceGemm& g) {
   ZsParams p;
   int units, splits;
   if (!plan_zs(g, &p) || !plan_grid(sm_count, &p, &units, &splits)) return 0;
-  return (size_t)units * splits * p.N * 128 * sizeof(float) + (size_t)splits * p.n_rc * p.n_rb * 32 * sizeof(float);
+  return (size_t)units * splits * p.N * 128 * sizeof(float) + (size_t)splits * units * p.n_rb * 32 * sizeof(float);
 }
 
 int e2_launch_wgrad_zs_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
@@ -370,7 +377,7 @@ int e2_launch_wgrad_zs_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws
   if (!plan_zs(g, &p) || !plan_grid(h->sm_count, &p, &units, &splits))
     return e2_fail(h, E2_ERR_UNSUPPORTED, "wgrad_zs_tc: problem does not qualify");
   const size_t w_part = (size_t)units * splits * p.N * 128 * sizeof(float);
-  const size_t ws_need = w_part + (size_t)splits * p.n_rc * p.n_rb * 32 * sizeof(float);
+  const size_t ws_need = w_part + (size_t)splits * units * p.n_rb * 32 * sizeof(float);
   if (!ws || ws_bytes < ws_need || (reinterpret_cast<uintptr_t>(ws) & 15))
     return e2_fail(h, E2_ERR_WORKSPACE, "wgrad_zs_tc: needs %zu bytes of workspace", ws_need);
   p.ws = static_cast<float*>(ws);
