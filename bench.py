@@ -159,6 +159,7 @@ def main():
     ap.add_argument('--compute', default=None, choices=['tf32', 'f32'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-solo-check', action='store_true', help='N > 1: skip the per-GPU single-process timing')
     ap.add_argument('--profile-out', default=None, help='write the per-launch timing table (JSON) here')
     args = ap.parse_args()
     if args.workload in DENSE:
@@ -203,6 +204,39 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         model = examples.BUILDERS[args.workload]()
     dp = None
+    solo = None
+    if world > 1 and not args.no_solo_check:
+        # Every rank first times the SAME step on its own GPU without data parallelism (no collective, no peer to wait
+        # for): synchronous data parallelism runs at the pace of the slowest GPU of the box, so the spread of these
+        # numbers is the part of the N-GPU step that no overlap scheme can recover.
+        nm.model_manager.reset()
+        np.random.seed(2)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m0 = examples.BUILDERS[args.workload]()
+        nm.optimiser.Optimiser.setlr(5e-4), nm.optimiser.Optimiser.setwd(0.5e-4), nm.optimiser.Optimiser.setmom(0.9)
+        x0, t0_ = synthetic_batch(m0, 1000 + rank)
+        p0 = m0._train_plan(1)
+        o0 = m0.optimisers['Adam']
+        p0.feed({m0.input_node: x0, m0.target_node: t0_})
+        for _ in range(W):
+            p0.train_step(o0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            p0.train_step(o0)
+        b.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([a.elapsed_time(b) / K], device='cuda', dtype=torch.float64)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        solo = [round(float(v), 4) for v in allms]
+        p0.release_graphs()
+        del p0, m0, o0
+        nm.model_manager.reset()
+        np.random.seed(2)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = examples.BUILDERS[args.workload]()
     if world > 1:
         dp = parallel.DataParallel(model)
     nm.optimiser.Optimiser.setlr(5e-4)                  # examples/unet3d.py optimiser_params
@@ -317,6 +351,8 @@ def main():
                 e2e=dict(value=n_vox * K / (e2e_ms * 1e-3), unit='voxels/s', h2d_bytes_per_step=in_bytes,
                          d2h_bytes_per_step=16, ms_per_step=e2e_ms / K, host_buffers='page-locked numpy arrays'),
                 gpu_launches=launches_per_step * K, clocks=clocks, loss=float(loss),
+                **(dict(solo_ms_per_step_by_rank=solo, allreduce='copy engines over symmetric peer memory (E2_DP_CE=1)'
+                        if getattr(dp, 'use_ce', False) else 'NCCL') if world > 1 else {}),
                 cuda_graph=bool(plan._opt_graphs) or plan._graph is not None)
     print(json.dumps(line))
     _finish(dist, world, model)

@@ -72,7 +72,7 @@ def _try_capture(fn, device, what):
 class ParamStore(object):
     """Flat device buffers for all trainable parameters of a model."""
 
-    def __init__(self, named_params, device):
+    def __init__(self, named_params, device, grad_alloc=None):
         # reverse graph order inside each region; weights (regularised) first, then the rest
         plist = list(named_params)[::-1]
         seen = {}
@@ -115,7 +115,9 @@ class ParamStore(object):
         self.total = off
         self.device = device
         self.P = torch.zeros(self.total, dtype=torch.float32, device=device)
-        self.G = torch.zeros(self.total, dtype=torch.float32, device=device)
+        # grad_alloc: data parallelism may want the gradient buffer in peer-mapped (symmetric) memory
+        self.G = grad_alloc(self.total, device) if grad_alloc is not None else \
+            torch.zeros(self.total, dtype=torch.float32, device=device)
         self.version = 0
         for k, p, o, size in self.entries:
             view = self.P[o:o + size].view(*p.shape)

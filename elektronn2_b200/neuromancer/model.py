@@ -103,7 +103,9 @@ class Model(object):
     def _ensure_param_store(self, device):
         if self._store is None:
             from .executor import ParamStore
-            self._store = ParamStore(self._all_named_params().items(), device)
+            dp = self.data_parallel
+            alloc = dp.alloc_gradient_buffer if (dp is not None and getattr(dp, 'use_ce', False)) else None
+            self._store = ParamStore(self._all_named_params().items(), device, grad_alloc=alloc)
         return self._store
 
     def get_param_values(self, skip_const=True, as_list=False):

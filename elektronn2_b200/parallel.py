@@ -57,6 +57,16 @@ def bucket_ranges(entries, total, bucket_floats):
     return out
 
 
+class _EventWork(object):
+    """``Work``-like handle of a collective that is just stream-ordered work on the comm stream."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class DataParallel(object):
     """Gradient all-reduce for a ``neuromancer.Model``."""
 
@@ -72,6 +82,11 @@ class DataParallel(object):
         self.graph_ok = os.environ.get('E2_DP_GRAPH', '1') != '0'   # capture the step incl. the collectives
         model.data_parallel = self
         self.bytes_reduced = 0
+        self.trace = None                     # list of (start, end, start_event, end_event) per bucket when tracing (eager steps only)
+        # E2_DP_CE=1: all-reduce over NVSwitch peer memory with the COPY ENGINES (reduce-scatter by pulling, local sum,
+        # all-gather by pulling; see _ce_allreduce) instead of NCCL's SM-resident kernels
+        self.use_ce = os.environ.get('E2_DP_CE', '0') == '1' and self.world > 1
+        self._hdl = self._stage = None
 
     def broadcast_parameters(self, store):
         """Rank 0's weights everywhere (identical init is also given by the shared seed)."""
@@ -82,11 +97,59 @@ class DataParallel(object):
     def grad_scale(self):
         return 1.0 / self.world
 
+    # -- copy-engine all-reduce over symmetric (peer-mapped) memory --------------------------------------------
+    def alloc_gradient_buffer(self, numel, device):
+        """The flat gradient buffer.  With E2_DP_CE it is allocated as symmetric memory and exchanged with the peers
+        (torch.distributed._symmetric_memory: one VMM allocation per rank, mapped into every rank's address space over
+        NVLink), so that a rank can read any peer's gradients with a plain device-to-device copy."""
+        if not self.use_ce:
+            return torch.zeros(numel, dtype=torch.float32, device=device)
+        import torch.distributed._symmetric_memory as symm_mem
+        g = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        g.zero_()
+        self._hdl = symm_mem.rendezvous(g, dist.group.WORLD.group_name)
+        self._numel = numel
+        return g
+
+    def _ce_allreduce(self, G, s, e):
+        """Sum G[s:e] over the ranks, on the current (comm) stream, without occupying SMs for the transfers.
+
+        rank r owns slice r of the bucket: it PULLS that slice from every peer's buffer (copy engines, NVLink 5 through
+        the NVSwitch: every peer at full bandwidth), adds the world-1 staged copies to its own (one small kernel; each
+        element is summed by exactly one rank in a fixed order, so all ranks end up bit-identical), then pulls the
+        other ranks' finished slices.  Three peer barriers (signal pads in peer memory) order the phases:
+        gradients ready -> slices summed -> everybody has read everything (the buffer may be overwritten)."""
+        hdl, world, rank = self._hdl, self.world, self.rank
+        n = e - s
+        per = ((n + world - 1) // world + 3) // 4 * 4
+        lo = [min(e, s + r * per) for r in range(world)]
+        hi = [min(e, s + (r + 1) * per) for r in range(world)]
+        if self._stage is None or self._stage.shape[1] < per:
+            self._stage = torch.empty((world - 1, per), dtype=torch.float32, device=G.device)
+        mine = hi[rank] - lo[rank]
+        hdl.barrier(channel=0, timeout_ms=20000)
+        if mine > 0:
+            for step in range(1, world):
+                peer = (rank + step) % world
+                src = hdl.get_buffer(peer, (mine,), torch.float32, lo[rank])
+                self._stage[step - 1, :mine].copy_(src, non_blocking=True)
+            G[lo[rank]:hi[rank]].add_(self._stage[:world - 1, :mine].sum(dim=0))
+        hdl.barrier(channel=1, timeout_ms=20000)
+        for step in range(1, world):
+            peer = (rank + step) % world
+            cnt = hi[peer] - lo[peer]
+            if cnt > 0:
+                G[lo[peer]:hi[peer]].copy_(hdl.get_buffer(peer, (cnt,), torch.float32, lo[peer]), non_blocking=True)
+        hdl.barrier(channel=2, timeout_ms=20000)
+
     def allreduce_gradients(self, store):
         """Simple form: one collective over the whole flat buffer on the current stream.
         Used when the step did not go through ``begin_step`` / ``finish_step``."""
         if self.world > 1 and not self._step_reduced:
-            dist.all_reduce(store.G, op=dist.ReduceOp.SUM)
+            if self.use_ce:
+                self._ce_allreduce(store.G, 0, store.total)
+            else:
+                dist.all_reduce(store.G, op=dist.ReduceOp.SUM)
             self.bytes_reduced += store.G.numel() * 4
         self._step_reduced = False
 
@@ -134,7 +197,20 @@ class DataParallel(object):
             with torch.cuda.stream(self.comm_stream):
                 for e2 in evs:
                     self.comm_stream.wait_event(e2)
-                self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+                if self.trace is not None:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record(self.comm_stream)
+                if self.use_ce:
+                    self._ce_allreduce(store.G, s, e)
+                    done = torch.cuda.Event()
+                    done.record(self.comm_stream)
+                    self._works.append(_EventWork(done))
+                else:
+                    self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+                if self.trace is not None:
+                    self._works[-1].wait()        # stream-ordered on the comm stream
+                    t1.record(self.comm_stream)
+                    self.trace.append((s, e, t0, t1))
         else:
             self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
         self.bytes_reduced += (e - s) * 4

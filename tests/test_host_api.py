@@ -362,3 +362,52 @@ def test_modelload_reads_a_file_written_by_the_reference_serialiser():
     # the stream carries the reference's module paths, none of this package's
     raw = open(os.path.join(golden, 'ref_written_small.mdl'), 'rb').read()
     assert b'elektronn2.neuromancer.graphmanager' in raw and b'elektronn2_b200' not in raw
+
+
+def test_f4_nodes_parameters_and_shapes():
+    """SURVEY 8f-4 on the host: parameter registration of batch norm / prelu (neural.py:146-242), pooling modes
+    (:1448-1452), the 2-D form of examples/mnist.py:35-37, and the weight-decay regions of the flat buffer."""
+    import torch
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200.neuromancer.executor import ParamStore
+    np.random.seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        inp = nm.Input((None, 1, 8, 20, 20), 'b,f,z,x,y', name='raw')
+        c0 = nm.Conv(inp, 8, (1, 3, 3), (1, 2, 2), batch_normalisation='train')
+        c1 = nm.Conv(c0, 12, (3, 3, 3), activation_func='prelu')
+        p1 = nm.Pool(c1, (2, 1, 1), mode='average')
+        c2 = nm.Conv(p1, 6, (1, 3, 3), batch_normalisation='predict', gamma=np.full(6, 2, np.float32),
+                     mean=np.zeros(6, np.float32), std=np.ones(6, np.float32))
+    assert list(c0.params) == ['w', 'b', 'gamma', 'mean', 'std']
+    assert c0.gamma.apply_train and c0.gamma.apply_reg == 3.0 and not c0.mean.apply_train and not c0.std.apply_train
+    assert np.all(c0.gamma.get_value() == 1) and np.all(c0.mean.get_value() == 0) and np.all(c0.std.get_value() == 1)
+    assert c1.b.shape == (12, 2) and np.all(c1.b.get_value()[:, 1] == 1) and np.allclose(c1.b.get_value()[:, 0], 1 / 27.)
+    assert p1.mode == 'average_inc_pad' and p1.shape.spatial_shape == [3, 7, 7]
+    assert not c2.gamma.apply_train and np.all(c2.gamma.get_value() == 2)
+    assert c0.unfused_epilogue and c1.unfused_epilogue and c2.unfused_epilogue
+    with pytest.raises(ValueError):
+        nm.Pool(c1, (2, 1, 1), mode='median')
+    with pytest.raises(ValueError):
+        nm.Conv(inp, 4, (1, 3, 3), batch_normalisation='train', mean=np.zeros(4, np.float32))
+    with pytest.raises(NotImplementedError):
+        nm.Conv(inp, 4, (1, 3, 3), batch_normalisation='fadeout')
+    with pytest.raises(NotImplementedError, match='neural.py:650'):
+        nm.Conv(inp, 4, (1, 3, 3), activation_func='maxout 2')
+    # flat parameter buffer: plain weights first (decay x1), then the gamma region (x3), then the undecayed rest
+    named = [('%s_%s' % (n.name, k), p) for n in (c0, c1, c2) for k, p in n.params.items() if p.apply_train]
+    store = ParamStore(named, torch.device('cpu'))
+    assert [m for _, _, m in store.regions] == [1.0, 3.0, 0.0]
+    assert store.regions[0][:2] == (0, store.n_reg) and store.regions[1][1] == 8
+    assert sum(c for _, c, _ in store.regions) == store.total
+    with pytest.raises(NotImplementedError, match='shared'):
+        ParamStore(named + [('again', c1.w)], torch.device('cpu'))
+    # 2-D: the conv stack of examples/mnist.py:35-37
+    nm.model_manager.reset()
+    with contextlib.redirect_stdout(io.StringIO()):
+        inp2 = nm.Input((None, 1, 26, 26), 'b,f,y,x', name='raw')
+        o = nm.Conv(inp2, 12, (3, 3), (2, 2), batch_normalisation='train')
+        o = nm.Conv(o, 36, (3, 3), (2, 2), batch_normalisation='train')
+        o = nm.Conv(o, 64, (3, 3), (1, 1), batch_normalisation='train')
+    assert o.shape.shape == [None, 64, 3, 3] and o.conv_dim == 2 and o.w_sh == [64, 36, 3, 3]
+    with pytest.raises(ValueError):
+        nm.Conv(inp2, 4, (3, 3, 3))
