@@ -209,6 +209,9 @@ def main():
         # Every rank first times the SAME step on its own GPU without data parallelism (no collective, no peer to wait
         # for): synchronous data parallelism runs at the pace of the slowest GPU of the box, so the spread of these
         # numbers is the part of the N-GPU step that no overlap scheme can recover.
+        if os.environ.get('E2_SOLO_AFTER_NCCL_INIT'):      # experiment: is an initialised (idle) communicator felt?
+            dist.all_reduce(torch.zeros(1 << 20, device='cuda'))
+            torch.cuda.synchronize()
         nm.model_manager.reset()
         np.random.seed(2)
         with contextlib.redirect_stdout(io.StringIO()):

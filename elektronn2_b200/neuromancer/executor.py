@@ -781,6 +781,9 @@ class Plan(object):
             ok = all(self.bwd_ops[i].param_end <= S for i in wg[:-keep]) and S <= self.store.n_reg
             if not ok:
                 S, j = 0, None
+        if j is not None:
+            # E2_EARLY_DELAY: launch the early update that many backward ops later than the first moment it could run
+            j = min(j + int(os.environ.get('E2_EARLY_DELAY', '0')), len(self.bwd_ops) - 1)
         off = {op: n.w._offset for n, op in self.conv_ops.items()}
         early = [op for op in self.pack_ops if off.get(op, 1 << 62) < S]
         late = [op for op in self.pack_ops if op not in early]

@@ -70,12 +70,18 @@ class _EventWork(object):
 class DataParallel(object):
     """Gradient all-reduce for a ``neuromancer.Model``."""
 
-    def __init__(self, model, bucket_mb=25.0, overlap=True):
+    def __init__(self, model, bucket_mb=1024.0, overlap=True):
         self.model = model
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
+        bucket_mb = float(os.environ.get('E2_DP_BUCKET_MB', bucket_mb))
         self.bucket_floats = int(bucket_mb * 1024 * 1024 / 4)
-        self.tail_entries = int(os.environ.get('E2_DP_TAIL', '4'))   # layers (from the input side) with a bucket of their own
+        self._nocomm = os.environ.get('E2_DP_NOCOMM') == '1'      # experiments only: bookkeeping without the collectives
+        # Measured on 2 and 8 B200 (DESIGN.md 7b): every additional bucket costs the step ~0.03 ms whatever carries it
+        # (NCCL or the copy engines), and the backward pass is long enough behind the split offset to hide one large
+        # collective -- so by default there is ONE bucket for everything below the fused optimiser's split offset and
+        # one bucket per layer for the E2_DP_TAIL layers nearest the input (their gradients are produced last).
+        self.tail_entries = int(os.environ.get('E2_DP_TAIL', '2'))
         self.overlap = overlap
         self.comm_stream = None
         self.producer_streams = []            # set by the executor: the streams its wgrad kernels run on
@@ -185,6 +191,8 @@ class DataParallel(object):
         self._next, self._works = 0, []
 
     def _launch_bucket(self, store, s, e):
+        if self._nocomm:
+            return
         view = store.G[s:e]
         if self.comm_stream is not None and self.overlap:
             ev = torch.cuda.Event()

@@ -64,7 +64,7 @@ def _worker(rank, world, port, q):
     dp.begin_step(store)
     # the layer nearest the input has a bucket of its own, merged with the (contiguous) bias region
     assert dp._buckets[0][0] == 0 and dp._buckets[-1] == (store.entries[4][2], store.total)
-    assert all(any(s == e[2] for s, _ in dp._buckets) for e in store.entries[1:5])   # E2_DP_TAIL=4: one bucket per tail layer
+    assert all(any(s == e[2] for s, _ in dp._buckets) for e in store.entries[3:5])   # E2_DP_TAIL=2: one bucket per tail layer
     assert all(a[1] == b[0] for a, b in zip(dp._buckets, dp._buckets[1:]))      # contiguous, no gaps
     launched = []
     for _, _, off, size in store.entries:
