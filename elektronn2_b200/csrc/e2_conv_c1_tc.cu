@@ -50,7 +50,9 @@ struct C1TcParams {
 template <bool FAST>
 __global__ void __launch_bounds__(C1_THREADS) k_c1_fwd_tc(const C1TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
+  // warps' own accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smA = smem;                                               // [2][KB][128 rows][128 B]
   uint8_t* smB = smem + p.off_b;                                     // [KB][NP rows][128 B]
   float* halo = reinterpret_cast<float*>(smem + p.off_halo);         // [halo] + XH*YH zeros behind it for the padding taps

@@ -785,6 +785,8 @@ extern "C" int e2_conv3d_wgrad(e2_handle* h, const e2_conv_desc* d, const float*
   cudaStream_t s = (cudaStream_t)stream;
   if (e2_conv_pw_wgrad_ok(g))
     rc = e2_launch_conv_pw_wgrad(h, g, db, s), db_done = (db != nullptr);
+  else if (d->x.c == 1 && d->compute == E2_COMPUTE_TF32 && e2_wgrad_c1_tc_ok(g))
+    rc = e2_launch_wgrad_c1_tc(h, g, db, s), db_done = (db != nullptr);
   else if (d->x.c == 1 && e2_conv_c1_wgrad_reg_ok(g))
     rc = e2_launch_conv_c1_wgrad_reg(h, g, db, s), db_done = (db != nullptr);
   else if (d->x.c == 1 && e2_conv_c1_wgrad_line_ok(g))

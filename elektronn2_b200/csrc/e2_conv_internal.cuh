@@ -92,3 +92,8 @@ bool e2_wgrad_zs_tc_ok(const e2_handle* h, const ReduceGemm& g);
 int e2_launch_wgrad_zs_tc(e2_handle* h, const ReduceGemm& g, void* ws, size_t ws_bytes, float* db, bool* db_done,
                           cudaStream_t s);
 size_t e2_wgrad_zs_workspace_bytes(int sm_count, const ReduceGemm& g);
+
+// first-layer wgrad on the tensor cores (e2_wgrad_c1_tc.cu): thread-built im2col rows + TMA-fed dy, bias gradient as an
+// extra im2col column; TF32 mode, <= 31 taps, <= 32 output channels
+bool e2_wgrad_c1_tc_ok(const ReduceGemm& g);
+int e2_launch_wgrad_c1_tc(e2_handle* h, const ReduceGemm& g, float* db, cudaStream_t s);

@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
                                                                 const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stage bases
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
+  // warps' own accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_stage_bytes = p.BN * BK * 4;
   uint8_t* smA = smem;
   uint8_t* smB = smem + p.stages * A_STAGE_BYTES;

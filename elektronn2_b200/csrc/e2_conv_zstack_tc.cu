@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmG,
                                                                   const ZsParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
+  // warps' own accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smP = smem;                                   // plane slots
   uint8_t* smW = smem + p.nslot * p.plane_stride;        // weight ring
   uint8_t* smE = smem + p.epi_off;                       // epilogue: per warp one 4 KB staging/aux tile, then bias

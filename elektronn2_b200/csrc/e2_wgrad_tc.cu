@@ -54,7 +54,9 @@ struct WgParams {
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(const __grid_constant__ CUtensorMap tmP,
                                                          const __grid_constant__ CUtensorMap tmQ, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
+  // warps' own accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_chunks = p.n_cols / 32;
   const int b_bytes = b_chunks * CHUNK_BYTES;
   uint8_t* smB = smem;

@@ -63,7 +63,9 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 __global__ void __launch_bounds__(ZS_THREADS) k_wgrad_zs_tc(const __grid_constant__ CUtensorMap tmP,
                                                             const __grid_constant__ CUtensorMap tmQ, const ZsParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
+  // warps' own accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = full + MAX_STAGES;

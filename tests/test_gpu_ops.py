@@ -89,6 +89,10 @@ CONV_CASES = [
     (1, 128, (4, 6, 6), 256, (3, 3, 3)),
     (1, 256, (5, 16, 16), 128, (3, 3, 3)),   # few tiles, long K: the z-stack kernel splits K over channel blocks
     (1, 200, (4, 15, 14), 72, (3, 3, 3)),    # same with ragged channel counts and edges
+    # the tensor-core first-layer wgrad (e2_wgrad_c1_tc.cu: <= 32 taps, <= 32 output channels, y extent % 4 == 0)
+    (1, 1, (7, 24, 44), 20, (3, 3, 3)),      # fewer than 32 output channels, two ragged y tiles
+    (2, 1, (4, 36, 72), 32, (1, 3, 3)),      # batch 2, 9 taps, three y tiles, several x tiles
+    (1, 1, (5, 19, 36), 16, (1, 4, 4)),      # 16 taps
     # the z-stacked wgrad kernel (e2_wgrad_zs_tc.cu: <= 64 output channels, kz >= 2, batch 1)
     (1, 40, (7, 11, 13), 32, (3, 3, 3)),     # one r block (N = 96), second s block partial, ragged tiles
     (1, 24, (6, 9, 9), 20, (2, 3, 3)),       # fewer than 32 output channels (clipped r block), kz = 2
