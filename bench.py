@@ -329,8 +329,15 @@ def main():
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         tf_ = tj.get('families', {}).get(top)
+        n_launch = tf['n']
+        if not tf_ and top in ('conv_fwd', 'conv_dgrad') and 'conv_fwd+dgrad' in tj.get('families', {}):
+            # forward and dgrad run the same kernels (k_conv_zstack_tc / tap kernel): ncu cannot tell them apart, so the
+            # per-launch traffic is that of the combined family
+            tf_ = tj['families']['conv_fwd+dgrad']
+            n_launch = tf_['launches_per_step']
+            roof['traffic_note'] = 'conv_fwd and conv_dgrad share kernels: DRAM bytes per launch of the combined family'
         if tf_:
-            roof['traffic'] = tf_['dram_bytes_per_step'] / tf['n']
+            roof['traffic'] = tf_['dram_bytes_per_step'] / n_launch
             roof['traffic_source'] = 'profiles/traffic_%s.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, %s)' % (
                 args.workload, tj.get('source', ''))
             roof['algorithmic_bytes'] = tf['bytes'] / tf['n']

@@ -7,7 +7,7 @@ OUT="$HERE/../lib"
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I$ROOT/include -I$HERE"
-SRCS="e2_api.cu e2_pool.cu e2_conv_ffma.cu e2_conv_c1.cu e2_conv_c1_tc.cu e2_conv_pw.cu e2_conv_tc.cu e2_conv_zstack_tc.cu e2_wgrad_tc.cu e2_wgrad_halo_tc.cu e2_wgrad_zs_tc.cu e2_wgrad_c1_tc.cu e2_train.cu e2_epilogue.cu"
+SRCS="e2_api.cu e2_pool.cu e2_conv_ffma.cu e2_conv_c1.cu e2_conv_c1_tc.cu e2_conv_c1_ws.cu e2_conv_pw.cu e2_conv_tc.cu e2_conv_zstack_tc.cu e2_wgrad_tc.cu e2_wgrad_halo_tc.cu e2_wgrad_zs_tc.cu e2_wgrad_c1_tc.cu e2_train.cu e2_epilogue.cu"
 OBJS=""
 pids=""
 for s in $SRCS; do

@@ -754,6 +754,7 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
         !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(wf) & 15) && e2_conv_zstack_tc_ok(h, g))
       return e2_launch_conv_zstack_tc(h, g, s);
     // TF32 mode: the threads build the im2col tile, the tensor core does the 27 MACs per output (e2_conv_c1_tc.cu)
+    if (d->compute == E2_COMPUTE_TF32 && e2_conv_c1_fwd_ws_ok(g)) return e2_launch_conv_c1_fwd_ws(h, g, s);
     if (d->compute == E2_COMPUTE_TF32 && e2_conv_c1_fwd_tc_ok(g)) return e2_launch_conv_c1_fwd_tc(h, g, s);
     if (e2_conv_c1_fwd_reg_ok(g)) return e2_launch_conv_c1_fwd_reg(h, g, s);
     return e2_conv_c1_fwd_line_ok(g) ? e2_launch_conv_c1_fwd_line(h, g, s) : e2_launch_conv_c1_fwd(h, g, s);

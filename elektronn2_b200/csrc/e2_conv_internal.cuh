@@ -97,3 +97,7 @@ size_t e2_wgrad_zs_workspace_bytes(int sm_count, const ReduceGemm& g);
 // extra im2col column; TF32 mode, <= 31 taps, <= 32 output channels
 bool e2_wgrad_c1_tc_ok(const ReduceGemm& g);
 int e2_launch_wgrad_c1_tc(e2_handle* h, const ReduceGemm& g, float* db, cudaStream_t s);
+
+// first-layer forward, warp-specialised (e2_conv_c1_ws.cu): TMA halo -> builder warps -> MMA -> epilogue warps -> TMA store
+bool e2_conv_c1_fwd_ws_ok(const GatherGemm& g);
+int e2_launch_conv_c1_fwd_ws(e2_handle* h, const GatherGemm& g, cudaStream_t s);

@@ -14,6 +14,7 @@ import sys
 
 FAMILY = [
     ('k_wgrad_halo_tc', 'conv_wgrad'), ('k_wgrad_halo_reduce', 'conv_wgrad'), ('k_c1_wgrad', 'conv_wgrad'),
+    ('k_wgrad_zs', 'conv_wgrad'),
     ('k_reduce_gemm', 'conv_wgrad'),
     ('k_wgrad_tc_reduce', 'upconv_wgrad'), ('k_wgrad_tc', 'upconv_wgrad'), ('k_bias_grad', 'upconv_wgrad'),
     ('k_conv_zstack_tc', 'conv_fwd+dgrad'), ('k_zstack_reduce', 'conv_fwd+dgrad'),
