@@ -9,7 +9,7 @@
 //                 warp writes the 8 chunks of one row (conflict-free); values tf32-rounded
 //   warp 1        MMA issuer: per tile 2 position blocks x ceil(T/8) MMAs M128 x N32 x K8 against the weight tile
 //                 (built once per CTA), accumulators double-buffered in TMEM
-//   warps 6-9     epilogue: tcgen05.ld -> +bias -> act -> tf32 round -> the thread's 128-byte row into a swizzled staging
+//   warps 6-13    epilogue: tcgen05.ld -> +bias -> act -> tf32 round -> the thread's 128-byte row into a swizzled staging
 //                 tile -> ONE TMA store of the [8 lines][32 y][32 ch] box per tile (clipped at the tensor edges)
 // tile = 256 positions (8 x-lines x 32 y of one z plane).
 #include <algorithm>
@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int WX = 8, WY = 32, ROWS = WX * WY;
-constexpr int WS_THREADS = 320;
+constexpr int WS_THREADS = 448;              // producer, MMA issuer, 4 builder warps, 8 epilogue warps
 constexpr int STAGES = 3;
 constexpr int A_BYTES = ROWS * 128, OUT_BYTES = ROWS * 128;
 
@@ -36,12 +36,14 @@ struct C1sParams {
   const float* bias;
   int act, round_tf32;
   uint32_t idesc;
+  int dbg;   // E2_C1S_DBG (bottleneck experiments): 1 no halo TMA, 2 no build, 4 no MMA, 8 no epilogue math, 16 no TMA store
 };
 
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   while (!tc::mbar_try_wait(bar, parity)) {
-    if (++n > (1u << 24)) {
+    __nanosleep(64);                 // 13 of the 14 warps wait most of the time: leave the issue slots to the one that works
+    if (++n > (1u << 22)) {
       printf("e2b200: conv_c1_ws mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
     tc::prefetch_tmap(&tmX);
     tc::prefetch_tmap(&tmY);
     for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&built[i], 4), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 4);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], 8);
     tc::fence_barrier_init();
   }
   if (threadIdx.x < 32) {
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
         int n, z, x0, y0;
         tile_coords(t, n, z, x0, y0);
         tc::mbar_wait(&empty[s], par);
-        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)p.halo_bytes);
-        tma_load_4d(smem + s * p.stage_bytes + A_BYTES, &tmX, &full[s], y0 + p.oy, x0 + p.ox, z + p.oz, n);
+        tc::mbar_arrive_expect_tx(&full[s], (p.dbg & 1) ? 0u : (uint32_t)p.halo_bytes);
+        if (!(p.dbg & 1)) tma_load_4d(smem + s * p.stage_bytes + A_BYTES, &tmX, &full[s], y0 + p.oy, x0 + p.ox, z + p.oz, n);
         if (++s == STAGES) s = 0, par ^= 1u;
       }
     }
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
         for (int mb = 0; mb < 2; ++mb) {
           const uint64_t ad0 = tmpl + (uint64_t)((a_addr + (uint32_t)(mb * 128 * 128)) >> 4);
           const uint32_t acc = tmem_base + (uint32_t)((buf * 2 + mb) * 32);
-          for (int k = 0; k < p.KS; ++k) tc::mma_tf32_ss(acc, ad0 + 2 * k, bd0 + 2 * k, p.idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < ((p.dbg & 4) ? 0 : p.KS); ++k) tc::mma_tf32_ss(acc, ad0 + 2 * k, bd0 + 2 * k, p.idesc, k > 0 ? 1u : 0u);
         }
         tc::mma_commit(&empty[s]);
         tc::mma_commit(&acc_full[buf]);
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
       wait_bar(&full[s], par);
       uint8_t* A = smem + s * p.stage_bytes;
       const float* halo = reinterpret_cast<const float*>(A + A_BYTES);
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int m0 = 0; m0 < ROWS / 16; m0 += 8) {
         float4 v[8];
@@ -198,8 +201,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
     }
   } else {
     // ---------------------------------------------------------------------- epilogue
-    const int ew = warp & 3;                          // TMEM lane quarter of this warp (warps 6..9 -> 2,3,0,1)
-    const int et = (int)threadIdx.x - 192;            // 0..127
+    // 8 warps: warps 6..9 take position block 0 of a tile, warps 10..13 block 1 (a warp reads the TMEM lane quarter
+    // warp % 4, whatever its block)
+    const int ew = warp & 3;
+    const int mb = (warp - 6) >> 2;
+    const int et = (int)threadIdx.x - 192;            // 0..255
     int buf = 0, ob = 0;
     uint32_t fpar = 0;
     int tl = 0;
@@ -208,12 +214,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
       tile_coords(t, n, z, x0, y0);
       // the TMA store that last read this staging buffer (two tiles ago) must have finished reading it
       if (et == 0) bulk_wait_read1();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      tc::mbar_wait(&acc_full[buf], fpar);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      wait_bar(&acc_full[buf], fpar);
       tc::tc_fence_after();
       uint8_t* out = smOut + ob * OUT_BYTES;
-#pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
+      if (!(p.dbg & 8)) {
         uint32_t r[32];
         tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((buf * 2 + mb) * 32), r);
         tc::tmem_ld_wait();
@@ -237,9 +242,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_c1_fwd_ws(const __grid_consta
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       if (et == 0) {
-        tc::tma_store_5d(&tmY, out, 0, y0, x0, z, n);
+        if (!(p.dbg & 16)) tc::tma_store_5d(&tmY, out, 0, y0, x0, z, n);
         tc::bulk_commit();
       }
       ob ^= 1;
@@ -297,6 +302,10 @@ int e2_launch_conv_c1_fwd_ws(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   C1sParams p;
   if (!enc || !plan_c1s(g, &p)) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_c1_fwd_ws: problem does not qualify");
   p.idesc = tc::make_idesc(2 /*TF32*/, 0, 0, 128, 32);
+  {
+    const char* dv = getenv("E2_C1S_DBG");
+    p.dbg = dv ? atoi(dv) : 0;
+  }
   CUtensorMap tmX, tmY;
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
