@@ -71,6 +71,24 @@ class Net(object):
         return trunc_tf32(v) if (self.tf32 and not exact) else v
 
     @staticmethod
+    def _c1_fwd_on_tensor_cores(w_sh, x_sh):
+        """Which first-layer forward kernel libe2b200 picks (csrc/e2_conv_ffma.cu e2_conv3d_fwd): the warp-specialised
+        one (9..32 taps, 8..32 channels, y extent % 4 == 0) or the older tcgen05 one (16..64 taps) round x to tf32;
+        otherwise the CUDA-core kernel multiplies exact fp32 values."""
+        taps, n = int(np.prod(w_sh[2:])), int(w_sh[0])
+        out_pos = int(np.prod([x_sh[2 + i] - w_sh[2 + i] + 1 for i in range(3)]))
+        if out_pos < 4096:
+            return False
+        ws = 9 <= taps <= 32 and 8 <= n <= 32 and x_sh[4] % 4 == 0
+        old = 16 <= taps <= 64 and 8 <= n <= 64 and n % 4 == 0
+        return ws or old
+
+    @staticmethod
+    def _c1_wgrad_on_tensor_cores(w_sh, x_sh):
+        """First-layer wgrad (csrc/e2_wgrad_c1_tc.cu): <= 32 taps, <= 32 channels, y extent % 4 == 0."""
+        return int(np.prod(w_sh[2:])) <= 32 and int(w_sh[0]) <= 32 and x_sh[4] % 4 == 0
+
+    @staticmethod
     def _cuda_core_layer(n):
         """Layers libe2b200 runs on CUDA cores in fp32 even in TF32 mode (csrc/e2_conv_pw.cu)."""
         w = n.params['w']
@@ -171,8 +189,9 @@ class Net(object):
                 w = n.params['w']
                 xin = p[0]
                 if w.shape[1] == 1:
-                    # first layer: the tcgen05 kernel (>= 16 taps) rounds its input halo, the CUDA-core one does not
-                    xin = rna_tf32(xin) if int(np.prod(w.shape[2:])) >= 16 else np.asarray(xin, np.float32).astype(F64)
+                    # first layer: the tcgen05 kernels round their input halo, the CUDA-core one does not
+                    xin = rna_tf32(xin) if self._c1_fwd_on_tensor_cores(w.shape, xin.shape) else \
+                        np.asarray(xin, np.float32).astype(F64)
                 else:
                     xin = self._use(xin, self._cuda_core_layer(n))
                 lin = (ops.conv3d_dot if tuple(w.shape[2:]) == (1, 1, 1) else ops.conv3d)(xin, rna_tf32(w))
@@ -271,7 +290,10 @@ class Net(object):
                 else:
                     dlin = dpre
                 exact = self._cuda_core_layer(n) or n.params['w'].shape[1] == 1
-                grads[(n, 'w')] = ops.conv3d_wgrad(self._use(dlin, exact), self._use(xin, exact), n.params['w'].shape)
+                xw = xin
+                if self.tf32 and n.params['w'].shape[1] == 1 and self._c1_wgrad_on_tensor_cores(n.params['w'].shape, xin.shape):
+                    exact, xw = False, rna_tf32(xin)     # the tensor-core first-layer wgrad rounds x while building im2col
+                grads[(n, 'w')] = ops.conv3d_wgrad(self._use(dlin, exact), self._use(xw, exact), n.params['w'].shape)
                 if par[0].op != 'input':
                     self._acc(g, par[0], ops.conv3d_dgrad(self._use(dlin, self._cuda_core_layer(n)),
                                                           self._q(n.params['w']), xin.shape), rounded=True)
