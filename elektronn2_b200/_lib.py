@@ -112,6 +112,8 @@ SIGNATURES = {
     'e2_conv3d_pack_weights': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp]),
     'e2_conv3d_workspace_size': (C.c_int, [P(ConvDesc), P(sz)]),
     'e2_conv3d_fwd': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
+    'e2_conv3d_fwd_pool_supported': (C.c_int, [vp, P(ConvDesc), P(PoolDesc)]),
+    'e2_conv3d_fwd_pool': (C.c_int, [vp, P(ConvDesc), P(PoolDesc), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_dgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_wgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_packed_floats': (C.c_int, [P(UpConvDesc), P(sz), P(sz)]),
@@ -143,6 +145,7 @@ SIGNATURES = {
     'e2_maxout_fwd': (C.c_int, [vp, vp, vp, C.c_int64, i32, C.c_int64, i32, vp]),
     'e2_maxout_bwd': (C.c_int, [vp, vp, vp, vp, C.c_int64, i32, C.c_int64, i32, vp]),
     'e2_debug_zstack_plan': (C.c_int, [C.c_int] * 10 + [P(C.c_int)]),
+    'e2_debug_zstack_pool_plan': (C.c_int, [C.c_int] * 12 + [P(C.c_int)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -215,6 +218,15 @@ class Handle(object):
             msg = lib.e2_last_error(self._h).decode()
             cls = {ERR_INVALID: E2InvalidError, ERR_UNSUPPORTED: E2UnsupportedError}.get(rc, E2Error)
             raise cls(rc, "%s: %s" % (name, msg))
+
+    def query(self, name, *args):
+        """For entry points whose non-negative return value is an answer, not a status."""
+        rc = getattr(lib, name)(self._h, *args)
+        if rc < 0:
+            msg = lib.e2_last_error(self._h).decode()
+            cls = {ERR_INVALID: E2InvalidError, ERR_UNSUPPORTED: E2UnsupportedError}.get(rc, E2Error)
+            raise cls(rc, "%s: %s" % (name, msg))
+        return rc
 
     @property
     def launches(self):

@@ -762,6 +762,57 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
   return e2_dispatch_gather_gemm(h, g, d->compute, s);
 }
 
+// ---- conv with the max-pool in its epilogue
+static int conv_pool_problem(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x, const float* wf,
+                             const float* bias, const float* pool_bias, float* y, float* yp, int32_t* argmax,
+                             GatherGemm* g) {
+  int rc = check_conv(h, d);
+  if (rc) return rc;
+  E2_REQUIRE(h, p && e2_tensor_ok(&p->x) && e2_tensor_ok(&p->y), "conv3d_fwd_pool: bad pool descriptor");
+  E2_REQUIRE(h, p->x.n == d->y.n && p->x.z == d->y.z && p->x.x == d->y.x && p->x.y == d->y.y && p->x.c == d->y.c,
+             "conv3d_fwd_pool: the pool's input is not the conv's output");
+  E2_REQUIRE(h, p->pz >= 1 && p->px >= 1 && p->py >= 1 && p->x.z % p->pz == 0 && p->x.x % p->px == 0 && p->x.y % p->py == 0 &&
+                    p->y.z == p->x.z / p->pz && p->y.x == p->x.x / p->px && p->y.y == p->x.y / p->py && p->y.n == p->x.n &&
+                    p->y.c == p->x.c,
+             "conv3d_fwd_pool: pooled extents do not match input/pool");
+  conv_fwd_problem(d, x, wf, bias, y, g);
+  g->fuse_pool = 1, g->qz = p->pz, g->qx = p->px, g->qy = p->py;
+  g->Cp = yp, g->Ci = argmax, g->cp_pitch = p->y.c_pitch;
+  g->pbias = p->has_bias ? pool_bias : nullptr, g->pact = p->act, g->pround = p->round_tf32;
+  return E2_OK;
+}
+
+static bool conv_pool_fusable(const e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const GatherGemm& g) {
+  static const bool off = getenv("E2_DISABLE_ZSTACK") != nullptr || getenv("E2_NO_POOL_FUSION") != nullptr;
+  if (off || d->compute != E2_COMPUTE_TF32 || d->x.c == 1 || p->mode != E2_POOL_MAX) return false;
+  if (p->x.c_pitch != d->y.c_pitch || e2_conv_pw_fwd_ok(g)) return false;
+  return e2_gather_gemm_tc_ok(h, g) && e2_conv_zstack_pool_ok(h, g);
+}
+
+extern "C" int e2_conv3d_fwd_pool_supported(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p) {
+  if (!h) return E2_ERR_INVALID;
+  alignas(16) static float dummy[4];
+  GatherGemm g;
+  int rc = conv_pool_problem(h, d, p, dummy, dummy, dummy, dummy, dummy, dummy, reinterpret_cast<int32_t*>(dummy), &g);
+  if (rc) return rc;
+  return conv_pool_fusable(h, d, p, g) ? 1 : 0;
+}
+
+extern "C" int e2_conv3d_fwd_pool(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x,
+                                  const float* wf, const float* bias, const float* pool_bias, float* y, float* yp,
+                                  int32_t* argmax, void* ws, size_t ws_bytes, void* stream) {
+  GatherGemm g;
+  int rc = conv_pool_problem(h, d, p, x, wf, bias, pool_bias, y, yp, argmax, &g);
+  if (rc) return rc;
+  E2_REQUIRE(h, x && wf && yp && (!d->has_bias || bias) && (!p->has_bias || pool_bias), "conv3d_fwd_pool: null pointer");
+  if (conv_pool_fusable(h, d, p, g)) return e2_launch_conv_zstack_tc(h, g, (cudaStream_t)stream);
+  // not fusable: the two calls this entry point stands for (they need the unpooled tensor)
+  E2_REQUIRE(h, y, "conv3d_fwd_pool: this problem is not fused (e2_conv3d_fwd_pool_supported), so y is required");
+  rc = e2_conv3d_fwd(h, d, x, wf, bias, y, ws, ws_bytes, stream);
+  if (rc) return rc;
+  return e2_maxpool3d_fwd(h, p, y, pool_bias, yp, argmax, stream);
+}
+
 extern "C" int e2_conv3d_dgrad(e2_handle* h, const e2_conv_desc* d, const float* dy, const float* wd, float* dx,
                                const float* relu_gate, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_conv(h, d);

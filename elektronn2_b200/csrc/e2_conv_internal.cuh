@@ -21,6 +21,15 @@ struct GatherGemm {
   const float* gate;            // fused ReLU backward: zero the result where gate <= 0 (same layout as C)
   void* ws;                     // optional caller-owned scratch (split-K partial tiles)
   size_t ws_bytes;
+  // max-pool fused into the z-stack kernel's epilogue (e2_conv3d_fwd_pool).  C may be null then (the caller does not
+  // want the unpooled tensor).  Cp / Ci: pooled values and int32 argmax, (On, Oz/qz, Ox/qx, Oy/qy, N) at pitch cp_pitch;
+  // the pooled values go through +pbias -> pact -> tf32 round (pround) after the maximum.
+  int fuse_pool, qz, qx, qy;
+  float* Cp;
+  int32_t* Ci;
+  int cp_pitch;
+  const float* pbias;
+  int pact, pround;
 };
 
 // W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]
@@ -70,6 +79,9 @@ int e2_launch_gather_gemm_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 size_t e2_gather_gemm_tc_workspace_bytes(int sm_count, const GatherGemm& g);
 // halo planes + z-taps stacked along N (e2_conv_zstack_tc.cu); preferred over both when it qualifies
 bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g);
+// would the z-stack kernel take g with the max-pool (g.fuse_pool, g.qz/qx/qy) in its epilogue -- and without losing a
+// K split it would otherwise use?
+bool e2_conv_zstack_pool_ok(const e2_handle* h, const GatherGemm& g);
 int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s);
 // scratch bytes its split-K plan wants (0: no split); g.ws / g.ws_bytes carry the scratch at launch
 size_t e2_conv_zstack_workspace_bytes(int sm_count, const GatherGemm& g);

@@ -58,7 +58,35 @@ struct ZsParams {
   int epi_off;                   // byte offset of the epilogue staging area (1024-aligned)
   long long* trace;              // E2_ZS_TRACE: per-role cycle counters of CTA 0 (debug)
   int dbg;                       // E2_ZS_DBG bottleneck experiments: 1 no plane TMA, 2 no weight TMA, 4 no MMA, 8 no stores
+  // max-pool fused into the epilogue (e2_conv3d_fwd_pool): window (ppz,ppx,ppy) in {1,2}^3 over the values the
+  // epilogue above produces, then +pbias -> pact -> tf32 round; argmax = first maximum in (z,x,y) scan order
+  int pool, ppz, ppx, ppy;
+  int store_full;                // also store the unpooled tile through tmC (0: the caller does not want that tensor)
+  int pool_amax;                 // store the argmax tile through tmI
+  const float* pbias;
+  int pact, pround;
 };
+
+// One butterfly step of the pooled reduction: every lane holds, per channel j, its best value pv[j] and where it came
+// from as bit j of (mz, mx, my) = offsets inside the window.  The partner's candidate replaces it when it is larger, or
+// equal and EARLIER in (z,x,y) scan order -- so the result is (max value, first position), whatever the merge order.
+__device__ __forceinline__ void zs_pool_merge(float (&pv)[32], uint32_t& mz, uint32_t& mx, uint32_t& my, int xor_lane) {
+  const uint32_t pmz = __shfl_xor_sync(0xffffffffu, mz, xor_lane);
+  const uint32_t pmx = __shfl_xor_sync(0xffffffffu, mx, xor_lane);
+  const uint32_t pmy = __shfl_xor_sync(0xffffffffu, my, xor_lane);
+  // bit j: partner's (dz,dx,dy) < mine, lexicographically
+  const uint32_t lt = (~pmz & mz) | (~(pmz ^ mz) & ((~pmx & mx) | (~(pmx ^ mx) & (~pmy & my))));
+  uint32_t take = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float o = __shfl_xor_sync(0xffffffffu, pv[j], xor_lane);
+    const bool t = (o > pv[j]) || (o == pv[j] && ((lt >> j) & 1u));
+    if (t) pv[j] = o, take |= 1u << j;
+  }
+  mz = (mz & ~take) | (pmz & take);
+  mx = (mx & ~take) | (pmx & take);
+  my = (my & ~take) | (pmy & take);
+}
 
 // lean bounded wait for the issuing warp (all lanes poll; try_wait suspends in hardware)
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
@@ -118,6 +146,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmC,
                                                                   const __grid_constant__ CUtensorMap tmG,
+                                                                  const __grid_constant__ CUtensorMap tmP,
+                                                                  const __grid_constant__ CUtensorMap tmI,
                                                                   const ZsParams p) {
   extern __shared__ uint8_t smem_raw[];
   // aligned base by OFFSET arithmetic on smem_raw (no integer round trip), so the pointer keeps its address space and the
@@ -143,6 +173,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
     tc::prefetch_tmap(&tmB);
     tc::prefetch_tmap(&tmC);
     if (p.gate) tc::prefetch_tmap(&tmG);
+    if (p.pool) tc::prefetch_tmap(&tmP);
+    if (p.pool && p.pool_amax) tc::prefetch_tmap(&tmI);
     for (int i = 0; i < p.nslot; ++i) tc::mbar_init(&pl_full[i], 1), tc::mbar_init(&pl_empty[i], 1);
     for (int i = 0; i < p.wslot; ++i) tc::mbar_init(&w_full[i], 1), tc::mbar_init(&w_empty[i], 1);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&acc_full[i], 1), tc::mbar_init(&acc_empty[i], EPI_WARPS);
@@ -323,95 +355,190 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       tr_full += e1 - e0;
       tc::tc_fence_after();
       int ci = 0;
-      for (int zl = 0; zl < p.TZ; ++zl) {
-        const uint32_t acc = tmem_base + (uint32_t)((buf * p.TZ + (p.TZ - 1 - zl)) * p.BN) + ((uint32_t)(q * 32) << 16);
-        if (z0 + zl >= p.Oz) break;                       // uniform: whole plane outside the tensor
+      const int PZ = p.pool ? p.ppz : 1;                  // planes per unit of epilogue work (the pool window's z extent)
+      for (int zp = 0; zp < p.TZ; zp += PZ) {
+        if (z0 + zp >= p.Oz) break;                       // uniform: whole plane (pair) outside the tensor
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
           if (n0 + c0 >= p.N) break;                      // uniform: chunk entirely past the last channel
           if ((ci++ & 1) != half) continue;               // the sibling warp's chunk
-          // the previous TMA store must have finished reading the buffer
-          if (lane == 0) {
-            tc::bulk_wait_read0();
-            if (has_aux) {
-              tc::mbar_arrive_expect_tx(abar, 4096u);
-              tc::tma_load_5d(stage, p.gate ? &tmG : &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
-            }
-          }
-          __syncwarp();
-          uint32_t r[32];
-          if (p.BN - c0 >= 32) {
-            tc::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
-          } else {
-            tc::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
+          float pv[32];                                   // fused pool: best value per channel so far ...
+          uint32_t mz = 0;                                // ... and bit j = it came from the window's second plane
 #pragma unroll
-            for (int jj = 16; jj < 32; ++jj) r[jj] = 0u;
-          }
-          tc::tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + j4 < p.BN) b4 = *reinterpret_cast<const float4*>(bias_w + c0 + j4);
-            v[j4 + 0] = __uint_as_float(r[j4 + 0]) + b4.x;
-            v[j4 + 1] = __uint_as_float(r[j4 + 1]) + b4.y;
-            v[j4 + 2] = __uint_as_float(r[j4 + 2]) + b4.z;
-            v[j4 + 3] = __uint_as_float(r[j4 + 3]) + b4.w;
-          }
-          // one (uniform) branch per chunk, not one switch per value
-          if (p.act == E2_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act != E2_ACT_LIN) {
-            // fully unrolled on purpose: a partially unrolled loop indexes v[] dynamically, which puts the
-            // whole array in local memory (L1 is carved out for shared memory here -> every access goes to L2)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = e2_apply_act(v[j], p.act);
-          }
-          if (has_aux) {
-            tc::mbar_wait(abar, apar);
-            apar ^= 1u;
-            if (p.gate) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 g4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
-                if (!(g4.x > 0.f)) v[4 * j + 0] = 0.f;
-                if (!(g4.y > 0.f)) v[4 * j + 1] = 0.f;
-                if (!(g4.z > 0.f)) v[4 * j + 2] = 0.f;
-                if (!(g4.w > 0.f)) v[4 * j + 3] = 0.f;
-              }
-              if (p.accumulate) {      // rare: both -> second aux load of the destination tile
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
+          for (int dz = 0; dz < 2; ++dz) {
+            if (dz < PZ) {
+              const int zl = zp + dz;
+              const uint32_t acc =
+                  tmem_base + (uint32_t)((buf * p.TZ + (p.TZ - 1 - zl)) * p.BN) + ((uint32_t)(q * 32) << 16);
+              // the previous TMA store must have finished reading the buffer
+              if (lane == 0) {
+                tc::bulk_wait_read0();
+                if (has_aux) {
                   tc::mbar_arrive_expect_tx(abar, 4096u);
-                  tc::tma_load_5d(stage, &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+                  tc::tma_load_5d(stage, p.gate ? &tmG : &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
                 }
+              }
+              __syncwarp();
+              uint32_t r[32];
+              if (p.BN - c0 >= 32) {
+                tc::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+              } else {
+                tc::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
+#pragma unroll
+                for (int jj = 16; jj < 32; ++jj) r[jj] = 0u;
+              }
+              tc::tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + j4 < p.BN) b4 = *reinterpret_cast<const float4*>(bias_w + c0 + j4);
+                v[j4 + 0] = __uint_as_float(r[j4 + 0]) + b4.x;
+                v[j4 + 1] = __uint_as_float(r[j4 + 1]) + b4.y;
+                v[j4 + 2] = __uint_as_float(r[j4 + 2]) + b4.z;
+                v[j4 + 3] = __uint_as_float(r[j4 + 3]) + b4.w;
+              }
+              // one (uniform) branch per chunk, not one switch per value
+              if (p.act == E2_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (p.act != E2_ACT_LIN) {
+                // fully unrolled on purpose: a partially unrolled loop indexes v[] dynamically, which puts the
+                // whole array in local memory (L1 is carved out for shared memory here -> every access goes to L2)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = e2_apply_act(v[j], p.act);
+              }
+              if (has_aux) {
                 tc::mbar_wait(abar, apar);
                 apar ^= 1u;
-              }
-            }
-            if (p.accumulate) {
+                if (p.gate) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 c4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
-                v[4 * j + 0] += c4.x, v[4 * j + 1] += c4.y, v[4 * j + 2] += c4.z, v[4 * j + 3] += c4.w;
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
+                    if (!(g4.x > 0.f)) v[4 * j + 0] = 0.f;
+                    if (!(g4.y > 0.f)) v[4 * j + 1] = 0.f;
+                    if (!(g4.z > 0.f)) v[4 * j + 2] = 0.f;
+                    if (!(g4.w > 0.f)) v[4 * j + 3] = 0.f;
+                  }
+                  if (p.accumulate) {      // rare: both -> second aux load of the destination tile
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                      tc::mbar_arrive_expect_tx(abar, 4096u);
+                      tc::tma_load_5d(stage, &tmC, abar, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+                    }
+                    tc::mbar_wait(abar, apar);
+                    apar ^= 1u;
+                  }
+                }
+                if (p.accumulate) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(stage + lane * 128 + ((j ^ r8) << 4));
+                    v[4 * j + 0] += c4.x, v[4 * j + 1] += c4.y, v[4 * j + 2] += c4.z, v[4 * j + 3] += c4.w;
+                  }
+                }
+              }
+              if (p.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
+              }
+              if (p.store_full) {
+                // each lane reads and writes only its own 128-byte row of the buffer: no cross-lane hazard
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ r8) << 4)) =
+                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(p.dbg & 8)) {
+                  tc::tma_store_5d(&tmC, stage, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
+                  tc::bulk_commit();
+                }
+              }
+              if (p.pool) {
+                if (dz == 0) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) pv[j] = v[j];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (v[j] > pv[j]) pv[j] = v[j], mz |= 1u << j;   // strict '>': the first plane keeps ties
+                }
               }
             }
           }
-          if (p.round_tf32) {
+          if (p.pool) {
+            // ------------------------------------------------------------ fused max-pool of this unit
+            // lane = x-line (lane >> 3) x y (lane & 7) of the 4 x 8 position patch; window partners are lane ^ 1
+            // (y) and lane ^ 8 (x).  After the merges the lane at a window's origin holds (max, first argmax).
+            const int xl = lane >> 3, yy = lane & 7;
+            uint32_t mx = (p.ppx == 2 && (xl & 1)) ? 0xffffffffu : 0u;
+            uint32_t my = (p.ppy == 2 && (yy & 1)) ? 0xffffffffu : 0u;
+            if (p.ppy == 2) zs_pool_merge(pv, mz, mx, my, 1);
+            if (p.ppx == 2) zs_pool_merge(pv, mz, mx, my, 8);
+            if (p.pbias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
-          }
-          // each lane reads and writes only its own 128-byte row of the buffer: no cross-lane hazard
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < p.N) pv[j] += __ldg(p.pbias + n0 + c0 + j);
+            }
+            if (p.pact == E2_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ r8) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          tc::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && !(p.dbg & 8)) {
-            tc::tma_store_5d(&tmC, stage, n0 + c0, y0, x0 + 4 * q, z0 + zl, in_);
-            tc::bulk_commit();
+              for (int j = 0; j < 32; ++j) pv[j] = fmaxf(pv[j], 0.f);
+            } else if (p.pact != E2_ACT_LIN) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pv[j] = e2_apply_act(pv[j], p.pact);
+            }
+            if (p.pround) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) pv[j] = e2_round_tf32(pv[j]);
+            }
+            const bool owner = (((xl & (p.ppx - 1)) | (yy & (p.ppy - 1))) == 0);
+            const int rows_y = TY / p.ppy;
+            const int row = (xl / p.ppx) * rows_y + yy / p.ppy;          // row of the pooled box [4/ppx][8/ppy][32 ch]
+            const int nrows = 32 / (p.ppx * p.ppy);
+            uint8_t* st_v = stage;
+            uint8_t* st_i = stage + (nrows * 256 <= 4096 ? nrows * 128 : 0);   // 1024-aligned either way (swizzle period)
+            const int pzc = (z0 + zp) / p.ppz, pxc = (x0 + 4 * q) / p.ppx, pyc = y0 / p.ppy;
+            if (lane == 0) tc::bulk_wait_read0();
+            __syncwarp();
+            if (owner) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(st_v + row * 128 + ((j ^ (row & 7)) << 4)) =
+                    make_float4(pv[4 * j], pv[4 * j + 1], pv[4 * j + 2], pv[4 * j + 3]);
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 8)) {
+              tc::tma_store_5d(&tmP, st_v, n0 + c0, pyc, pxc, pzc, in_);
+              tc::bulk_commit();
+            }
+            if (p.pool_amax) {
+              if (st_i == st_v) {
+                if (lane == 0) tc::bulk_wait_read0();
+                __syncwarp();
+              }
+              if (owner) {
+                // int32 z*X*Y + x*Y + y in the geometry of the unpooled tensor (include/e2b200.h, e2_pool_desc)
+                const int base = ((z0 + zp) * p.Ox + (x0 + 4 * q + xl)) * p.Oy + y0 + yy;
+                const int sz = p.Ox * p.Oy, sx = p.Oy;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  int4 a;
+                  a.x = base + (int)((mz >> (4 * j + 0)) & 1u) * sz + (int)((mx >> (4 * j + 0)) & 1u) * sx + (int)((my >> (4 * j + 0)) & 1u);
+                  a.y = base + (int)((mz >> (4 * j + 1)) & 1u) * sz + (int)((mx >> (4 * j + 1)) & 1u) * sx + (int)((my >> (4 * j + 1)) & 1u);
+                  a.z = base + (int)((mz >> (4 * j + 2)) & 1u) * sz + (int)((mx >> (4 * j + 2)) & 1u) * sx + (int)((my >> (4 * j + 2)) & 1u);
+                  a.w = base + (int)((mz >> (4 * j + 3)) & 1u) * sz + (int)((mx >> (4 * j + 3)) & 1u) * sx + (int)((my >> (4 * j + 3)) & 1u);
+                  *reinterpret_cast<int4*>(st_i + row * 128 + ((j ^ (row & 7)) << 4)) = a;
+                }
+              }
+              tc::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(p.dbg & 8)) {
+                tc::tma_store_5d(&tmI, st_i, n0 + c0, pyc, pxc, pzc, in_);
+                tc::bulk_commit();
+              }
+            }
           }
         }
       }
@@ -513,6 +640,15 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
   p->plane_bytes = p->XH * p->YP * 128;
   p->plane_stride = (p->plane_bytes + 1023) / 1024 * 1024;   // slots stay 1024-B aligned (swizzle period)
   if (g.c_pitch % 4 || (reinterpret_cast<uintptr_t>(g.C) & 15) || (reinterpret_cast<uintptr_t>(g.gate) & 15)) return false;
+  if (g.fuse_pool) {
+    // pooled tiles must be whole windows of whole tiles: windows of 1 or 2 per axis (tile = TZ x 16 x 8, TZ even below),
+    // extents divisible by the window (Pool._calc_shape, neural.py:1543-1546), no K split (the epilogue lives here)
+    if (g.qz < 1 || g.qz > 2 || g.qx < 1 || g.qx > 2 || g.qy < 1 || g.qy > 2) return false;
+    if (g.Oz % g.qz || g.Ox % g.qx || g.Oy % g.qy) return false;
+    if (g.gate || g.accumulate || !g.Cp || g.cp_pitch % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(g.Cp) & 15) || (reinterpret_cast<uintptr_t>(g.Ci) & 15)) return false;
+    may_split = false;
+  }
   const int ntx = (g.Ox + TX - 1) / TX, nty = (g.Oy + TY - 1) / TY;
   const double kLatency = 1200.0, kStageOvh = 250.0, kEpiChunk = 1200.0, kReduceFixed = 8000.0, kReduceBpc = 2500.0;
   const int T9 = g.tx * g.ty, CBn = (g.K + 31) / 32;
@@ -535,6 +671,7 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
     static const int force_tz = getenv("E2_ZS_TZ") ? atoi(getenv("E2_ZS_TZ")) : 0;   // experiments only
     for (int tz = 8; tz >= 1; --tz) {
       if (force_tz && tz != force_tz) continue;
+      if (g.fuse_pool && g.qz == 2 && (tz & 1)) continue;   // a tile holds whole pool windows
       if (std::min(tz, S) * b > 256) continue;   // widest stacked MMA
       if (2 * tz * b > 512) continue;            // double-buffered accumulators in TMEM
       const int np = tz + S - 1;
@@ -631,9 +768,43 @@ extern "C" int e2_debug_zstack_plan(int sm_count, int K, int N, int Oz, int Ox, 
   return 1;
 }
 
+// same for the conv + fused max-pool plan (window qz,qx,qy): 1 if e2_conv3d_fwd_pool would fuse the pair
+extern "C" int e2_debug_zstack_pool_plan(int sm_count, int K, int N, int Oz, int Ox, int Oy, int kz, int kx, int ky, int qz,
+                                         int qx, int qy, int* out) {
+  e2_handle fake;
+  memset(&fake, 0, sizeof(fake));
+  fake.sm_count = sm_count;
+  GatherGemm g;
+  memset(&g, 0, sizeof(g));
+  alignas(16) static float dummy[4];
+  g.K = K, g.N = N, g.On = 1, g.Oz = Oz, g.Ox = Ox, g.Oy = Oy, g.tz = kz, g.tx = kx, g.ty = ky, g.sz = g.sx = g.sy = 1;
+  g.c_pitch = g.cp_pitch = (N + 3) / 4 * 4;
+  g.fuse_pool = 1, g.qz = qz, g.qx = qx, g.qy = qy, g.Cp = dummy;
+  if (!e2_conv_zstack_pool_ok(&fake, g)) return 0;
+  ZsParams p;
+  if (!plan_zstack(&fake, g, &p, false)) return 0;
+  out[0] = p.BN, out[1] = p.TZ, out[2] = p.ksplit, out[3] = p.cb_per, out[4] = p.wslot, out[5] = p.nslot, out[6] = p.num_tiles,
+  out[7] = p.ntn;
+  return 1;
+}
+
 bool e2_conv_zstack_tc_ok(const e2_handle* h, const GatherGemm& g) {
   ZsParams p;
   return plan_zstack(h, g, &p, g.ws != nullptr);
+}
+
+bool e2_conv_zstack_pool_ok(const e2_handle* h, const GatherGemm& g) {
+  if (!g.fuse_pool) return false;
+  // the plan without the pool: if it splits K (few tiles, long K loop) the epilogue runs in k_zstack_reduce and
+  // fusing would cost the split
+  GatherGemm plain = g;
+  plain.fuse_pool = 0;
+  alignas(16) static float dummy_ws[4];
+  plain.ws = dummy_ws;
+  if (!plain.C) plain.C = g.Cp;
+  ZsParams p;
+  if (!plan_zstack(h, plain, &p, true) || p.ksplit > 1) return false;
+  return plan_zstack(h, g, &p, false);
 }
 
 int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) {
@@ -657,6 +828,14 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     if (getenv("E2_ZS_INFO")) fprintf(stderr, "zstack: TZ %d NP %d nslot %d wslot %d BN %d CB %d ksplit %d units %d smem plane %d w %d\n", p.TZ, p.NP, p.nslot, p.wslot, p.BN, p.CB, p.ksplit, p.num_tiles, p.plane_stride, p.w_bytes);
   }
   p.idesc_step = (uint32_t)(p.BN >> 3) << 17;
+  if (g.fuse_pool) {
+    if (split) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: fused pool with a K split");
+    p.pool = 1, p.ppz = g.qz, p.ppx = g.qx, p.ppy = g.qy;
+    p.store_full = g.C != nullptr, p.pool_amax = g.Ci != nullptr;
+    p.pbias = g.pbias, p.pact = g.pact, p.pround = g.pround;
+  } else {
+    p.store_full = 1;
+  }
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5] = {(cuuint64_t)g.K, (cuuint64_t)g.Ay, (cuuint64_t)g.Ax, (cuuint64_t)g.Az, (cuuint64_t)g.An};
@@ -684,6 +863,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   CUtensorMap tmC, tmG;
   for (int which = 0; which < 2; ++which) {
     const float* base = which == 0 ? p.C : p.gate;
+    if (which == 0 && !base) base = g.Cp;   // fused pool without the unpooled tensor: tmC is never used, keep it valid
     if (!base) {
       tmG = tmC;
       continue;
@@ -698,8 +878,27 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
   }
+  // pooled values / argmax as [32 ch x 8/qy x 4/qx] boxes (one per epilogue warp and plane pair)
+  CUtensorMap tmP = tmC, tmI = tmC;
+  if (g.fuse_pool) {
+    for (int which = 0; which < 2; ++which) {
+      void* base = which == 0 ? static_cast<void*>(g.Cp) : static_cast<void*>(g.Ci);
+      if (!base) continue;
+      cuuint64_t dims[5] = {(cuuint64_t)g.N, (cuuint64_t)(g.Oy / g.qy), (cuuint64_t)(g.Ox / g.qx), (cuuint64_t)(g.Oz / g.qz),
+                            (cuuint64_t)g.On};
+      cuuint64_t pitch = (cuuint64_t)g.cp_pitch * 4;
+      cuuint64_t strides[4] = {pitch, pitch * dims[1], pitch * dims[1] * dims[2], pitch * dims[1] * dims[2] * dims[3]};
+      cuuint32_t box[5] = {32, (cuuint32_t)(TY / g.qy), (cuuint32_t)(4 / g.qx), 1, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(which == 0 ? &tmP : &tmI, which == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_INT32,
+                       5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(pooled) failed: %d", (int)r);
+    }
+  }
   const size_t smem = 1024 + (size_t)p.epi_off + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 4 + EPI_WARPS) * 8 + 16;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ZsParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const CUtensorMap, const ZsParams);
 #define ZS_ROW(KZ)                                                                                               \
   {k_conv_zstack_tc<1, KZ>, k_conv_zstack_tc<2, KZ>, k_conv_zstack_tc<3, KZ>, k_conv_zstack_tc<4, KZ>,             \
    k_conv_zstack_tc<5, KZ>, k_conv_zstack_tc<6, KZ>, k_conv_zstack_tc<7, KZ>, k_conv_zstack_tc<8, KZ>}
@@ -715,7 +914,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     cudaMalloc(&p.trace, 32 * sizeof(long long));
     cudaMemset(p.trace, 0, 32 * sizeof(long long));
   }
-  fn<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, tmC, tmG, p);
+  fn<<<grid, ZS_THREADS, smem, s>>>(tmA, tmB, tmC, tmG, tmP, tmI, p);
   if (p.trace) {
     long long tr[32];
     cudaMemcpy(tr, p.trace, sizeof(tr), cudaMemcpyDeviceToHost);

@@ -253,6 +253,7 @@ class Plan(object):
         h = self.h
         out_ids = set(id(o) for o in self.outputs)
         self.crop_into, self.copy_into, self.alias_of = {}, {}, {}
+        self._fused_pools = set()    # Pool nodes whose forward runs in their producer's conv epilogue
         for n in self.nodes:
             if isinstance(n, Concat):
                 buf = self._new(n)
@@ -297,6 +298,8 @@ class Plan(object):
             elif isinstance(n, Conv):
                 self._plan_conv(n)
             elif isinstance(n, Pool):
+                if n in self._fused_pools:
+                    continue      # planned together with its producer (_plan_conv)
                 x = self.val[n.parent]
                 y = self._new(n)
                 self.val[n] = y
@@ -377,7 +380,24 @@ class Plan(object):
         unfused = self._unfused(n)
         if not pooled and not unfused:
             op = ops.ConvOp(h, x, y, w, b, k3, n.activation_func, self.compute)
-            self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(y)), kind)
+            pn = self._pool_consumer(n)
+            pop = None
+            if pn is not None:
+                # Conv -> Pool (examples/unet3d.py:63-74): the window maximum is taken in the conv kernel's epilogue,
+                # the unpooled tensor is still written (skip connection / ReLU gate) but not read back
+                yp = self._new(pn)
+                pop = ops.PoolOp(h, y, yp, _sp3(pn.pool_shape), keep_argmax=self.train, tie_mode=config.pool_tie_mode,
+                                 mode='max')
+                if op.pool_fusable(pop):
+                    self.val[pn], self.aux[pn] = yp, pop
+                    self._fused_pools.add(pn)
+                else:
+                    pop = None
+            if pop is not None:
+                self._f('conv_fwd:' + n.name, lambda op=op, pop=pop: op.fwd_pool(pop, True), flops,
+                        4 * (_nel(x) + _nel(y) + 2 * _nel(pop.y)), kind)
+            else:
+                self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(y)), kind)
         else:
             # conv -> pool|MFP -> +bias -> act  (neural.py:662-712): the conv writes raw
             # accumulators, the pooling kernel carries the bias/activation epilogue -- or, for batch
@@ -394,13 +414,30 @@ class Plan(object):
             elif pooled:
                 pop = ops.PoolOp(h, lin, v, p3, bias=pb, act=pact, keep_argmax=self.train,
                                  tie_mode=config.pool_tie_mode, round_tf32=rnd)
-                self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(v)))
+                if (not unfused and (not self.train or config.pool_tie_mode == 'first') and op.pool_fusable(pop)):
+                    # conv -> pool -> +bias -> act in ONE launch; the raw conv output is never written (the backward
+                    # pass routes through the argmax)
+                    self.fwd_ops.pop()
+                    self._f('conv_fwd:' + n.name, lambda op=op, pop=pop: op.fwd_pool(pop, False), flops,
+                            4 * (_nel(x) + 2 * _nel(v)), kind)
+                else:
+                    self._f('pool_fwd:' + n.name, pop.fwd, 0, 4 * (_nel(lin) + _nel(v)))
             if unfused:
                 self._plan_affine(n, lin, pop, v if pooled else lin, y)
             else:
                 self.aux[n] = (lin, pop)
         self.conv_ops[n] = op
         self.pack_ops.append(op)
+
+    def _pool_consumer(self, n):
+        """The one max-Pool node (windows of 1 or 2 per axis) among the consumers of Conv ``n``, or None."""
+        pools = [c for c in self._consumers(n) if isinstance(c, Pool) and c.parent is n]
+        if len(pools) != 1 or pools[0].mode != 'max' or getattr(pools[0], 'mfp', False):
+            return None
+        p3 = _sp3(pools[0].pool_shape)
+        if any(p not in (1, 2) for p in p3) or all(p == 1 for p in p3):
+            return None
+        return pools[0]
 
     def _unfused(self, n):
         """Does this Conv / UpConv need the separate epilogue kernel?  Batch normalisation and prelu always; 'abs'

@@ -60,6 +60,22 @@ class ConvOp(object):
         self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), ws, ws_bytes, self.h.stream())
 
+    def pool_fusable(self, pop):
+        """Does libe2b200 run this conv and the max-pool ``pop`` (a PoolOp whose input is this conv's output) as one
+        launch (e2_conv3d_fwd_pool_supported)?"""
+        if not pop.is_max or pop.x.desc.dims() != self.y.desc.dims() or pop.x.desc.c_pitch != self.y.desc.c_pitch:
+            return False
+        return self.h.query('e2_conv3d_fwd_pool_supported', C.byref(self.d), C.byref(pop.d)) == 1
+
+    def fwd_pool(self, pop, store_full=True):
+        """conv -> max-pool in one launch (e2_conv3d_fwd_pool): the same bits as ``self.fwd(); pop.fwd()``;
+        with store_full=False the unpooled tensor is not written at all."""
+        ws, ws_bytes = self.h.workspace()
+        self.h.call('e2_conv3d_fwd_pool', C.byref(self.d), C.byref(pop.d), self.x.ptr(), _lib.ptr(self.wf),
+                    _lib.ptr(self.b) if self.d.has_bias else None, _lib.ptr(pop.bias),
+                    self.y.ptr() if store_full else None, pop.y.ptr(),
+                    pop.argmax.ptr() if pop.argmax is not None else None, ws, ws_bytes, self.h.stream())
+
     def dgrad(self, dy, dx, accumulate=False, relu_gate=None):
         """relu_gate: post-ReLU output of the layer that produced x (fused ReLU backward)."""
         d = self._desc(x=dx, y=dy, accumulate=accumulate)

@@ -179,6 +179,17 @@ typedef struct {
 
 int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const float* bias, float* y,
                      int32_t* argmax, void* stream);
+/* The conv and the max-pool that consumes it as ONE launch: exactly e2_conv3d_fwd(d, ..., y) followed by
+ * e2_maxpool3d_fwd(p, y, pool_bias, yp, argmax) -- same values, same argmax, bit for bit -- with the window reduced in
+ * the conv kernel's epilogue, so the unpooled tensor is not read back (Conv nodes that carry a pool, neural.py:662-712:
+ * conv -> pool -> +bias -> act; and the Conv -> Pool pairs of the U-Nets, examples/unet3d.py:63-74).  p->x must describe
+ * the conv's output.  y may be NULL when the caller has no use for the unpooled tensor (fused problems only).
+ * e2_conv3d_fwd_pool_supported: 1 if the pair is fused (TF32 mode, windows of 1 or 2 per axis, a layer the z-stack
+ * kernel runs without a K split), 0 if e2_conv3d_fwd_pool would issue the two launches instead, < 0 on a bad descriptor. */
+int e2_conv3d_fwd_pool_supported(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p);
+int e2_conv3d_fwd_pool(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x, const float* wf,
+                       const float* bias, const float* pool_bias, float* y, float* yp, int32_t* argmax, void* ws,
+                       size_t ws_bytes, void* stream);
 /* E2_TIE_FIRST routes dy through argmax (x may be NULL); E2_TIE_ALL (Theano-CPU
  * semantics) needs x and the pooled pre-bias maximum is recomputed from it. */
 int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax, const float* x,
@@ -311,6 +322,10 @@ int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t
  * cuDNN's algorithm choice is opaque; used by tests/test_host_api.py to pin the planner.) */
 int e2_debug_zstack_plan(int sm_count, int K, int N, int Oz, int Ox, int Oy, int kz, int kx, int ky, int may_split,
                          int* out);
+/* The same for a conv whose max-pool (window qz,qx,qy) runs in the kernel's epilogue (e2_conv3d_fwd_pool): returns 1 and
+ * the plan if the pair is fused, 0 if it runs as two launches. */
+int e2_debug_zstack_pool_plan(int sm_count, int K, int N, int Oz, int Ox, int Oy, int kz, int kx, int ky, int qz, int qx,
+                              int qy, int* out);
 
 #ifdef __cplusplus
 }

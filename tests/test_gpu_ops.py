@@ -271,6 +271,94 @@ def test_maxpool_golden_and_fused_epilogue(h):
     assert np.array_equal(yd.numpy(), np.maximum(g['pool_y222'] + b.reshape(1, 3, 1, 1, 1), 0))
 
 
+# conv with the max-pool in its epilogue (e2_conv3d_fwd_pool): must equal the two separate launches BIT FOR BIT --
+# values, argmax (first maximum in (z,x,y) scan order, ties included) and the unpooled tensor when it is kept
+POOLFUSE_CASES = [
+    # (n, c_in, spatial, c_out, k, pool, own_pool, quantised)
+    (1, 32, (8, 20, 26), 64, (3, 3, 3), (2, 2, 2), False, False),    # unet3d conv1 -> Pool family, ragged x / y tiles
+    (1, 64, (10, 36, 20), 128, (3, 3, 3), (2, 2, 2), False, False),  # several x and y tiles, four channel chunks
+    (1, 20, (3, 30, 30), 20, (1, 3, 3), (1, 2, 2), False, False),    # unet3d_litelite: flat filter, in-plane pool
+    (2, 20, (5, 22, 22), 30, (1, 5, 5), (1, 2, 2), True, False),     # neuro3d: Conv carrying its pool (bias/act after), batch 2
+    (1, 40, (13, 32, 31), 80, (4, 4, 4), (2, 1, 1), True, False),    # neuro3d: z-only pool, kz = 4
+    (1, 32, (6, 16, 14), 40, (3, 3, 3), (2, 2, 2), True, True),      # integer data: exact ties among raw accumulators
+    (1, 32, (6, 16, 14), 40, (3, 3, 3), (2, 2, 2), False, True),
+    (1, 24, (4, 14, 22), 32, (1, 3, 3), (2, 2, 1), False, True),     # windows over z and x only
+]
+
+
+@pytest.mark.parametrize('train', [True, False])
+@pytest.mark.parametrize('case', POOLFUSE_CASES)
+def test_conv_pool_fused_equals_separate_launches(h, case, train):
+    from elektronn2_b200.ops import ConvOp, PoolOp
+    n, ci, sp, co, k, pool, own, quant = case
+    r = np.random.RandomState(abs(hash(case)) % 2**31)
+    if quant:
+        x = r.randint(0, 2, (n, ci) + sp).astype(np.float32)
+        w = r.randint(-1, 2, (co, ci) + k).astype(np.float32)
+        b = r.randint(-2, 3, co).astype(np.float32)
+    else:
+        x = r.rand(n, ci, *sp).astype(np.float32)
+        w = (r.randn(co, ci, *k) * np.sqrt(2.0 / (ci * np.prod(k)))).astype(np.float32)
+        b = (r.randn(co) * 0.1).astype(np.float32)
+    osp = [s - f + 1 for s, f in zip(sp, k)]
+    psp = [s // q for s, q in zip(osp, pool)]
+    xd = dev(x)
+
+    def run(fused):
+        yd, pd = empty(n, co, osp), empty(n, co, psp)
+        if own:     # conv -> pool -> +bias -> relu (neural.py:662-712)
+            op = ConvOp(h, xd, yd, t(w), None, k, 'lin', 'tf32')
+            pop = PoolOp(h, yd, pd, pool, bias=t(b), act='relu', keep_argmax=train, round_tf32=True)
+        else:       # Conv(relu) -> Pool
+            op = ConvOp(h, xd, yd, t(w), t(b), k, 'relu', 'tf32')
+            pop = PoolOp(h, yd, pd, pool, keep_argmax=train)
+        op.pack()
+        if fused:
+            assert op.pool_fusable(pop)
+            op.fwd_pool(pop, store_full=not own)
+        else:
+            op.fwd()
+            pop.fwd()
+        torch.cuda.synchronize()
+        return yd.numpy(), pd.numpy(), (pop.argmax.int_numpy() if train else None), op, pop
+
+    y0, p0, a0, _, _ = run(False)
+    y1, p1, a1, op, pop = run(True)
+    assert np.array_equal(p0, p1)
+    if train:
+        assert np.array_equal(a0, a1)
+        assert np.array_equal(a0, oo.pooling_argmax(y0, pool))     # and both are the oracle's argmax of the stored tensor
+    if own:
+        assert not y1.any()                                        # the unpooled tensor was not written
+    else:
+        assert np.array_equal(y0, y1)
+    ref = oo.conv3d(x, w)
+    ref = (np.maximum(oo.pooling(ref, pool) + b.reshape(1, -1, 1, 1, 1), 0) if own else
+           oo.pooling(np.maximum(ref + b.reshape(1, -1, 1, 1, 1), 0), pool))
+    assert rel(p1, ref) <= TOL['tf32']
+
+
+def test_conv_pool_unfusable_pairs_run_as_two_launches(h):
+    from elektronn2_b200.ops import ConvOp, PoolOp
+    r = np.random.RandomState(5)
+    x = r.rand(1, 16, 6, 14, 14).astype(np.float32)
+    w = (r.randn(24, 16, 3, 3, 3) * 0.1).astype(np.float32)
+    b = (r.randn(24) * 0.1).astype(np.float32)
+    xd, yd, pd = dev(x), empty(1, 24, (4, 12, 12)), empty(1, 24, (2, 6, 6))
+    op = ConvOp(h, xd, yd, t(w), t(b), (3, 3, 3), 'relu', 'f32')       # exact-fp32 mode never fuses
+    pop = PoolOp(h, yd, pd, (2, 2, 2))
+    op.pack()
+    assert not op.pool_fusable(pop)
+    n0 = h.launches
+    op.fwd_pool(pop, store_full=True)
+    assert h.launches - n0 == 2
+    y = yd.numpy()
+    assert np.array_equal(pd.numpy(), oo.pooling(y, (2, 2, 2))) and np.array_equal(pop.argmax.int_numpy(),
+                                                                                   oo.pooling_argmax(y, (2, 2, 2)))
+    with pytest.raises(ValueError):
+        op.fwd_pool(pop, store_full=False)      # nothing to pool from without the unpooled tensor
+
+
 def test_maxpool_rejects_non_dividing_axes(h):
     from elektronn2_b200.ops import PoolOp
     with pytest.raises(ValueError, match="cannot downsample"):

@@ -233,6 +233,26 @@ def test_zstack_planner_invariants():
     assert fn(148, 256, 512, 7, 9, 9, 3, 3, 3, 1, out) == 0                          # 9x9 planes: tap kernel
 
 
+def test_zstack_pool_fusion_plans():
+    """Conv + max-pool in one launch (e2_conv3d_fwd_pool): a tile must hold whole pool windows (TZ even for a z window
+    of 2), the pair is not fused where the conv would split K (its epilogue then lives in the reduce kernel), and the
+    three Conv -> Pool pairs of examples/unet3d.py keep the plan they have without the pool."""
+    import ctypes as C
+    from elektronn2_b200 import _lib
+    plain, fused = _lib.lib.e2_debug_zstack_plan, _lib.lib.e2_debug_zstack_pool_plan
+    a, b = (C.c_int * 8)(), (C.c_int * 8)()
+    for K, N, z, x, y in [(32, 64, 112, 128, 128), (64, 128, 52, 60, 60), (128, 256, 22, 26, 26)]:
+        assert plain(148, K, N, z, x, y, 3, 3, 3, 1, a) == 1 and fused(148, K, N, z, x, y, 3, 3, 3, 2, 2, 2, b) == 1
+        assert list(a) == list(b) and b[1] % 2 == 0 and b[2] == 1
+    # small layers: the plain plan has one output plane per tile, the fused one two
+    assert plain(148, 32, 64, 6, 18, 24, 3, 3, 3, 1, a) == 1 and a[1] == 1
+    assert fused(148, 32, 64, 6, 18, 24, 3, 3, 3, 2, 2, 2, b) == 1 and b[1] == 2
+    assert fused(148, 32, 64, 6, 18, 24, 3, 3, 3, 1, 2, 2, b) == 1 and b[1] == 1        # in-plane window: any TZ
+    assert fused(148, 768, 256, 12, 16, 16, 3, 3, 3, 2, 2, 2, b) == 0                    # K split wins
+    assert fused(148, 32, 64, 6, 18, 24, 3, 3, 3, 3, 2, 2, b) == 0                       # windows of 1 or 2 only
+    assert fused(148, 32, 64, 7, 18, 24, 3, 3, 3, 2, 2, 2, b) == 0                       # extents must divide
+
+
 def test_mdl_round_trip_uses_reference_module_paths(tmp_path):
     """``Model.save`` writes the reference's .mdl pickle (model.py:229-235, graphmanager.py:236-247): every global in
     the stream carries the REFERENCE's module path (so a Theano install can load it), and ``modelload`` brings back
