@@ -88,6 +88,10 @@ class F2DDesc(C.Structure):
     _fields_ = [('frag', Tensor), ('dense', Tensor), ('sz', i32), ('sx', i32), ('sy', i32)]
 
 
+class Window(C.Structure):
+    _fields_ = [('z0', i32), ('z1', i32), ('x0', i32), ('x1', i32), ('y0', i32), ('y1', i32)]
+
+
 class CropDesc(C.Structure):
     _fields_ = [('src', Tensor), ('dst', Tensor), ('oz', i32), ('ox', i32), ('oy', i32), ('dst_c0', i32),
                 ('accumulate', i32)]
@@ -113,7 +117,7 @@ SIGNATURES = {
     'e2_conv3d_workspace_size': (C.c_int, [P(ConvDesc), P(sz)]),
     'e2_conv3d_fwd': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_fwd_pool_supported': (C.c_int, [vp, P(ConvDesc), P(PoolDesc)]),
-    'e2_conv3d_fwd_pool': (C.c_int, [vp, P(ConvDesc), P(PoolDesc), vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    'e2_conv3d_fwd_pool': (C.c_int, [vp, P(ConvDesc), P(PoolDesc), vp, vp, vp, vp, vp, P(Window), vp, vp, vp, sz, vp]),
     'e2_conv3d_dgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_conv3d_wgrad': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     'e2_upconv3d_packed_floats': (C.c_int, [P(UpConvDesc), P(sz), P(sz)]),

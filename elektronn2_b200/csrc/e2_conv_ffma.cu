@@ -764,8 +764,8 @@ extern "C" int e2_conv3d_fwd(e2_handle* h, const e2_conv_desc* d, const float* x
 
 // ---- conv with the max-pool in its epilogue
 static int conv_pool_problem(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x, const float* wf,
-                             const float* bias, const float* pool_bias, float* y, float* yp, int32_t* argmax,
-                             GatherGemm* g) {
+                             const float* bias, const float* pool_bias, float* y, const e2_window* y_keep, float* yp,
+                             int32_t* argmax, GatherGemm* g) {
   int rc = check_conv(h, d);
   if (rc) return rc;
   E2_REQUIRE(h, p && e2_tensor_ok(&p->x) && e2_tensor_ok(&p->y), "conv3d_fwd_pool: bad pool descriptor");
@@ -779,6 +779,15 @@ static int conv_pool_problem(e2_handle* h, const e2_conv_desc* d, const e2_pool_
   g->fuse_pool = 1, g->qz = p->pz, g->qx = p->px, g->qy = p->py;
   g->Cp = yp, g->Ci = argmax, g->cp_pitch = p->y.c_pitch;
   g->pbias = p->has_bias ? pool_bias : nullptr, g->pact = p->act, g->pround = p->round_tf32;
+  if (y_keep) {
+    E2_REQUIRE(h, y_keep->z0 <= y_keep->z1 && y_keep->x0 <= y_keep->x1 && y_keep->y0 <= y_keep->y1,
+               "conv3d_fwd_pool: y_keep is not a half-open window");
+    g->keep[0] = y_keep->z0, g->keep[1] = y_keep->z1, g->keep[2] = y_keep->x0, g->keep[3] = y_keep->x1;
+    g->keep[4] = y_keep->y0, g->keep[5] = y_keep->y1;
+  } else {
+    g->keep[0] = g->keep[2] = g->keep[4] = 0;
+    g->keep[1] = d->y.z, g->keep[3] = d->y.x, g->keep[5] = d->y.y;
+  }
   return E2_OK;
 }
 
@@ -793,16 +802,17 @@ extern "C" int e2_conv3d_fwd_pool_supported(e2_handle* h, const e2_conv_desc* d,
   if (!h) return E2_ERR_INVALID;
   alignas(16) static float dummy[4];
   GatherGemm g;
-  int rc = conv_pool_problem(h, d, p, dummy, dummy, dummy, dummy, dummy, dummy, reinterpret_cast<int32_t*>(dummy), &g);
+  int rc = conv_pool_problem(h, d, p, dummy, dummy, dummy, dummy, dummy, nullptr, dummy, reinterpret_cast<int32_t*>(dummy), &g);
   if (rc) return rc;
   return conv_pool_fusable(h, d, p, g) ? 1 : 0;
 }
 
 extern "C" int e2_conv3d_fwd_pool(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x,
-                                  const float* wf, const float* bias, const float* pool_bias, float* y, float* yp,
-                                  int32_t* argmax, void* ws, size_t ws_bytes, void* stream) {
+                                  const float* wf, const float* bias, const float* pool_bias, float* y,
+                                  const e2_window* y_keep, float* yp, int32_t* argmax, void* ws, size_t ws_bytes,
+                                  void* stream) {
   GatherGemm g;
-  int rc = conv_pool_problem(h, d, p, x, wf, bias, pool_bias, y, yp, argmax, &g);
+  int rc = conv_pool_problem(h, d, p, x, wf, bias, pool_bias, y, y_keep, yp, argmax, &g);
   if (rc) return rc;
   E2_REQUIRE(h, x && wf && yp && (!d->has_bias || bias) && (!p->has_bias || pool_bias), "conv3d_fwd_pool: null pointer");
   if (conv_pool_fusable(h, d, p, g)) return e2_launch_conv_zstack_tc(h, g, (cudaStream_t)stream);

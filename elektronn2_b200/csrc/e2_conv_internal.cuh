@@ -30,6 +30,7 @@ struct GatherGemm {
   int cp_pitch;
   const float* pbias;
   int pact, pround;
+  int keep[6];   // window {z0,z1,x0,x1,y0,y1} of C the caller needs (tiles outside it are not stored)
 };
 
 // W[r][tap][s] = sum_m P[m][r] * Q[pos(m)*st + tap + org][s]

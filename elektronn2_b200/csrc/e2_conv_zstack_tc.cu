@@ -62,30 +62,33 @@ struct ZsParams {
   // epilogue above produces, then +pbias -> pact -> tf32 round; argmax = first maximum in (z,x,y) scan order
   int pool, ppz, ppx, ppy;
   int store_full;                // also store the unpooled tile through tmC (0: the caller does not want that tensor)
+  int kz0, kz1, kx0, kx1, ky0, ky1;   // ... but only the [32 ch x 8 y x 4 x] boxes that intersect this window (half-open)
   int pool_amax;                 // store the argmax tile through tmI
   const float* pbias;
   int pact, pround;
 };
 
-// One butterfly step of the pooled reduction: every lane holds, per channel j, its best value pv[j] and where it came
-// from as bit j of (mz, mx, my) = offsets inside the window.  The partner's candidate replaces it when it is larger, or
-// equal and EARLIER in (z,x,y) scan order -- so the result is (max value, first position), whatever the merge order.
-__device__ __forceinline__ void zs_pool_merge(float (&pv)[32], uint32_t& mz, uint32_t& mx, uint32_t& my, int xor_lane) {
-  const uint32_t pmz = __shfl_xor_sync(0xffffffffu, mz, xor_lane);
-  const uint32_t pmx = __shfl_xor_sync(0xffffffffu, mx, xor_lane);
-  const uint32_t pmy = __shfl_xor_sync(0xffffffffu, my, xor_lane);
-  // bit j: partner's (dz,dx,dy) < mine, lexicographically
-  const uint32_t lt = (~pmz & mz) | (~(pmz ^ mz) & ((~pmx & mx) | (~(pmx ^ mx) & (~pmy & my))));
-  uint32_t take = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float o = __shfl_xor_sync(0xffffffffu, pv[j], xor_lane);
-    const bool t = (o > pv[j]) || (o == pv[j] && ((lt >> j) & 1u));
-    if (t) pv[j] = o, take |= 1u << j;
-  }
-  mz = (mz & ~take) | (pmz & take);
-  mx = (mx & ~take) | (pmx & take);
-  my = (my & ~take) | (pmy & take);
+// Fused max-pool, argmax part.  Every lane of a 2x2 (x,y) window group knows the window maximum m[j]; `e` = bit j set
+// if this lane's column (its own position, best of the two planes) attains it, `mz` = bit j set if the column's best
+// came from the second plane.  Seen from the lane at the window's origin the other columns sit at lane ^ 1 (dy = 1),
+// lane ^ 8 (dx = 1) and lane ^ 9, so six shuffles bring all masks together and the FIRST maximum in (z,x,y) scan order
+// -- candidates ordered (dz,dx,dy) -- is picked for all 32 channels at once with bitwise logic.
+__device__ __forceinline__ void zs_pool_first(uint32_t e, uint32_t mz, bool has_x, bool has_y, uint32_t& rz, uint32_t& rx,
+                                              uint32_t& ry) {
+  const uint32_t e01 = __shfl_xor_sync(0xffffffffu, e, 1), z01 = __shfl_xor_sync(0xffffffffu, mz, 1);
+  const uint32_t e10 = __shfl_xor_sync(0xffffffffu, e, 8), z10 = __shfl_xor_sync(0xffffffffu, mz, 8);
+  const uint32_t e11 = __shfl_xor_sync(0xffffffffu, e, 9), z11 = __shfl_xor_sync(0xffffffffu, mz, 9);
+  const uint32_t E00 = e, E01 = has_y ? e01 : 0u, E10 = has_x ? e10 : 0u, E11 = (has_x && has_y) ? e11 : 0u;
+  uint32_t found, c;
+  rz = rx = ry = 0u;
+  found = E00 & ~mz;                                                  // (0,0,0)
+  c = E01 & ~z01 & ~found, ry |= c, found |= c;                       // (0,0,1)
+  c = E10 & ~z10 & ~found, rx |= c, found |= c;                       // (0,1,0)
+  c = E11 & ~z11 & ~found, rx |= c, ry |= c, found |= c;              // (0,1,1)
+  c = E00 & mz & ~found, rz |= c, found |= c;                         // (1,0,0)
+  c = E01 & z01 & ~found, rz |= c, ry |= c, found |= c;               // (1,0,1)
+  c = E10 & z10 & ~found, rz |= c, rx |= c, found |= c;               // (1,1,0)
+  c = E11 & z11 & ~found, rz |= c, rx |= c, ry |= c;                  // (1,1,1)
 }
 
 // lean bounded wait for the issuing warp (all lanes poll; try_wait suspends in hardware)
@@ -442,7 +445,10 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
               }
-              if (p.store_full) {
+              // fused pool: the caller may need only a window of the unpooled tensor (the skip connection's crop)
+              const bool keep = p.store_full && (!p.pool || (z0 + zl >= p.kz0 && z0 + zl < p.kz1 && x0 + 4 * q + 4 > p.kx0 &&
+                                                             x0 + 4 * q < p.kx1 && y0 + TY > p.ky0 && y0 < p.ky1));
+              if (keep) {
                 // each lane reads and writes only its own 128-byte row of the buffer: no cross-lane hazard
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -472,10 +478,30 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
             // lane = x-line (lane >> 3) x y (lane & 7) of the 4 x 8 position patch; window partners are lane ^ 1
             // (y) and lane ^ 8 (x).  After the merges the lane at a window's origin holds (max, first argmax).
             const int xl = lane >> 3, yy = lane & 7;
-            uint32_t mx = (p.ppx == 2 && (xl & 1)) ? 0xffffffffu : 0u;
-            uint32_t my = (p.ppy == 2 && (yy & 1)) ? 0xffffffffu : 0u;
-            if (p.ppy == 2) zs_pool_merge(pv, mz, mx, my, 1);
-            if (p.ppx == 2) zs_pool_merge(pv, mz, mx, my, 8);
+            // window maximum: two butterfly steps of plain maxima (relu outputs / accumulators: no -0 vs +0 question
+            // in practice -- max.f32 orders -0 below +0, the pool kernel keeps the first of equal values)
+            float m[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m[j] = pv[j];
+            if (p.ppy == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], 1));
+            }
+            if (p.ppx == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], 8));
+            }
+            uint32_t mx = 0, my = 0;
+            if (p.pool_amax) {
+              uint32_t e = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) e |= (pv[j] == m[j]) ? (1u << j) : 0u;
+              uint32_t rz;
+              zs_pool_first(e, mz, p.ppx == 2, p.ppy == 2, rz, mx, my);
+              mz = rz;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pv[j] = m[j];
             if (p.pbias) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -832,6 +858,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
     if (split) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: fused pool with a K split");
     p.pool = 1, p.ppz = g.qz, p.ppx = g.qx, p.ppy = g.qy;
     p.store_full = g.C != nullptr, p.pool_amax = g.Ci != nullptr;
+    p.kz0 = g.keep[0], p.kz1 = g.keep[1], p.kx0 = g.keep[2], p.kx1 = g.keep[3], p.ky0 = g.keep[4], p.ky1 = g.keep[5];
     p.pbias = g.pbias, p.pact = g.pact, p.pround = g.pround;
   } else {
     p.store_full = 1;

@@ -540,6 +540,117 @@ static bool plan_mfp_tile(const PoolP& p, MfpTile* m, size_t* smem) {
   return true;
 }
 
+// Sliding form of the forward pass (round 2, default for windows of 1 or 2 per axis).  Max-fragment-pooling is a
+// STRIDE-1 max-pool whose outputs are de-interleaved: the window starting at (sz,sx,sy) goes to fragment
+// (sz % pz, sx % px, sy % py) at position (sz / pz, sx / px, sy / py).  The row kernel above computes every fragment's
+// windows from scratch, so each input element travels from L2 prod(p) times (2.0 - 2.6 TB/s algorithmic on the
+// dense-prediction tile: the L2, not HBM, was the limit).  Here a thread owns (sy, 4 channels) at a fixed coordinate of
+// one outer axis and WALKS the other one (x for in-plane windows, z when the window spans z): per step it loads the
+// cross-section of the window once, keeps the previous step's partial maximum in registers, and emits one output --
+// every input element is loaded once per thread that needs it (py times, neighbours in L1), not prod(p) times.
+// Ties: each partial result is (max value, smallest linear index); merges compare the index on equal values, so the
+// argmax is the first maximum in (z,x,y) scan order whatever the merge order.
+template <int PZ, int PX, int PY, bool WALKZ, bool AMAX>
+__global__ void __launch_bounds__(256) k_mfp_fwd_slide(PoolP p, int seg, int nseg, int nchunks, E2FastDiv dcv,
+                                                       const float* __restrict__ x, const float* __restrict__ bias,
+                                                       float* __restrict__ y, int* __restrict__ amax) {
+  constexpr int PW = WALKZ ? PZ : PX;      // window extent along the walking axis
+  constexpr int PA = WALKZ ? PX : PZ;      // cross-section: the fixed outer axis ... and y (PY)
+  static_assert(PW == 2, "the walking axis is one the window spans");
+  const int cv = (p.C + 3) / 4;
+  const int Sz = p.Z - PZ + 1, Sx = p.X - PX + 1, Sy = p.Y - PY + 1;   // window start positions per axis
+  const int Sf = WALKZ ? Sx : Sz, Sw = WALKZ ? Sz : Sx;
+  int b = blockIdx.x;
+  const int chunk = b % nchunks;
+  b /= nchunks;
+  const int f = b % Sf;                    // neighbouring blocks share cross-section rows through L2
+  b /= Sf;
+  const int sg = b % nseg;
+  const int n = b / nseg;
+  const int t = chunk * 256 + threadIdx.x;
+  if (t >= Sy * cv) return;
+  const int sy = (int)dcv.div((uint32_t)t);
+  const int c = (t - sy * cv) * 4;
+  const int w0 = sg * seg, w1 = min(Sw, w0 + seg);
+  const int sw = WALKZ ? p.X * p.Y : p.Y;  // input positions per step of the walking axis
+  const int sf = WALKZ ? p.Y : p.X * p.Y;  // ... and of the fixed axis
+  const float* xn = x + (int64_t)n * p.Z * p.X * p.Y * p.xp + c;
+  float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.has_bias) {
+    bz.x = c + 0 < p.C ? __ldg(bias + c + 0) : 0.f, bz.y = c + 1 < p.C ? __ldg(bias + c + 1) : 0.f;
+    bz.z = c + 2 < p.C ? __ldg(bias + c + 2) : 0.f, bz.w = c + 3 < p.C ? __ldg(bias + c + 3) : 0.f;
+  }
+  // maximum over the window's cross-section at walking coordinate wp; loads in ascending linear index, strict '>'
+  auto cross = [&](int wp, float (&v)[4], int (&li)[4]) {
+#pragma unroll
+    for (int da = 0; da < PA; ++da)
+#pragma unroll
+      for (int dy = 0; dy < PY; ++dy) {
+        const int lin = wp * sw + (f + da) * sf + sy + dy;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(xn + (int64_t)lin * p.xp));
+        const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((da == 0 && dy == 0) || e[j] > v[j]) {
+            v[j] = e[j];
+            if (AMAX) li[j] = lin;
+          }
+      }
+  };
+  float g0[4], g1[4];
+  int l0[4], l1[4];
+  cross(w0, g0, l0);
+#pragma unroll 2
+  for (int w = w0; w < w1; ++w) {
+    cross(w + 1, g1, l1);
+    float o[4];
+    int oi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // walking along z the later cross-section has the larger index: strict '>' is enough; walking along x with a
+      // window over z it has not (dz outranks dx), so equal values compare their indices
+      const bool take = g1[j] > g0[j] || (AMAX && !WALKZ && PA > 1 && g1[j] == g0[j] && l1[j] < l0[j]);
+      float r2 = take ? g1[j] : g0[j];
+      if (AMAX) oi[j] = take ? l1[j] : l0[j];
+      if (c + j < p.C) {
+        r2 += j == 0 ? bz.x : j == 1 ? bz.y : j == 2 ? bz.z : bz.w;     // reference order: pool -> +bias -> act
+        r2 = e2_apply_act(r2, p.act);
+        o[j] = p.round_tf32 ? e2_round_tf32(r2) : r2;
+      } else {
+        o[j] = 0.f;                                                      // pad lane
+      }
+      g0[j] = g1[j];
+      if (AMAX) l0[j] = l1[j];
+    }
+    const int sz = WALKZ ? w : f, sx = WALKZ ? f : w;
+    const int off = ((sz % PZ) * PX + sx % PX) * PY + sy % PY;           // itertools.product order, last axis fastest
+    const int fr = off * p.n + n;
+    const int64_t oofs = ((((int64_t)fr * p.Zo + sz / PZ) * p.Xo + sx / PX) * p.Yo + sy / PY) * p.yp + c;
+    *reinterpret_cast<float4*>(y + oofs) = make_float4(o[0], o[1], o[2], o[3]);
+    if (AMAX) *reinterpret_cast<int4*>(amax + oofs) = make_int4(oi[0], oi[1], oi[2], oi[3]);
+  }
+}
+
+template <int PZ, int PX, int PY, bool WALKZ>
+static void launch_mfp_slide(const PoolP& p, int sm_count, const float* x, const float* bias, float* y, int* amax,
+                             cudaStream_t s) {
+  const int cv = (p.C + 3) / 4;
+  const int Sz = p.Z - PZ + 1, Sx = p.X - PX + 1, Sy = p.Y - PY + 1;
+  const int Sf = WALKZ ? Sx : Sz, Sw = WALKZ ? Sz : Sx;
+  const int nchunks = (Sy * cv + 255) / 256;
+  // segments of the walking axis: long enough that the one re-read cross-section per segment is small change, short
+  // enough for a few waves of blocks
+  int seg = 16;
+  while (seg > 4 && (int64_t)p.n * ((Sw + seg - 1) / seg) * Sf * nchunks < 8ll * sm_count) seg /= 2;
+  const int nseg = (Sw + seg - 1) / seg;
+  const unsigned grid = (unsigned)((int64_t)p.n * nseg * Sf * nchunks);
+  const E2FastDiv dv = e2_fastdiv((uint32_t)cv, (uint64_t)Sy * cv);
+  if (amax)
+    k_mfp_fwd_slide<PZ, PX, PY, WALKZ, true><<<grid, 256, 0, s>>>(p, seg, nseg, nchunks, dv, x, bias, y, amax);
+  else
+    k_mfp_fwd_slide<PZ, PX, PY, WALKZ, false><<<grid, 256, 0, s>>>(p, seg, nseg, nchunks, dv, x, bias, y, amax);
+}
+
 // Gather form (no atomics, deterministic): each input element checks the prod(p) windows
 // (one per fragment offset) that contain it.
 template <int V>
@@ -622,7 +733,8 @@ extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, co
   E2_REQUIRE(h, rows < (1ll << 31), "mfp_fwd: too many rows");
   MfpTile mt;
   size_t smem = 0;
-  static const bool use_tile = getenv("E2_MFP_TILE") != nullptr;      // A/B switch for profiling (default: row kernel)
+  static const bool use_tile = getenv("E2_MFP_TILE") != nullptr;      // A/B switches for profiling (default: sliding kernel)
+  static const bool row_only = getenv("E2_MFP_ROW") != nullptr;       // the round-1 row kernel
   if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp) && use_tile &&
       p.xp == 4 * ((p.C + 3) / 4) && p.yp == p.xp && plan_mfp_tile(p, &mt, &smem) && (int64_t)p.n * p.Zo * p.Xo * mt.n_chunks < (1ll << 31)) {
     if (smem > 48 * 1024 &&
@@ -630,6 +742,15 @@ extern "C" int e2_mfp_fwd(e2_handle* h, const e2_mfp_desc* d, const float* x, co
       return e2_fail(h, E2_ERR_CUDA, "mfp_fwd: cudaFuncSetAttribute(max dynamic smem) failed");
     k_mfp_fwd_tile<<<(unsigned)((int64_t)p.n * p.Zo * p.Xo * mt.n_chunks), 256, smem, (cudaStream_t)stream>>>(
         p, mt, e2_fastdiv((p.C + 3) / 4, (uint64_t)mt.yc * ((p.C + 3) / 4)), x, bias, y, argmax);
+  } else if (!row_only && vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp) &&
+             ((p.pz == 1 && p.px == 2 && p.py == 2) || (p.pz == 2 && p.px == 1 && p.py == 1) ||
+              (p.pz == 2 && p.px == 2 && p.py == 2) || (p.pz == 1 && p.px == 2 && p.py == 1)) &&
+             (int64_t)p.n * p.Z * p.X * ((p.Y * ((p.C + 3) / 4) + 255) / 256) < (1ll << 31)) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p.pz == 1 && p.py == 2) launch_mfp_slide<1, 2, 2, false>(p, h->sm_count, x, bias, y, argmax, s);
+    else if (p.pz == 1) launch_mfp_slide<1, 2, 1, false>(p, h->sm_count, x, bias, y, argmax, s);
+    else if (p.px == 1) launch_mfp_slide<2, 1, 1, true>(p, h->sm_count, x, bias, y, argmax, s);
+    else launch_mfp_slide<2, 2, 2, true>(p, h->sm_count, x, bias, y, argmax, s);
   } else if (vec4_ok({x, y, argmax}, {p.xp, p.yp}) && pad4_ok(p.C, p.xp) && pad4_ok(p.C, p.yp)) {
     const int rowlen = p.Yo * ((p.C + 3) / 4);
     k_mfp_fwd<4><<<(int)rows, pool_block(rowlen), 0, (cudaStream_t)stream>>>(p, e2_fastdiv((p.C + 3) / 4, rowlen), x, bias, y, argmax);

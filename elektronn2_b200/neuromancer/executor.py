@@ -394,7 +394,8 @@ class Plan(object):
                 else:
                     pop = None
             if pop is not None:
-                self._f('conv_fwd:' + n.name, lambda op=op, pop=pop: op.fwd_pool(pop, True), flops,
+                keep = self._keep_window(n, pn)
+                self._f('conv_fwd:' + n.name, lambda op=op, pop=pop, keep=keep: op.fwd_pool(pop, True, keep), flops,
                         4 * (_nel(x) + _nel(y) + 2 * _nel(pop.y)), kind)
             else:
                 self._f('conv_fwd:' + n.name, op.fwd, flops, 4 * (_nel(x) + _nel(y)), kind)
@@ -438,6 +439,27 @@ class Plan(object):
         if any(p not in (1, 2) for p in p3) or all(p == 1 for p in p3):
             return None
         return pools[0]
+
+    def _keep_window(self, n, pool_node):
+        """Window (z0,z1,x0,x1,y0,y1) of Conv ``n``'s unpooled output that anything but its fused Pool reads, or None
+        for all of it.  In the U-Nets the only other reader is the skip connection's Crop (a few percent of the
+        tensor): the pool backward gates with the pooled values, the crop backward reads the gate inside its window,
+        and a ReLU layer whose gradient contributions are all gated needs no activation backward of its own."""
+        if os.environ.get('E2_KEEP_FULL') or n in self.outputs or n.activation_func not in ('relu', 'lin', 'linear'):
+            return None
+        sp = _sp3(n.shape.spatial_shape)
+        lo, hi = list(sp), [0, 0, 0]
+        for c in self._consumers(n):
+            if c is pool_node:
+                continue
+            if not isinstance(c, Crop) or c.parent is not n:
+                return None
+            cr = _sp3(c.crop, 0)
+            for a in range(3):
+                lo[a], hi[a] = min(lo[a], cr[a]), max(hi[a], sp[a] - cr[a])
+        if any(h <= l for l, h in zip(lo, hi)):
+            lo, hi = [0, 0, 0], [0, 0, 0]       # no other reader at all
+        return (lo[0], hi[0], lo[1], hi[1], lo[2], hi[2])
 
     def _unfused(self, n):
         """Does this Conv / UpConv need the separate epilogue kernel?  Batch normalisation and prelu always; 'abs'

@@ -67,13 +67,15 @@ class ConvOp(object):
             return False
         return self.h.query('e2_conv3d_fwd_pool_supported', C.byref(self.d), C.byref(pop.d)) == 1
 
-    def fwd_pool(self, pop, store_full=True):
+    def fwd_pool(self, pop, store_full=True, keep=None):
         """conv -> max-pool in one launch (e2_conv3d_fwd_pool): the same bits as ``self.fwd(); pop.fwd()``;
-        with store_full=False the unpooled tensor is not written at all."""
+        with store_full=False the unpooled tensor is not written at all, with keep=(z0,z1,x0,x1,y0,y1) only the
+        part of it inside that window is guaranteed to be."""
         ws, ws_bytes = self.h.workspace()
+        win = C.byref(_lib.Window(*[int(v) for v in keep])) if keep is not None else None
         self.h.call('e2_conv3d_fwd_pool', C.byref(self.d), C.byref(pop.d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if self.d.has_bias else None, _lib.ptr(pop.bias),
-                    self.y.ptr() if store_full else None, pop.y.ptr(),
+                    self.y.ptr() if store_full else None, win, pop.y.ptr(),
                     pop.argmax.ptr() if pop.argmax is not None else None, ws, ws_bytes, self.h.stream())
 
     def dgrad(self, dy, dx, accumulate=False, relu_gate=None):

@@ -183,13 +183,16 @@ int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const 
  * e2_maxpool3d_fwd(p, y, pool_bias, yp, argmax) -- same values, same argmax, bit for bit -- with the window reduced in
  * the conv kernel's epilogue, so the unpooled tensor is not read back (Conv nodes that carry a pool, neural.py:662-712:
  * conv -> pool -> +bias -> act; and the Conv -> Pool pairs of the U-Nets, examples/unet3d.py:63-74).  p->x must describe
- * the conv's output.  y may be NULL when the caller has no use for the unpooled tensor (fused problems only).
+ * the conv's output.  y may be NULL when the caller has no use for the unpooled tensor (fused problems only); y_keep
+ * (nullable = everything) names the window of y the caller will read -- the skip connection's Crop, neural.py:1152-1168
+ * -- and only that part of y is guaranteed to be written (the fused kernel stores the tiles that intersect it).
  * e2_conv3d_fwd_pool_supported: 1 if the pair is fused (TF32 mode, windows of 1 or 2 per axis, a layer the z-stack
  * kernel runs without a K split), 0 if e2_conv3d_fwd_pool would issue the two launches instead, < 0 on a bad descriptor. */
 int e2_conv3d_fwd_pool_supported(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p);
+typedef struct { int32_t z0, z1, x0, x1, y0, y1; } e2_window; /* half-open ranges of positions */
 int e2_conv3d_fwd_pool(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x, const float* wf,
-                       const float* bias, const float* pool_bias, float* y, float* yp, int32_t* argmax, void* ws,
-                       size_t ws_bytes, void* stream);
+                       const float* bias, const float* pool_bias, float* y, const e2_window* y_keep, float* yp,
+                       int32_t* argmax, void* ws, size_t ws_bytes, void* stream);
 /* E2_TIE_FIRST routes dy through argmax (x may be NULL); E2_TIE_ALL (Theano-CPU
  * semantics) needs x and the pooled pre-bias maximum is recomputed from it. */
 int e2_maxpool3d_bwd(e2_handle* h, const e2_pool_desc* d, const float* dy, const int32_t* argmax, const float* x,

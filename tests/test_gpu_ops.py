@@ -338,6 +338,35 @@ def test_conv_pool_fused_equals_separate_launches(h, case, train):
     assert rel(p1, ref) <= TOL['tf32']
 
 
+def test_conv_pool_fused_keeps_the_requested_window(h):
+    """y_keep of e2_conv3d_fwd_pool: the window of the unpooled tensor the caller reads (a skip connection's Crop) is
+    written exactly; whole tiles outside it are skipped (the buffer keeps its zeros there); pooled outputs unaffected."""
+    from elektronn2_b200.ops import ConvOp, PoolOp
+    r = np.random.RandomState(11)
+    x = r.rand(1, 32, 10, 40, 30).astype(np.float32)
+    w = (r.randn(64, 32, 3, 3, 3) * 0.05).astype(np.float32)
+    b = (r.randn(64) * 0.1).astype(np.float32)
+    osp, psp = (8, 38, 28), (4, 19, 14)
+    xd = dev(x)
+    outs = []
+    for keep in (None, (2, 6, 9, 30, 6, 20), (0, 0, 0, 0, 0, 0)):
+        yd, pd = empty(1, 64, osp), empty(1, 64, psp)
+        op = ConvOp(h, xd, yd, t(w), t(b), (3, 3, 3), 'relu', 'tf32')
+        pop = PoolOp(h, yd, pd, (2, 2, 2))
+        op.pack()
+        assert op.pool_fusable(pop)
+        op.fwd_pool(pop, True, keep)
+        outs.append((yd.numpy(), pd.numpy(), pop.argmax.int_numpy()))
+    (y0, p0, a0), (y1, p1, a1), (y2, p2, a2) = outs
+    assert np.array_equal(p0, p1) and np.array_equal(a0, a1) and np.array_equal(p0, p2) and np.array_equal(a0, a2)
+    assert np.array_equal(y1[:, :, 2:6, 9:30, 6:20], y0[:, :, 2:6, 9:30, 6:20])
+    written = y1 != 0
+    assert not written[:, :, :2].any() and not written[:, :, 6:].any()       # planes outside the window: untouched
+    assert not written[:, :, :, :8].any() and not written[:, :, :, 32:].any()   # x boxes of 4: [8,32) covers [9,30)
+    assert np.array_equal(y1[written], y0[written])
+    assert not y2.any()
+
+
 def test_conv_pool_unfusable_pairs_run_as_two_launches(h):
     from elektronn2_b200.ops import ConvOp, PoolOp
     r = np.random.RandomState(5)
@@ -367,7 +396,10 @@ def test_maxpool_rejects_non_dividing_axes(h):
 
 # --------------------------------------------------------------------------- MFP
 @pytest.mark.parametrize('case', [(1, 3, (7, 9, 11), (2, 2, 2)), (1, 20, (5, 13, 13), (1, 2, 2)),
-                                  (4, 8, (7, 7, 7), (2, 1, 1)), (1, 5, (9, 8, 11), (2, 3, 2))])
+                                  (4, 8, (7, 7, 7), (2, 1, 1)), (1, 5, (9, 8, 11), (2, 3, 2)),
+                                  # the sliding kernel with several row chunks and several segments of the walking axis
+                                  (1, 30, (6, 41, 43), (1, 2, 2)), (1, 80, (37, 9, 10), (2, 1, 1)),
+                                  (1, 12, (19, 21, 23), (2, 2, 2)), (1, 8, (4, 9, 6), (1, 2, 1))])
 def test_mfp_bit_exact_fragment_order(h, case):
     from elektronn2_b200.ops import MfpOp, Frag2DenseOp
     n, c, sp, p = case
