@@ -250,7 +250,8 @@ def main():
     if dp is not None:
         dp.broadcast_parameters(plan.store)
     opt = model.optimisers['Adam']
-    launches_per_step = plan.launches_per_step() + 4    # + adam_prepare and the three Adam region launches
+    # forward + backward launches (counted by the library in an eager pass) + the optimiser / re-pack launches of the step
+    launches_per_step = plan.launches_per_step(with_pack=False) + plan.update_launches(opt)
     n_vox = float(np.prod(x.shape)) * world
 
     def barrier():
@@ -300,7 +301,7 @@ def main():
 
     # ---- roofline of the dominant kernel family (eager, per-launch CUDA events) ---------
     peaks = load_peaks()
-    prof = plan.profile(repeats=3)
+    prof = plan.profile(repeats=3, opt=opt)
     step_ms = sum(p[4] for p in prof)
     fam = {}
     for label, kind, flops, nbytes, ms in prof:

@@ -141,6 +141,8 @@ SIGNATURES = {
     'e2_sgd_step': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     'e2_adam_prepare': (C.c_int, [vp, vp, vp, vp]),
     'e2_adam_step_dev': (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, C.c_float, vp]),
+    'e2_conv3d_adam_pack_dev': (C.c_int, [vp, P(ConvDesc), vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]),
+    'e2_upconv3d_adam_pack_dev': (C.c_int, [vp, P(UpConvDesc), vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]),
     'e2_bn_batch_stats': (C.c_int, [vp, P(Tensor), vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp]),
     'e2_bn_fold': (C.c_int, [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]),
     'e2_affine_act_fwd': (C.c_int, [vp, P(AffineDesc), vp, vp, vp, vp, vp, vp]),

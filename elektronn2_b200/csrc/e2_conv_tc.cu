@@ -13,6 +13,8 @@
 //   roles   = warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 //             (tcgen05.ld -> +bias -> activation -> (accumulate) -> store).
 // Several CTAs share an SM (smem permitting), so one CTA's epilogue overlaps another's MMAs.
+#include <algorithm>
+#include <stdlib.h>
 #include "e2_common.cuh"
 #include "e2_conv_internal.cuh"
 #include "e2_tc_ptx.cuh"
@@ -27,7 +29,7 @@ constexpr int NUM_THREADS = (2 + EPI_WARPS) * 32;
 
 struct TcParams {
   int On, Oz, Ox, Oy;        // output position grid
-  int tz, tx, ty;            // tile box (tz*tx*ty == 128)
+  int tz, tx, ty;            // tile box (tz*tx*ty <= 128 rows; the rest of the 128-row operand tile is masked)
   int ntz, ntx, nty;         // tiles per axis
   int kz, kx, ky;            // taps
   int oz, ox, oy;            // origin
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
         const int s = li % p.stages;
         const uint32_t ph = (uint32_t)(li / p.stages) & 1u;
         tc::mbar_wait(&empty[s], ph ^ 1u);
-        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
+        tc::mbar_arrive_expect_tx(&full[s], (uint32_t)(p.tz * p.tx * p.ty * BK * 4 + b_stage_bytes));
         tc::tma_load_5d(smA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, y0 * p.sy + k3 + p.oy,
                         x0 * p.sx + j3 + p.ox, z0 * p.sz + i3 + p.oz, in_);
         tc::tma_load_3d(smB + s * b_stage_bytes, &tmB, &full[s], kb * BK, tap, n0);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(NUM_THREADS) k_gather_gemm_tc(const __grid_con
       const int rr = q * 32 + (vec_ok ? it * 4 + rsub : lane);
       const int ry = rr % p.ty, rx = (rr / p.ty) % p.tx, rz = rr / (p.ty * p.tx);
       const int pz_ = z0 + rz, px_ = x0 + rx, py_ = y0 + ry;
-      if (pz_ < p.Oz && px_ < p.Ox && py_ < p.Oy) rowmask |= 1u << it;
+      if (rz < p.tz && pz_ < p.Oz && px_ < p.Ox && py_ < p.Oy) rowmask |= 1u << it;   // rz >= tz: row behind the box
       rowofs[it] = p.shuffle ? ((((int64_t)in_ * (p.Oz * p.pz) + pz_ * p.pz) * (p.Ox * p.px) + px_ * p.px) * (p.Oy * p.py) +
                                 py_ * p.py) * p.c_pitch
                              : ((((int64_t)in_ * p.Oz + pz_) * p.Ox + px_) * p.Oy + py_) * p.c_pitch;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(BM) k_gather_gemm_reduce(const TcParams p, int
   const int in_ = tile / p.ntz;
   const int ly = row % p.ty, lx = (row / p.ty) % p.tx, lz = row / (p.ty * p.tx);
   const int oz = itz * p.tz + lz, ox = itx * p.tx + lx, oy = ity * p.ty + ly;
-  if (oz >= p.Oz || ox >= p.Ox || oy >= p.Oy) return;
+  if (lz >= p.tz || oz >= p.Oz || ox >= p.Ox || oy >= p.Oy) return;
   const int64_t pos = (((int64_t)in_ * p.Oz + oz) * p.Ox + ox) * p.Oy + oy;
   const float v[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
@@ -356,22 +358,38 @@ EncodeTiledFn e2_get_tmap_encode() {
 namespace {
 
 bool pick_tile(int Oz, int Ox, int Oy, int sz, int sx, int sy, int* tz, int* tx, int* ty) {
-  // all (tz,tx,ty) with product 128; minimise padded volume, prefer long y runs
-  static const int opts[][3] = {{1, 8, 16}, {2, 8, 8},  {1, 4, 32}, {2, 4, 16}, {4, 4, 8},  {1, 16, 8}, {1, 2, 64},
-                                {2, 2, 32}, {4, 8, 4},  {8, 4, 4},  {1, 1, 128}, {2, 16, 4}, {4, 2, 16}, {1, 32, 4},
-                                {2, 1, 64}, {4, 1, 32}, {8, 2, 8},  {8, 1, 16}, {16, 2, 4}, {8, 8, 2},  {4, 16, 2},
-                                {2, 32, 2}, {1, 64, 2}, {16, 4, 2}, {16, 8, 1}, {8, 16, 1}, {4, 32, 1}, {2, 64, 1},
-                                {1, 128, 1}, {32, 2, 2}, {32, 4, 1}, {16, 1, 8}, {32, 1, 4}};
-  int64_t best = -1;
-  for (auto& o : opts) {
-    if (o[0] * sz > 256 || o[1] * sx > 256 || o[2] * sy > 256) continue;   // TMA box extent limit (strided gather)
-    int64_t v = (int64_t)((Oz + o[0] - 1) / o[0]) * o[0] * ((Ox + o[1] - 1) / o[1]) * o[1] * ((Oy + o[2] - 1) / o[2]) * o[2];
-    if (best < 0 || v < best) {
-      best = v;
-      *tz = o[0], *tx = o[1], *ty = o[2];
+  // The M tile is a (tz, tx, ty) box of up to 128 output positions -- ANY extents, not only powers of two: the TMA box
+  // fills tz*tx*ty rows of the 128-row operand tile and the rows behind them are masked in the epilogue (MMA rows are
+  // independent).  Every tile costs a full M = 128 MMA whatever its fill, so the box that needs the fewest tiles wins
+  // (unet3d conv7, 7x9x9 positions: five (7,2,9) boxes at 90 % fill instead of nine (8,4,4) boxes at 49 %);
+  // ties go to the longer y run (contiguous stores), then to the smaller padded volume.
+  static const bool pow2_only = getenv("E2_TC_POW2_TILES") != nullptr;     // A/B switch: round-1 behaviour
+  int64_t best_tiles = -1, best_vol = 0;
+  int best_ty = 0;
+  for (int z = 1; z <= 128 && z <= Oz; ++z) {
+    if (z * sz > 256) break;                                              // TMA box extent limit (strided gather)
+    for (int x = 1; x * z <= 128 && x <= Ox; ++x) {
+      if (x * sx > 256) break;
+      const int ymax = std::min(std::min(128 / (z * x), Oy), 256 / sy);
+      if (ymax < 1) continue;
+      const int ny = (Oy + ymax - 1) / ymax;
+      const int cand[2] = {ymax, (Oy + ny - 1) / ny};                     // widest, and the balanced split of the y axis
+      for (int y : cand) {
+        if (pow2_only && ((z & (z - 1)) || (x & (x - 1)) || (y & (y - 1)) || z * x * y != 128)) continue;
+        const int64_t tiles = (int64_t)((Oz + z - 1) / z) * ((Ox + x - 1) / x) * ((Oy + y - 1) / y);
+        const int64_t vol = tiles * z * x * y;
+        if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && (y > best_ty || (y == best_ty && vol < best_vol)))) {
+          best_tiles = tiles, best_vol = vol, best_ty = y;
+          *tz = z, *tx = x, *ty = y;
+        }
+      }
     }
   }
-  return best > 0;
+  if (best_tiles < 0 && pow2_only) {   // shapes smaller than every power-of-two box: fall back to the free search
+    *tz = std::min(Oz, 128), *tx = std::min(Ox, 128 / *tz), *ty = std::min(Oy, 128 / (*tz * *tx));
+    return true;
+  }
+  return best_tiles > 0;
 }
 
 }  // namespace

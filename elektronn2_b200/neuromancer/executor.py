@@ -865,19 +865,56 @@ class Plan(object):
             if dp is not None:
                 dp.on_gradients_ready(S)           # every bucket below S is launched by now
                 dp.wait_launched()                 # this stream waits for those collectives
-            opt.dev_step(store, 0, S, 1)
-            for op in packs_early:
-                op.pack(True)
+            self._update_and_pack(opt, store, 0, S, packs_early)
 
         self._launch_bwd(hook, (j, early_update) if j is not None and S > 0 else None)
         if dp is not None:
             dp.finish_step(store)
-        opt.dev_step(store, S, store.n_reg - S, 1)
         for off, cnt, m in store.regions:
             if off >= store.n_reg:
                 opt.dev_step(store, off, cnt, m)
-        for op in (packs_late if j is not None and S > 0 else self.pack_ops):
-            op.pack(True)
+        self._update_and_pack(opt, store, S, store.n_reg, packs_late if j is not None and S > 0 else self.pack_ops)
+
+    def _can_fuse_pack(self, opt, store, lo, hi, pack_ops):
+        """Is every parameter in [lo, hi) of the flat buffer the weight of one of ``pack_ops`` (and the optimiser one
+        whose hyper-parameters live on the device)?  Then each layer's update + re-pack is one launch."""
+        if os.environ.get('E2_FUSE_PACK', '0') != '1' or not getattr(opt, 'fusable', False):
+            return False
+        mine = {op.w.data_ptr(): op for op in pack_ops if getattr(op, 'w', None) is not None}
+        need = [p for _, p, off, _ in store.entries if lo <= off < hi]
+        return (len(need) == len(mine) == len(pack_ops) and all(p._dev.data_ptr() in mine for p in need)
+                and all(op.adam_pack_ok() for op in pack_ops))
+
+    def _update_and_pack(self, opt, store, lo, hi, pack_ops):
+        """Adam update of the parameters [lo, hi) of the flat buffer (weights, weight-decay multiplier 1) and the
+        re-pack of the layers ``pack_ops`` whose weights they are: one launch per layer that updates and re-packs
+        (e2_*_adam_pack_dev: the weights cross HBM once) when the range is exactly those layers' weights, else the flat
+        update followed by the separate pack kernels."""
+        if not self._can_fuse_pack(opt, store, lo, hi, pack_ops):
+            opt.dev_step(store, lo, hi - lo, 1)
+            for op in pack_ops:
+                op.pack(True)
+            return
+        for op in pack_ops:
+            op.adam_pack(opt, store, 1.0)
+
+    def update_launches(self, opt):
+        """Kernel launches of the optimiser + re-pack part of a fused training step (``_train_body_fwd/_bwd``)."""
+        store = self.store
+        S, j, packs_early, packs_late = self._opt_split()
+        parts = [(0, S, packs_early), (S, store.n_reg, packs_late)] if (j is not None and S > 0) else \
+            [(0, store.n_reg, self.pack_ops)]
+        n = 1 + len([1 for off, cnt, m in store.regions if off >= store.n_reg and cnt])     # adam_prepare + other regions
+        for lo, hi, ops_ in parts:
+            if self._can_fuse_pack(opt, store, lo, hi, ops_):
+                n += len(ops_)
+            else:
+                before = self.h.launches
+                for op in ops_:
+                    op.pack(True)
+                torch.cuda.synchronize(self.device)
+                n += (self.h.launches - before) + (1 if hi > lo else 0)
+        return n
 
     def train_step(self, opt, loss_async=False):
         """Forward + backward + optimiser update + weight re-pack as two CUDA graphs -- [forward, loss] and
@@ -1105,17 +1142,22 @@ class Plan(object):
             self._inputs_free = torch.cuda.Event()
         self._inputs_free.record()
 
-    def launches_per_step(self):
-        """Kernel launches of one step (counted by the library, eager pass)."""
+    def launches_per_step(self, with_pack=True):
+        """Kernel launches of one step (counted by the library, eager pass); ``with_pack``: including the separate
+        weight re-pack (inference plans after a parameter change; training steps count ``update_launches`` instead)."""
+        if with_pack:
+            self.pack()
         before = self.h.launches
-        self.pack()
+        if with_pack:
+            self.pack()
         self._launch_all()
         torch.cuda.synchronize(self.device)
         return self.h.launches - before
 
-    def profile(self, repeats=3):
+    def profile(self, repeats=3, opt=None):
         """Per-launch device times (ms, CUDA events on the launching stream), eager
-        passes after one warm-up; returns [(label, kind, flops, bytes, ms)]."""
+        passes after one warm-up; returns [(label, kind, flops, bytes, ms)].  With ``opt`` (training plans) the last
+        entry is the optimiser update + weight re-pack as the fused step runs it (it really updates the parameters)."""
         self.pack()
         self._launch_all()
         torch.cuda.synchronize(self.device)
@@ -1133,7 +1175,22 @@ class Plan(object):
             for i, (a, b) in enumerate(evs):
                 acc[i] += a.elapsed_time(b)
         out = [(f.label, f.kind, f.flops, f.bytes, acc[i] / repeats) for i, f in enumerate(all_ops)]
-        if self.train:
+        if self.train and opt is not None and getattr(opt, 'fusable', False):
+            store = self.store
+            opt.dev_sync(store)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(repeats):
+                opt.dev_prepare()
+                for off, cnt, m in store.regions:
+                    if off >= store.n_reg:
+                        opt.dev_step(store, off, cnt, m)
+                self._update_and_pack(opt, store, 0, store.n_reg, self.pack_ops)
+            b.record()
+            torch.cuda.synchronize(self.device)
+            # p, g, m, s read + p, m, s and the two packed images written
+            out.append(('adam_update_pack', 'hbm', 0.0, 36.0 * store.n_reg, a.elapsed_time(b) / repeats))
+        elif self.train:
             # the per-step weight re-pack (read the fp32 master once, write the fwd and dgrad layouts)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()

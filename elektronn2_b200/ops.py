@@ -60,6 +60,18 @@ class ConvOp(object):
         self.h.call('e2_conv3d_fwd', C.byref(d), self.x.ptr(), _lib.ptr(self.wf),
                     _lib.ptr(self.b) if d.has_bias else None, yy.ptr(), ws, ws_bytes, self.h.stream())
 
+    def adam_pack(self, opt, store, wd_mult=1.0):
+        """Adam update of this layer's weights (a view into ``store.P``) and the re-pack of the updated weights in one
+        launch (e2_conv3d_adam_pack_dev); ``opt`` holds the moments and the device-resident hyper-parameters."""
+        off = (self.w.data_ptr() - store.P.data_ptr()) // 4
+        sl = lambda t: C.c_void_p(t.data_ptr() + 4 * off)      # noqa: E731
+        self.h.call('e2_conv3d_adam_pack_dev', C.byref(self.d), sl(store.P), sl(store.G), sl(opt._state[0]),
+                    sl(opt._state[1]), _lib.ptr(opt._hyper_dev), C.c_float(wd_mult), _lib.ptr(self.wf), _lib.ptr(self.wd),
+                    self.h.stream())
+
+    def adam_pack_ok(self):
+        return self.k[0] * self.k[1] * self.k[2] <= 125
+
     def pool_fusable(self, pop):
         """Does libe2b200 run this conv and the max-pool ``pop`` (a PoolOp whose input is this conv's output) as one
         launch (e2_conv3d_fwd_pool_supported)?"""
@@ -121,6 +133,17 @@ class UpConvOp(object):
     def pack(self, need_dgrad=True):
         self.h.call('e2_upconv3d_pack_weights', C.byref(self.d), _lib.ptr(self.w), _lib.ptr(self.wf),
                     _lib.ptr(self.wd) if need_dgrad else None, self.h.stream())
+
+    def adam_pack(self, opt, store, wd_mult=1.0):
+        """See ConvOp.adam_pack (e2_upconv3d_adam_pack_dev)."""
+        off = (self.w.data_ptr() - store.P.data_ptr()) // 4
+        sl = lambda t: C.c_void_p(t.data_ptr() + 4 * off)      # noqa: E731
+        self.h.call('e2_upconv3d_adam_pack_dev', C.byref(self.d), sl(store.P), sl(store.G), sl(opt._state[0]),
+                    sl(opt._state[1]), _lib.ptr(opt._hyper_dev), C.c_float(wd_mult), _lib.ptr(self.wf), _lib.ptr(self.wd),
+                    self.h.stream())
+
+    def adam_pack_ok(self):
+        return self.pool[0] * self.pool[1] * self.pool[2] <= 125
 
     def fwd(self):
         ws, ws_bytes = self.h.workspace()

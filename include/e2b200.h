@@ -313,6 +313,15 @@ int e2_adam_step(e2_handle* h, float* p, const float* g, float* m, float* s, int
 int e2_adam_prepare(e2_handle* h, float* hyper, int32_t* t_dev, void* stream);
 int e2_adam_step_dev(e2_handle* h, float* p, const float* g, float* m, float* s, int64_t count, const float* hyper,
                      float wd_mult, void* stream);
+/* e2_adam_step_dev for the weights of ONE Conv / UpConv layer that also writes the packed forward / dgrad images of the
+ * updated weights (what e2_conv3d_pack_weights / e2_upconv3d_pack_weights would produce from them, bit for bit) in the
+ * same pass: the weights cross HBM once per step instead of three times.  w, g, m, s: the layer's (f_out,f_in,k..)
+ * slices of the parameter / gradient / moment buffers.  wf / wd must have been packed once before (pad lanes are not
+ * rewritten); either may be NULL.  E2_ERR_UNSUPPORTED for filters with more than ~150 taps (use the two calls). */
+int e2_conv3d_adam_pack_dev(e2_handle* h, const e2_conv_desc* d, float* w, const float* g, float* m, float* s,
+                            const float* hyper, float wd_mult, float* wf, float* wd, void* stream);
+int e2_upconv3d_adam_pack_dev(e2_handle* h, const e2_upconv_desc* d, float* w, const float* g, float* m, float* s,
+                              const float* hyper, float wd_mult, float* wf, float* wd, void* stream);
 /* SGD with momentum, optimiser.py:146-160 */
 int e2_sgd_step(e2_handle* h, float* p, const float* g, float* last_dir, int64_t count, float lr, float mom, float wd,
                 float wd_mult, void* stream);

@@ -510,6 +510,59 @@ def test_adam_and_sgd_match_reference_formulas(h):
     assert rel(p.cpu().numpy(), ref[0]) <= 1e-6
 
 
+ADAM_PACK_CASES = [
+    # (kind, f_out, f_in, filter / pool)
+    ('conv', 64, 32, (3, 3, 3)), ('conv', 30, 20, (1, 5, 5)), ('conv', 20, 1, (1, 6, 6)), ('conv', 2, 200, (1, 1, 1)),
+    ('conv', 150, 40, (2, 4, 4)), ('conv', 35, 42, (3, 3, 3)), ('conv', 80, 40, (4, 4, 4)),
+    ('upconv', 24, 32, (2, 2, 2)), ('upconv', 45, 35, (1, 2, 2)), ('upconv', 256, 512, (2, 2, 2)),
+]
+
+
+@pytest.mark.parametrize('case', ADAM_PACK_CASES)
+def test_adam_pack_fused_equals_update_then_pack(h, case):
+    """e2_*_adam_pack_dev (one launch per layer: Adam update + both packed images) against the two steps it replaces,
+    e2_adam_step_dev over the layer's slice and e2_*_pack_weights: parameters, both moments and both packed images
+    must be the same bits (pad lanes included: they keep the zeros of the first pack)."""
+    from elektronn2_b200 import _lib
+    from elektronn2_b200.ops import ConvOp, UpConvOp
+    kind, co, ci, k = case
+    r = np.random.RandomState(abs(hash(case)) % 2**31)
+    n = co * ci * int(np.prod(k))
+    w0 = (r.randn(n) * 0.1).astype(np.float32)
+    g0 = (r.randn(n) * 0.01).astype(np.float32)
+    m0 = (r.randn(n) * 0.01).astype(np.float32)
+    s0 = (r.rand(n) * 1e-4).astype(np.float32)
+    hyper = torch.tensor([5e-4, 0.9, 0.999, 0.5e-4, 0.0, 0, 0, 0], dtype=torch.float32, device='cuda')
+    tdev = torch.tensor([6], dtype=torch.int32, device='cuda')
+    h.call('e2_adam_prepare', _lib.ptr(hyper), _lib.ptr(tdev), h.stream())       # factor(t = 7)
+
+    def make(w):
+        if kind == 'conv':
+            sp = [f + 1 for f in k]
+            return ConvOp(h, empty(1, ci, sp), empty(1, co, (2, 2, 2)), w.view(co, ci, *k), None, k, 'relu', 'tf32')
+        return UpConvOp(h, empty(1, ci, (2, 2, 2)), empty(1, co, [2 * q for q in k]), w.view(co, ci, *k), None, k, 'relu',
+                        'tf32')
+
+    fn = 'e2_conv3d_adam_pack_dev' if kind == 'conv' else 'e2_upconv3d_adam_pack_dev'
+    res = []
+    for fused in (False, True):
+        w, g, m, s = t(w0), t(g0), t(m0), t(s0)
+        op = make(w)
+        op.pack()                                  # first pack: zeroes the pad lanes
+        if fused:
+            h.call(fn, _lib.C.byref(op.d), _lib.ptr(w), _lib.ptr(g), _lib.ptr(m), _lib.ptr(s), _lib.ptr(hyper),
+                   _lib.C.c_float(1.0), _lib.ptr(op.wf), _lib.ptr(op.wd), h.stream())
+        else:
+            h.call('e2_adam_step_dev', _lib.ptr(w), _lib.ptr(g), _lib.ptr(m), _lib.ptr(s), n, _lib.ptr(hyper),
+                   _lib.C.c_float(1.0), h.stream())
+            op.pack()
+        torch.cuda.synchronize()
+        res.append([a.cpu().numpy() for a in (w, m, s, op.wf, op.wd)])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(res[0][0], w0)       # the update happened
+
+
 # -------------------------------------------- size-independent properties at full size
 def test_full_size_properties_unet3d_conv1(h):
     """unet3d conv1 (1,32,114,130,130) -> (1,64,112,128,128), the largest layer of the
