@@ -144,7 +144,9 @@ __device__ __forceinline__ void zs_issue_stage(uint64_t a_desc0, uint32_t pstrid
   }
 }
 
-template <int TZ_, int KZ_>
+// POOL_: the fused max-pool epilogue is a separate instantiation -- with it compiled into every kernel the epilogue of
+// the plain convolutions doubled in size and the small, epilogue-bound layers (unet3d_litelite, neuro3d_lite) lost 4-9 %
+template <int TZ_, int KZ_, int POOL_>
 __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmC,
@@ -358,7 +360,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
       tr_full += e1 - e0;
       tc::tc_fence_after();
       int ci = 0;
-      const int PZ = p.pool ? p.ppz : 1;                  // planes per unit of epilogue work (the pool window's z extent)
+      constexpr bool POOL = POOL_ != 0;
+      const int PZ = POOL ? p.ppz : 1;                    // planes per unit of epilogue work (the pool window's z extent)
       for (int zp = 0; zp < p.TZ; zp += PZ) {
         if (z0 + zp >= p.Oz) break;                       // uniform: whole plane (pair) outside the tensor
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -446,8 +449,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                 for (int j = 0; j < 32; ++j) v[j] = e2_round_tf32(v[j]);
               }
               // fused pool: the caller may need only a window of the unpooled tensor (the skip connection's crop)
-              const bool keep = p.store_full && (!p.pool || (z0 + zl >= p.kz0 && z0 + zl < p.kz1 && x0 + 4 * q + 4 > p.kx0 &&
-                                                             x0 + 4 * q < p.kx1 && y0 + TY > p.ky0 && y0 < p.ky1));
+              const bool keep = !POOL || (p.store_full && z0 + zl >= p.kz0 && z0 + zl < p.kz1 && x0 + 4 * q + 4 > p.kx0 &&
+                                                             x0 + 4 * q < p.kx1 && y0 + TY > p.ky0 && y0 < p.ky1);
               if (keep) {
                 // each lane reads and writes only its own 128-byte row of the buffer: no cross-lane hazard
 #pragma unroll
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
                   tc::bulk_commit();
                 }
               }
-              if (p.pool) {
+              if (POOL) {
                 if (dz == 0) {
 #pragma unroll
                   for (int j = 0; j < 32; ++j) pv[j] = v[j];
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
               }
             }
           }
-          if (p.pool) {
+          if (POOL) {
             // ------------------------------------------------------------ fused max-pool of this unit
             // lane = x-line (lane >> 3) x y (lane & 7) of the 4 x 8 position patch; window partners are lane ^ 1
             // (y) and lane ^ 8 (x).  After the merges the lane at a window's origin holds (max, first argmax).
@@ -926,13 +929,14 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
   const size_t smem = 1024 + (size_t)p.epi_off + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 4 + EPI_WARPS) * 8 + 16;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const ZsParams);
-#define ZS_ROW(KZ)                                                                                               \
-  {k_conv_zstack_tc<1, KZ>, k_conv_zstack_tc<2, KZ>, k_conv_zstack_tc<3, KZ>, k_conv_zstack_tc<4, KZ>,             \
-   k_conv_zstack_tc<5, KZ>, k_conv_zstack_tc<6, KZ>, k_conv_zstack_tc<7, KZ>, k_conv_zstack_tc<8, KZ>}
-  static const KernelFn table[4][8] = {ZS_ROW(1), ZS_ROW(2), ZS_ROW(3), ZS_ROW(4)};
+#define ZS_ROW(KZ, P)                                                                                            \
+  {k_conv_zstack_tc<1, KZ, P>, k_conv_zstack_tc<2, KZ, P>, k_conv_zstack_tc<3, KZ, P>, k_conv_zstack_tc<4, KZ, P>,     \
+   k_conv_zstack_tc<5, KZ, P>, k_conv_zstack_tc<6, KZ, P>, k_conv_zstack_tc<7, KZ, P>, k_conv_zstack_tc<8, KZ, P>}
+  static const KernelFn table[2][4][8] = {{ZS_ROW(1, 0), ZS_ROW(2, 0), ZS_ROW(3, 0), ZS_ROW(4, 0)},
+                                          {ZS_ROW(1, 1), ZS_ROW(2, 1), ZS_ROW(3, 1), ZS_ROW(4, 1)}};
 #undef ZS_ROW
   if (p.kz < 1 || p.kz > 4 || p.TZ < 1 || p.TZ > 8) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: no kernel for TZ %d kz %d", p.TZ, p.kz);
-  KernelFn fn = table[p.kz - 1][p.TZ - 1];
+  KernelFn fn = table[p.pool ? 1 : 0][p.kz - 1][p.TZ - 1];
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
     return e2_fail(h, E2_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed");
   if (smem > 227 * 1024) return e2_fail(h, E2_ERR_UNSUPPORTED, "conv_zstack_tc: shared memory plan exceeds 227 KB");

@@ -380,7 +380,7 @@ class Plan(object):
         unfused = self._unfused(n)
         if not pooled and not unfused:
             op = ops.ConvOp(h, x, y, w, b, k3, n.activation_func, self.compute)
-            pn = self._pool_consumer(n)
+            pn = self._pool_consumer(n) if self._pool_fusion_pays(x, k3) else None
             pop = None
             if pn is not None:
                 # Conv -> Pool (examples/unet3d.py:63-74): the window maximum is taken in the conv kernel's epilogue,
@@ -415,7 +415,8 @@ class Plan(object):
             elif pooled:
                 pop = ops.PoolOp(h, lin, v, p3, bias=pb, act=pact, keep_argmax=self.train,
                                  tie_mode=config.pool_tie_mode, round_tf32=rnd)
-                if (not unfused and (not self.train or config.pool_tie_mode == 'first') and op.pool_fusable(pop)):
+                if (not unfused and (not self.train or config.pool_tie_mode == 'first') and self._pool_fusion_pays(x, k3)
+                        and op.pool_fusable(pop)):
                     # conv -> pool -> +bias -> act in ONE launch; the raw conv output is never written (the backward
                     # pass routes through the argmax)
                     self.fwd_ops.pop()
@@ -429,6 +430,15 @@ class Plan(object):
                 self.aux[n] = (lin, pop)
         self.conv_ops[n] = op
         self.pack_ops.append(op)
+
+    # reduction length (input channels x filter taps) from which the conv kernel's main loop is long enough to hide the
+    # extra epilogue work of a fused max-pool.  Measured: the three Conv -> Pool pairs of unet3d (864 / 1728 / 3456) gain
+    # 65 + 20 + 10 us per step; unet3d_litelite (180 ... 315) and the 20 -> 40 layer of neuro3d_lite (540) are epilogue
+    # bound already and LOSE 2 % of their step with the pool fused
+    POOL_FUSE_MIN_K = int(os.environ.get('E2_POOL_FUSE_MIN_K', '800'))
+
+    def _pool_fusion_pays(self, x, k3):
+        return x.desc.c * int(np.prod(k3)) >= self.POOL_FUSE_MIN_K
 
     def _pool_consumer(self, n):
         """The one max-Pool node (windows of 1 or 2 per axis) among the consumers of Conv ``n``, or None."""

@@ -187,7 +187,9 @@ int e2_maxpool3d_fwd(e2_handle* h, const e2_pool_desc* d, const float* x, const 
  * (nullable = everything) names the window of y the caller will read -- the skip connection's Crop, neural.py:1152-1168
  * -- and only that part of y is guaranteed to be written (the fused kernel stores the tiles that intersect it).
  * e2_conv3d_fwd_pool_supported: 1 if the pair is fused (TF32 mode, windows of 1 or 2 per axis, a layer the z-stack
- * kernel runs without a K split), 0 if e2_conv3d_fwd_pool would issue the two launches instead, < 0 on a bad descriptor. */
+ * kernel runs without a K split), 0 if e2_conv3d_fwd_pool would issue the two launches instead, < 0 on a bad descriptor.
+ * Whether fusing PAYS is the caller's policy: layers with a short reduction (c_in * taps below ~800) are bound by their
+ * epilogue already and ran 2 % slower per step with the pool inside it (elektronn2_b200/neuromancer/executor.py). */
 int e2_conv3d_fwd_pool_supported(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p);
 typedef struct { int32_t z0, z1, x0, x1, y0, y1; } e2_window; /* half-open ranges of positions */
 int e2_conv3d_fwd_pool(e2_handle* h, const e2_conv_desc* d, const e2_pool_desc* p, const float* x, const float* wf,

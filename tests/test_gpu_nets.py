@@ -212,6 +212,63 @@ def test_cuda_graph_replay_equals_eager():
         assert rel(b, a) <= 1e-5 and rel(c, a) <= 1e-5   # atomics reorder fp32 sums in wgrad
 
 
+def test_fused_pool_plan_equals_unfused_plan():
+    """A Conv -> Pool pair with a skip connection (the U-Net pattern): the executor runs conv + pool as one launch and
+    stores only the window of the unpooled tensor that the skip connection's Crop reads (executor._keep_window).
+    Everything downstream -- probabilities, loss, every parameter gradient (pool backward gated by the pooled values,
+    crop backward reading the gate inside its window) and the parameters after two Adam steps -- must equal the plan
+    that runs the two launches and stores the whole tensor (bit for bit where no fp32 atomics are involved)."""
+    _cuda()
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200.config import config
+    from elektronn2_b200.neuromancer import executor
+    assert config.compute == 'tf32'
+
+    def run(min_k):
+        old = executor.Plan.POOL_FUSE_MIN_K
+        executor.Plan.POOL_FUSE_MIN_K = min_k
+        try:
+            nm.model_manager.reset()
+            np.random.seed(3)
+            with contextlib.redirect_stdout(io.StringIO()):
+                inp = nm.Input((None, 1, 12, 46, 46), 'b,f,z,x,y', name='raw')
+                c0 = nm.Conv(inp, 32, (1, 3, 3))
+                c1 = nm.Conv(c0, 32, (3, 3, 3))
+                d0 = nm.Pool(c1, (2, 2, 2))
+                c2 = nm.Conv(d0, 48, (3, 3, 3))
+                mrg = nm.UpConvMerge(c1, c2, 24)
+                c3 = nm.Conv(mrg, 16, (1, 3, 3))
+                out = nm.Conv(c3, 2, (1, 1, 1), activation_func='lin')
+                probs = nm.Softmax(out)
+                target = nm.Input_like(out, override_f=1, name='target')
+                loss = nm.AggregateLoss(nm.MultinoulliNLL(probs, target, target_is_sparse=True), name='loss')
+                errors = nm.Errors(probs, target, target_is_sparse=True)
+                m = nm.model_manager.getmodel()
+                m.designate_nodes(input_node=inp, target_node=target, loss_node=loss, prediction_node=probs,
+                                  prediction_ext=[loss, errors, probs])
+            x, t = data_for(m)
+            l, e, p = m.predict_ext(x, t)
+            g = m.gradients(x, t)
+            labels = [f.label for f in m._train_plan(1).fwd_ops]
+            nm.optimiser.Optimiser.setlr(1e-3)
+            m.trainingstep(x, t, optimiser='Adam')
+            m.trainingstep(x, t, optimiser='Adam')
+            nm.optimiser.Optimiser.setlr(1)
+            return l, p, g, [q.get_value() for q in m.trainable_params], labels
+        finally:
+            executor.Plan.POOL_FUSE_MIN_K = old
+
+    l0, p0, g0, w0, lab0 = run(1 << 30)
+    l1, p1, g1, w1, lab1 = run(800)
+    assert any(s.startswith('pool_fwd') for s in lab0) and not any(s.startswith('pool_fwd') for s in lab1)
+    assert np.array_equal(p0, p1)                       # the forward pass has no atomics: the same bits
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)               # loss scalars, bias / first-layer / 1x1x1 weight gradients are summed
+    for a, b in zip(g0, g1):                            # with fp32 atomics: equal up to summation order
+        assert rel(a, b) <= 1e-5
+    for a, b in zip(w0, w1):
+        assert rel(a, b) <= 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------------
 # TF32 mode against an oracle that applies the SAME operand roundings (oracle/nets.py ``Net.tf32``): pins the
 # claim of DESIGN.md "TF32 end-to-end sensitivity" -- what exceeds 1e-3 against the unrounded oracle is the
