@@ -21,7 +21,8 @@ FAMILY = [
     ('k_c1_fwd', 'conv_fwd+dgrad'), ('k_gather_gemm_tc', 'conv/upconv tap kernel'), ('k_gather_gemm_reduce', 'conv/upconv tap kernel'),
     ('k_gather_gemm', 'conv_fwd+dgrad'),
     ('k_maxpool_fwd', 'pool_fwd'), ('k_maxpool_bwd', 'pool_bwd'), ('k_crop_fwd', 'crop_concat_fwd'), ('k_crop_bwd', 'crop_concat_bwd'),
-    ('k_softmax_nll', 'loss'), ('k_adam', 'adam'), ('k_pack', 'pack'), ('k_repack', 'pack'),
+    ('k_mfp_fwd', 'mfp_fwd'), ('k_mfp_bwd', 'mfp_bwd'),
+    ('k_softmax_nll', 'loss'), ('k_adam_pack', 'adam+pack'), ('k_adam', 'adam'), ('k_pack', 'pack'), ('k_repack', 'pack'),
 ]
 
 
