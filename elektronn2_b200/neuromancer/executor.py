@@ -457,6 +457,8 @@ class Plan(object):
         and a ReLU layer whose gradient contributions are all gated needs no activation backward of its own."""
         if os.environ.get('E2_KEEP_FULL') or n in self.outputs or n.activation_func not in ('relu', 'lin', 'linear'):
             return None
+        if self.train and config.pool_tie_mode != 'first':
+            return None      # the Theano-CPU tie rule recomputes the window maximum from the unpooled tensor in the backward pass
         sp = _sp3(n.shape.spatial_shape)
         lo, hi = list(sp), [0, 0, 0]
         for c in self._consumers(n):
