@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from .devtensor import DevTensor
-from .ops import ConvOp, UpConvOp, PoolOp, MfpOp, Frag2DenseOp
+from .ops import ConvOp, UpConvOp, PoolOp, MfpOp, Frag2DenseOp, LossOp
 
 
 def _t(a):
@@ -229,3 +229,14 @@ def fragments2dense(fragments, offsets, strides):
     dd = DevTensor(1, f.shape[2] * st[0], f.shape[3] * st[1], f.shape[4] * st[2], f.shape[1])
     Frag2DenseOp(h, fd, dd, offsets, st).fwd()
     return dd.numpy(h)
+
+
+def softmax(x):
+    """computations.softmax over the feature axis of a (b, f, z, x, y) array (computations.py:137-177): the Softmax
+    node alone, i.e. the fused loss head called without a target (include/e2b200.h, e2_softmax_nll_fwd)."""
+    x = _f32(x)
+    h = _lib.get_handle()
+    xd = DevTensor.from_numpy(x, h)
+    pd = xd.like()
+    LossOp(h, xd, None, pd).fwd()
+    return pd.numpy(h)

@@ -118,6 +118,22 @@ def apply_activation(x, activation_func, b1=None):
     return F.affine_act(x, activation_func, alpha=np.asarray(b1, np.float32).reshape(-1) if b1 is not None else None)
 
 
+def softmax(x, axis=1, force_builtin=False):
+    """computations.softmax (computations.py:137-177) over the feature axis of a ``(b, f[, z], x[, y])`` array:
+    ``exp(x - max) / sum`` (:174-176; the cuDNN 'accurate' mode the reference uses on ``axis == 1`` is the same
+    max-subtracted form)."""
+    x = np.asarray(x)
+    if x.ndim == 2 and axis == 1:
+        x5 = x.T.reshape((1, x.shape[1], 1, 1, x.shape[0]))                      # T.nnet.softmax on rows (:170-171)
+        return F.softmax(x5).reshape(x.shape[1], x.shape[0]).T
+    if force_builtin:
+        raise NotImplementedError()                                               # :172-173
+    if axis != 1 or x.ndim not in (3, 4, 5):
+        raise NotImplementedError("b200 backend: softmax over the feature axis (1) of a b,f[,z],x[,y] array")
+    lead = (1,) * (5 - x.ndim)
+    return F.softmax(x.reshape(x.shape[:2] + lead + x.shape[2:])).reshape(x.shape)
+
+
 def fragmentpool(conv_out, pool, offsets, strides, spatial_axes, mode='max'):
     """computations.fragmentpool (computations.py:652-678) -> (fragments, offsets_new, strides_new)."""
     if np.all(np.equal(pool, 1)):                                                 # :653-654

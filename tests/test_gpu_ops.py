@@ -866,3 +866,52 @@ def test_computations_seam_values(h):
         assert np.array_equal(cp.fragments2dense(fr, off, st, [2, 3, 4]), oo.fragments2dense(ref, roff, rst))
     finally:
         config.compute = old
+
+
+def test_reference_test_conv_at_its_own_size(h):
+    """The reference's only enabled hot-path test (tests/test_conv.py:106-163), at its own size and with its own
+    tolerances: conv of x (1,5,100,300,200) with W (7,5,3,3,3), uniform[0,1) float32; then conv + (2,2,2) max-pool;
+    then + softmax over the features (atol 1e-5).  The reference compares its cuDNN path with its conv3d2d path; here the
+    B200 path (through the computations.py seam) stands where cuDNN stood and the oracle's restatement of the conv3d2d /
+    pool_2d path stands on the other side.  F32 mode carries the reference's np.allclose defaults; TF32 mode the
+    north star's 1e-3."""
+    from elektronn2_b200.neuromancer import computations as cp
+    from elektronn2_b200.config import config
+    r = np.random.RandomState(1234)
+    x_val = r.rand(1, 5, 100, 300, 200).astype(np.float32)
+    W_val = r.rand(7, 5, 3, 3, 3).astype(np.float32)                             # (nof, ch, zf, xf, yf)
+    r4 = oo.conv3d(x_val, W_val)
+    r4p = oo.pooling(r4, (2, 2, 2))
+    r4s = ol.softmax(r4p, 1)
+    old = config.compute
+    try:
+        config.compute = 'f32'
+        r3 = cp.conv(x_val, W_val, axis_order='dnn', conv_dim=3)
+        assert r3.shape == (1, 7, 98, 298, 198)
+        assert np.allclose(r3, r4)                                               # test_conv.py:127-128
+        r3p = cp.pooling(r3, (2, 2, 2), [2, 3, 4])
+        assert np.allclose(r3p, r4p)                                             # :141-142
+        assert np.array_equal(r3p, oo.pooling(r3, (2, 2, 2)))                    # the pool itself: bit-exact
+        r3s = cp.softmax(r3p, axis=1)
+        assert np.allclose(r3s, r4s, atol=1e-5)                                  # :161-162
+        assert np.allclose(r3s.sum(1), 1.0, atol=1e-6)
+        config.compute = 'tf32'
+        r5 = cp.conv(x_val, W_val, axis_order='dnn', conv_dim=3)
+        assert rel(r5, r4) <= TOL['tf32']
+    finally:
+        config.compute = old
+
+
+def test_reference_demo_pooling_3d_shapes(h):
+    """tests/test_pooling.py:31-60 (demo_pooling_3d) only runs pooling and its gradient on (1,4,30,200,200) with pool
+    (2,2,2); here the same call is also checked: values, first-maximum argmax and both gradient tie rules bit-exact."""
+    from elektronn2_b200 import functional as F
+    r = np.random.RandomState(5)
+    x = r.rand(1, 4, 30, 200, 200).astype(np.float32)
+    x[0, :, :4, :6, :6] = 0.5                                                     # windows full of ties
+    y, am = F.maxpool3d(x, (2, 2, 2), return_argmax=True)
+    assert np.array_equal(y, oo.pooling(x, (2, 2, 2)))
+    assert np.array_equal(am, oo.pooling_argmax(x, (2, 2, 2)))
+    dy = r.randn(*y.shape).astype(np.float32)
+    for tie in ('first', 'all'):
+        assert np.array_equal(F.maxpool3d_grad(x, dy, (2, 2, 2), tie), oo.pooling_bwd(dy, x, (2, 2, 2), tie).astype(np.float32))

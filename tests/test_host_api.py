@@ -357,6 +357,10 @@ def test_computations_seam_error_behaviour():
         cp.fragmentpool(x, (2, 2, 2), [[0, 0, 0]], [1, 1, 1], [2, 3, 4])    # (4-2+1) % 2 != 0
     with pytest.raises(ValueError):
         cp.fragments2dense(np.zeros((3, 2, 2, 2, 2), np.float32), [[0, 0, 0]] * 3, (1, 2, 2), [2, 3, 4])
+    with pytest.raises(NotImplementedError):
+        cp.softmax(x, axis=1, force_builtin=True)                # :172-173 (not a 2-d input)
+    with pytest.raises(NotImplementedError):
+        cp.softmax(x, axis=2)
 
 
 def test_modelload_reads_a_file_written_by_the_reference_serialiser():
