@@ -56,6 +56,7 @@ struct ZsParams {
   int act, accumulate, round_tf32;
   uint32_t idesc0, idesc_step;   // idesc for N = nblk*BN is idesc0 + nblk*idesc_step
   int epi_off;                   // byte offset of the epilogue staging area (1024-aligned)
+  int bias_copies;               // EPI_WARPS private copies of the bias tile, or 1 shared copy when every tile has the same n0
   long long* trace;              // E2_ZS_TRACE: per-role cycle counters of CTA 0 (debug)
   int dbg;                       // E2_ZS_DBG bottleneck experiments: 1 no plane TMA, 2 no weight TMA, 4 no MMA, 8 no stores
   // max-pool fused into the epilogue (e2_conv3d_fwd_pool): window (ppz,ppx,ppy) in {1,2}^3 over the values the
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
   uint8_t* smP = smem;                                   // plane slots
   uint8_t* smW = smem + p.nslot * p.plane_stride;        // weight ring
   uint8_t* smE = smem + p.epi_off;                       // epilogue: per warp one 4 KB staging/aux tile, then bias
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + EPI_WARPS * 4096 + p.bias_copies * p.BN * 4);
   uint64_t* pl_full = bars;
   uint64_t* pl_empty = pl_full + MAX_PSLOTS;
   uint64_t* w_full = pl_empty + MAX_PSLOTS;
@@ -341,7 +342,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) k_conv_zstack_tc(const __grid_c
     const int ew = warp - 4;
     const int q = warp & 3, half = ew >> 2;
     uint8_t* stage = smE + ew * 4096;
-    float* bias_w = reinterpret_cast<float*>(smE + EPI_WARPS * 4096) + ew * p.BN;
+    // one N tile (n0 == 0 for every tile): all warps write the same values, so one copy serves them all (frees 7 x BN x 4
+    // bytes -- what the N = 100 layers of neuro3d need to run BN = 112 with two output planes per tile)
+    float* bias_w = reinterpret_cast<float*>(smE + EPI_WARPS * 4096) + (p.bias_copies > 1 ? ew * p.BN : 0);
     uint64_t* abar = &aux_bar[ew];
     uint32_t apar = 0;
     const int r8 = lane & 7;
@@ -695,7 +698,7 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
     if (ntn > 1 && (b % 32)) continue;   // the epilogue stores 32-channel boxes: inner N tiles must be whole boxes
     if (narrow && S * b > 256) continue;
     const int w_bytes = S * b * 128;
-    const int epi_bytes = EPI_WARPS * 4096 + EPI_WARPS * b * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
+    const int epi_bytes = EPI_WARPS * 4096 + (ntn == 1 ? 1 : EPI_WARPS) * b * 4;  // per epilogue warp: one 4 KB staging/aux tile; bias copies
     const int budget = 227 * 1024 - 1024 - 1024 - epi_bytes;   // alignment slack + barriers + epilogue
     static const int force_tz = getenv("E2_ZS_TZ") ? atoi(getenv("E2_ZS_TZ")) : 0;   // experiments only
     for (int tz = 8; tz >= 1; --tz) {
@@ -738,6 +741,7 @@ static bool plan_zstack(const e2_handle* h, const GatherGemm& g, ZsParams* p, bo
   if (best_tz == 0) return false;
   const int bn = best_bn;
   p->BN = bn, p->ntn = best_ntn;
+  p->bias_copies = best_ntn == 1 ? 1 : EPI_WARPS;
   p->wblk_bytes = bn * 128;
   p->w_bytes = S * bn * 128;
   p->TZ = best_tz;
@@ -926,7 +930,7 @@ int e2_launch_conv_zstack_tc(e2_handle* h, const GatherGemm& g, cudaStream_t s) 
       if (r != CUDA_SUCCESS) return e2_fail(h, E2_ERR_CUDA, "cuTensorMapEncodeTiled(pooled) failed: %d", (int)r);
     }
   }
-  const size_t smem = 1024 + (size_t)p.epi_off + EPI_WARPS * 4096 + EPI_WARPS * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 4 + EPI_WARPS) * 8 + 16;
+  const size_t smem = 1024 + (size_t)p.epi_off + EPI_WARPS * 4096 + (size_t)p.bias_copies * p.BN * 4 + (2 * MAX_PSLOTS + 2 * MAX_WSLOTS + 4 + EPI_WARPS) * 8 + 16;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const ZsParams);
 #define ZS_ROW(KZ, P)                                                                                            \
