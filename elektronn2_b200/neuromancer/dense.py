@@ -165,6 +165,8 @@ def predict_dense(node, raw_img, as_uint8=False, pad_raw=False, tile_range=None,
     tile_sh, prob_sh, pred_sh, n_tiles = tile_geometry(node, raw_img.shape[1:])
     if np.any(pred_sh <= 0):
         raise ValueError("raw image %s is smaller than the field of view %s" % (raw_img.shape[1:], node.shape.fov))
+    logger.info("Predicting img %s in %i Blocks: (%i, %i, %i)"
+                % (raw_img.shape, int(np.prod(n_tiles)), n_tiles[0], n_tiles[1], n_tiles[2]))   # node_basic.py:958-959
     n_lab = node.shape['f']
     strides = [int(s) for s in node.shape.strides]
     patch = [int(s) for s in node.input_nodes[0].shape.spatial_shape]
@@ -206,7 +208,8 @@ def predict_dense(node, raw_img, as_uint8=False, pad_raw=False, tile_range=None,
         place(*pending, runner.collect())
     dt = time.time() - t_start
     n_vox = float(np.prod(pred_sh))
-    logger.info("Predicted img %s in %d Blocks %s: %.3f MPix/s" % (raw_img.shape, len(tiles), n_tiles, n_vox / 1e6 / dt))
+    logger.info(" Inference speed: %.3f MB or MPix /s, time %.3f s (%d of %d blocks)"
+                % (n_vox / 1e6 / dt, dt, len(tiles), int(np.prod(n_tiles))))                    # node_basic.py:1003-1007
     if return_stats:
         return predictions, dict(seconds=dt, tiles=len(tiles), n_tiles=n_tiles, h2d_bytes=runner.h2d_bytes,
                                  d2h_bytes=runner.d2h_bytes, launches=runner.h.launches)

@@ -70,7 +70,7 @@ class TaggedShape(object):
     tags = property(lambda self: self._tags)
     strides = property(lambda self: self._strides)
     mfp_offsets = property(lambda self: self._mfp_offsets)
-    fov = property(lambda self: list(self._fov))
+    fov = property(lambda self: [int(v) for v in self._fov])
 
     @property
     def fov_all_centered(self):

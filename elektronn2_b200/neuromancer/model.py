@@ -53,7 +53,7 @@ class Model(object):
         return list(self.nodes.values())[slice]
 
     def __repr__(self):
-        return "\n".join(repr(n) for n in self.nodes.values())
+        return repr(list(self.nodes.keys()))                         # graphmanager.py:211-212
 
     # -- designation (model.py:95-227) ---------------------------------------------
     def designate_nodes(self, input_node='input', target_node=None, loss_node=None, prediction_node=None,
@@ -86,10 +86,26 @@ class Model(object):
                     self.target_node.shape._fov = diff
             elif not psh.fov_all_centered:
                 logger.warning("Not all field of views are centered (odd) this might cause problems for many setups")
+            self._say("Prediction properties:\n%s" % (self.prediction_node.shape.ext_repr,))       # model.py:157-158
         if self.loss_node is not None:
             self.trainable_params = list(self.loss_node.all_trainable_params.values())
             self.nontrainable_params = self.loss_node.all_nontrainable_params
             self.optimisers = dict(SGD=optimiser.SGD(self), Adam=optimiser.Adam(self))
+        # aggregated model stats (model.py:160-169, 200-211)
+        top = self.loss_node if self.loss_node is not None else self.prediction_node
+        if top is not None:
+            from .node_basic import pretty_string_ops
+            n_comp = top.all_computational_cost
+            ref = self.prediction_node if self.prediction_node is not None else top
+            per_pixel = float(n_comp) / max(1, ref.shape.spatial_size)
+            self._say("\nTotal Computational Cost of Model: {0:s}\nTotal number of trainable parameters: {1:,d}.\n"
+                      "Computational Cost per pixel: {2:s}\n".format(pretty_string_ops(n_comp), top.all_params_count,
+                                                                     pretty_string_ops(per_pixel)))
+
+    @staticmethod
+    def _say(text):
+        logger.info(text)
+        print(text)
 
     # -- parameters ------------------------------------------------------------------
     def _all_named_params(self):

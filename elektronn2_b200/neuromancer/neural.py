@@ -222,6 +222,9 @@ class FragmentsToDense(Node):
         n = len(sh.spatial_axes)
         self.shape = TaggedShape(sh.shape, sh.tags, np.ones(n, np.int64), np.zeros((1, n), np.int64), sh.fov)
 
+    def _calc_comp_cost(self):
+        self.computational_cost = 0                                  # neural.py:895-901
+
 
 class UpConv(Conv):
     """Transposed convolution with kernel == pool == stride (neural.py:907-1129)."""
@@ -280,6 +283,9 @@ class Crop(Node):
                 raise ValueError("Crop %s leaves nothing of axis %s" % (self.crop, sh.tags[i]))
             sh = sh.updateshape(i, s)
         self.shape = sh
+
+    def _calc_comp_cost(self):
+        self.computational_cost = 0                                  # neural.py:1184-1190
 
 
 def AutoMerge(parent1, parent2, upconv_n_f=None, merge_mode='concat', disable_upconv=False, upconv_kwargs=None,

@@ -80,6 +80,14 @@ class ModelContainer(object):
 model_manager = ModelContainer()
 
 
+def pretty_string_ops(n):
+    """Humanised op count, '25.2 Giga Ops' (utils_basic.py:740-751)."""
+    for factor, suffix in [(1000000000000, 'Tera Ops'), (1000000000, 'Giga Ops'), (1000000, 'Mega Ops'), (1000, 'kilo Ops')]:
+        if n >= factor:
+            break
+    return "%.1f %s" % (float(n) / factor, suffix)
+
+
 def choose_name(proposal, names):
     """Unique node name: 'conv', 'conv1', 'conv2', ... (node_basic.py:158-195)."""
     if proposal in names:
@@ -167,7 +175,9 @@ class Node(object, metaclass=_MetaNode):
         self.shape = self.parents[0].shape.copy()
 
     def _calc_comp_cost(self):
-        self.computational_cost = 0
+        """Default: one op per element of the (first) parent's output (node_basic.py:566-573)."""
+        ps = self.parents
+        self.computational_cost = int(ps[0].shape.stripnone_prod) if ps and ps[0].shape is not None else 0
 
     @property
     def input_nodes(self):
@@ -241,8 +251,10 @@ class Node(object, metaclass=_MetaNode):
         if self.param_count > 0:
             s += "#Params={0:,d} ".format(self.param_count)
         if self.computational_cost > 0:
-            s += "Comp.Cost=%.4g Ops, " % (float(self.computational_cost),)
+            s += "Comp.Cost=%s, " % (pretty_string_ops(self.computational_cost),)
         s += "Out:%s" % (str(self.shape),)
+        if len(self.input_nodes) > 1:                               # node_basic.py:458-460
+            s += "\n  Order of sources=%s, " % (str([n.name for n in self.input_nodes]),)
         return s
 
     # -- execution ---------------------------------------------------------------

@@ -435,3 +435,59 @@ def test_f4_nodes_parameters_and_shapes():
     assert o.shape.shape == [None, 64, 3, 3] and o.conv_dim == 2 and o.w_sh == [64, 36, 3, 3]
     with pytest.raises(ValueError):
         nm.Conv(inp2, 4, (3, 3, 3))
+
+
+def test_docs_walkthrough_prints_what_the_reference_prints(capsys):
+    """docs/examples.rst:55-218, the reference's own model walkthrough, replayed through the product's host API: the node
+    printouts (#Params / Comp.Cost / Out), the prediction properties, the model totals, the dict interface, the MFP
+    rebuild's patch snapping (23,183,183) -> (22,182,182) and the tile count of predict_dense on a (3,58,326,326) image."""
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200.neuromancer import dense
+    nm.model_manager.reset()
+    try:
+        image = nm.Input((10, 3, 23, 183, 183), 'b,f,z,x,y', name='image')
+        conv0 = nm.Conv(image, 32, (1, 6, 6), (1, 2, 2))
+        conv1 = nm.Conv(conv0, 64, (4, 6, 6), (2, 2, 2))
+        conv2 = nm.Conv(conv1, 5, (3, 3, 3), (1, 1, 1), activation_func='lin')
+        class_probs = nm.Softmax(conv2)
+        target = nm.Input_like(class_probs, override_f=1, name='target', dtype='int16')
+        voxel_loss = nm.MultinoulliNLL(class_probs, target, target_is_sparse=True)
+        scalar_loss = nm.AggregateLoss(voxel_loss, name='loss')
+        errors = nm.Errors(class_probs, target, target_is_sparse=True)
+        model = nm.model_manager.getmodel()
+        model.designate_nodes(input_node=image, target_node=target, loss_node=scalar_loss, prediction_node=class_probs,
+                              prediction_ext=[scalar_loss, errors, class_probs])
+        out = capsys.readouterr().out
+        for line in [                                                       # docs/examples.rst:100-140, verbatim
+            "<Input-Node> 'image'", "Out:[(10,b), (3,f), (23,z), (183,x), (183,y)]",
+            "#Params=3,488 Comp.Cost=25.2 Giga Ops, Out:[(10,b), (32,f), (23,z), (89,x), (89,y)]",
+            "n_f=32, 3d conv, kernel=(1, 6, 6), pool=(1, 2, 2), act='relu',",
+            "#Params=294,976 Comp.Cost=416.2 Giga Ops, Out:[(10,b), (64,f), (10,z), (42,x), (42,y)]",
+            "n_f=64, 3d conv, kernel=(4, 6, 6), pool=(2, 2, 2), act='relu',",
+            "#Params=8,645 Comp.Cost=1.1 Giga Ops, Out:[(10,b), (5,f), (8,z), (40,x), (40,y)]",
+            "n_f=5, 3d conv, kernel=(3, 3, 3), pool=(1, 1, 1), act='lin',",
+            "<Softmax-Node> 'softmax'", "Comp.Cost=640.0 kilo Ops, Out:[(10,b), (5,f), (8,z), (40,x), (40,y)]",
+            "<MultinoulliNLL-Node> 'nll'", "Comp.Cost=640.0 kilo Ops, Out:[(10,b), (1,f), (8,z), (40,x), (40,y)]",
+            "Order of sources=['image', 'target'],",
+            "<AggregateLoss-Node> 'loss'", "Comp.Cost=128.0 kilo Ops, Out:[(1,f)]", "<_Errors-Node> 'errors'",
+            "Prediction properties:", "[(10,b), (5,f), (8,z), (40,x), (40,y)]",
+            "fov=[9, 27, 27], offsets=[4, 13, 13], strides=[2 4 4], spatial shape=[8, 40, 40]",
+            "Total Computational Cost of Model: 442.5 Giga Ops", "Total number of trainable parameters: 307,109.",
+            "Computational Cost per pixel: 34.6 Mega Ops",
+        ]:
+            assert line in out, line
+        # docs/examples.rst:176-183: the dict interface
+        assert repr(model) == "['image', 'conv', 'conv1', 'conv2', 'softmax', 'target', 'nll', 'loss', 'cls for errors', 'errors']"
+        assert model['nll'] == voxel_loss
+        assert conv2.shape.ext_repr == ('[(10,b), (5,f), (8,z), (40,x), (40,y)]\nfov=[9, 27, 27], offsets=[4, 13, 13], '
+                                        'strides=[2 4 4], spatial shape=[8, 40, 40]')
+        # docs/examples.rst:197-209: MFP needs a different patch size, the closest possible one is selected
+        mp = nm.rebuild_model(model, imposed_batch_size=1, override_mfp_to_active=True)
+        assert mp.input_node.shape.shape == [1, 3, 22, 182, 182]
+        # docs/examples.rst:214-218: "Predicting img (3, 58, 326, 326) in 16 Blocks: (4, 2, 2)" -- the shape in that message
+        # is the image after pad_raw added the offsets (4,13,13) on both sides (node_basic.py:930-937, 958-959)
+        _, prob_sh, pred_sh, n_tiles = dense.tile_geometry(mp.prediction_node, (58, 326, 326))
+        assert list(pred_sh) == [50, 300, 300] and list(prob_sh) == [14, 156, 156]
+        assert list(n_tiles) == [4, 2, 2] and int(np.prod(n_tiles)) == 16
+    finally:
+        nm.model_manager.reset()
