@@ -15,6 +15,8 @@ class _Config(object):
     use_cuda_graph = True
     # pooling backward tie rule: 'first' (cuDNN-like single winner) or 'all' (Theano CPU)
     pool_tie_mode = 'first'
+    # Model.time_per_step / loss_smooth average over this many steps (elektronn2/config.py:77)
+    time_per_step_smoothing_length = 50
 
 
 config = _Config()

@@ -508,6 +508,11 @@ class Plan(object):
         if nll and nll[0].pred is not sm:
             raise NotImplementedError("MultinoulliNLL must consume the planned Softmax node")
         self.loss_op = ops.LossOp(self.h, logits, target, probs)
+        agg = [n for n in self.nodes if isinstance(n, loss_nodes.AggregateLoss)]
+        if agg:
+            # one component: loss = w * mean(nll) (loss.py:1355-1363).  The weight is read when the plan is built;
+            # ``Model.mixing = ...`` drops the training plans so that the next step is planned with the new value
+            self.loss_op.weight = float(np.asarray(agg[0].mixing_weights.get_value(), np.float64).reshape(-1)[0])
         self.logits_node = sm.parent
         self._f('softmax_nll_fwd', self.loss_op.fwd, 0, 4 * (2 * _nel(logits) + logits.desc.positions))
 
@@ -526,7 +531,7 @@ class Plan(object):
         for n, (cat, c0) in self.alias_of.items():
             self.grad[n] = self.grad[cat].channel_slice(c0, n.shape['f'])
         lg = self.logits_node
-        self._b('softmax_nll_bwd', lambda: self.loss_op.bwd(self.grad[lg], self.grad_scale), 0,
+        self._b('softmax_nll_bwd', lambda: self.loss_op.bwd(self.grad[lg], self.grad_scale * self.loss_op.weight), 0,
                 4 * 3 * _nel(self.grad[lg]))
         written.add(lg)
         # A Crop contributes to only part of its parent's gradient.  Emitted first it would have to

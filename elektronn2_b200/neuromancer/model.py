@@ -37,7 +37,10 @@ class Model(object):
         self.ndim = None
         self.iterations = 0
         self.elapsed_time = 0.0
-        self._last_exec_times, self._last_losses = [], []
+        from collections import deque
+        from ..config import config as _cfg
+        n_smooth = int(getattr(_cfg, 'time_per_step_smoothing_length', 50))      # config.py:77 (CircularBuffer, model.py:70-73)
+        self._last_exec_times, self._last_losses = deque(maxlen=n_smooth), deque(maxlen=n_smooth)
         self._store = None
         self._train_plans, self._ext_plans = {}, {}
         self.data_parallel = None  # set by parallel.DataParallel
@@ -106,6 +109,102 @@ class Model(object):
     def _say(text):
         logger.info(text)
         print(text)
+
+    # -- training state the interactive shell / trainer read and set (model.py:257-546) -----------
+    def _first_optimiser(self):
+        if not self.optimisers:
+            raise RuntimeError("no optimisers: designate a loss_node first")
+        return list(self.optimisers.values())[0]
+
+    def set_opt_meta_params(self, opt_name, value_dict):
+        self.optimisers[opt_name].set_opt_meta_params(value_dict)
+
+    lr = property(lambda self: self._first_optimiser().global_lr.get_value(),
+                  lambda self, val: self._first_optimiser().setlr(val), doc="learning rate (model.py:281-293)")
+    mom = property(lambda self: self._first_optimiser().global_mom.get_value(),
+                   lambda self, val: self._first_optimiser().setmom(val), doc="momentum (model.py:295-307)")
+    wd = property(lambda self: self._first_optimiser().global_weight_decay.get_value(),
+                  lambda self, val: self._first_optimiser().setwd(val), doc="weight decay (model.py:309-321)")
+
+    def _aggregate_loss_node(self):
+        from .loss import AggregateLoss
+        if isinstance(self.loss_node, AggregateLoss):
+            return self.loss_node
+        for n in self.nodes.values():
+            if isinstance(n, AggregateLoss):
+                logger.info("model.loss_node is not of type AggregateLoss and hence has no mixing_weights. "
+                            "But '%s' is, so this is used." % n.name)
+                return n
+        logger.error("no mixing_weights found in model")
+        return None
+
+    @property
+    def mixing(self):
+        """Mixing weights of the AggregateLoss (model.py:323-342)."""
+        n = self._aggregate_loss_node()
+        return None if n is None else n.mixing_weights.get_value()
+
+    @mixing.setter
+    def mixing(self, val):
+        n = self._aggregate_loss_node()
+        if n is not None:
+            n.mixing_weights.set_value(np.asarray(val, np.float32))
+            self._train_plans.clear()       # the weight is folded into the planned loss head (executor._plan_loss_head)
+            for node in self.nodes.values():
+                node._plans.clear()
+
+    def _rates(self, key):
+        return [n.params[key] for n in self.nodes.values() if n.params.get(key, None)]
+
+    def _set_rates(self, key, rates):
+        for i, r in enumerate(self._rates(key)):
+            r.set_value(np.float32(rates[i] if isinstance(rates, (tuple, list, np.ndarray)) else rates))
+
+    # dropout / gradnet nodes are outside the B200 hot path (their constructors raise), so these are empty here
+    dropout_rates = property(lambda self: np.array([r.get_value() for r in self._rates('dropout_rate')]),
+                             lambda self, rates: self._set_rates('dropout_rate', rates), doc="model.py:358-386")
+    gradnet_rates = property(lambda self: [r.get_value() for r in self._rates('gradnet_rate')],
+                             lambda self, rates: self._set_rates('gradnet_rate', rates), doc="model.py:388-433")
+
+    @property
+    def batch_normalisation_active(self):
+        """model.py:435-446."""
+        return any(getattr(n, 'batch_normalisation', None) in ('train', 'fadeout') for n in self.nodes.values())
+
+    @property
+    def debug_output_names(self):
+        return [x.name for x in self.debug_outputs] if self.debug_outputs else None
+
+    @property
+    def prediction_feature_names(self):
+        return self.prediction_node.feature_names if self.prediction_node is not None else None
+
+    @property
+    def loss_input_shapes(self):
+        """Shapes of the loss node's input nodes (model.py:511-523)."""
+        return [s.shape for s in self.loss_node.input_nodes]
+
+    @property
+    def time_per_step(self):
+        """Mean run time of the last ``config.time_per_step_smoothing_length`` training steps (model.py:525-534)."""
+        return float(np.mean(self._last_exec_times)) + 1e-6 if self._last_exec_times else 1e-6
+
+    @property
+    def loss_smooth(self):
+        return float(np.mean(self._last_losses)) if self._last_losses else 0.0
+
+    def paramstats(self):
+        print("Parameter statistics")
+        for k, W in self.loss_node.all_trainable_params.items():
+            W = W.get_value()
+            print("Param %s:\tshape=%s,\tmean=%f,\tstd=%f,\tmedian(abs)=%f"
+                  % (k, W.shape, W.mean(), W.std(), np.median(np.abs(W))))
+
+    def gradstats(self, *args, **kwargs):
+        grads = self.gradients(*args, **kwargs)
+        print("Gradient statistics")
+        for g in grads:
+            print("\tshape=%s,\tmean=%f,\tstd=%f,\tmedian(abs)=%f" % (g.shape, np.mean(g), np.std(g), np.median(np.abs(g))))
 
     # -- parameters ------------------------------------------------------------------
     def _all_named_params(self):

@@ -237,6 +237,19 @@ class Node(object, metaclass=_MetaNode):
     def all_computational_cost(self):
         return int(sum(n.computational_cost for n in self.ancestors()))
 
+    @property
+    def feature_names(self):
+        """Names of the features on the 'f' axis (node_basic.py:787-802)."""
+        return self._features_names if self._features_names else None
+
+    @feature_names.setter
+    def feature_names(self, value):
+        if 'f' not in self.shape.tags:
+            raise ValueError("Shape has no feature tag")
+        if len(value) != self.shape['f']:
+            raise ValueError("Shape has %i features, but %i names were given" % (self.shape['f'], len(value)))
+        self._features_names = tuple(value)
+
     def get_param_values(self, skip_const=False):
         return OrderedDict((k, p.get_value()) for k, p in self.params.items() if not (skip_const and p.constant))
 

@@ -322,6 +322,7 @@ class LossOp(object):
     def __init__(self, h, logits, target, probs):
         self.h, self.logits, self.target, self.probs = h, logits, target, probs
         self.scalars = _dev_f32(4, logits.buf.device)
+        self.weight = 1.0     # AggregateLoss mixing weight of this (single) component: loss = w * mean(nll) (loss.py:1355-1363)
 
     def fwd(self):
         self.h.call('e2_softmax_nll_fwd', C.byref(self.logits.desc), self.logits.ptr(),
@@ -336,7 +337,7 @@ class LossOp(object):
         """(loss, error_rate) -- one D2H copy of 4 floats."""
         s = self.scalars.cpu().numpy()
         n_pos = self.logits.desc.positions
-        return float(s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
+        return float(self.weight * s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
 
     def read_async(self):
         """Enqueue the D2H copy of the 4 scalars behind the work submitted so far; ``read_wait`` blocks on that
@@ -351,7 +352,7 @@ class LossOp(object):
         self._ev.synchronize()
         s = self._host.numpy()
         n_pos = self.logits.desc.positions
-        return float(s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
+        return float(self.weight * s[0] / (s[1] + self.EPS)), float(s[2] / n_pos)
 
 
 def act_bwd(h, t, act, y, dy, dpre):

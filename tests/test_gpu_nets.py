@@ -457,3 +457,22 @@ def test_reference_written_mdl_predicts_like_the_oracle(compute):
         assert a.shape == b.shape and np.abs(a - b).max() <= (2e-6 if compute == 'f32' else 1e-3)
     finally:
         config.compute = 'tf32'
+
+
+def test_mixing_weight_scales_loss_and_gradients():
+    """AggregateLoss: loss = w * mean(nll) (loss.py:1355-1363).  ``model.mixing = [0.5]`` (model.py:344-356) re-plans the
+    training step; halving is exact in fp32, so the loss and every parameter gradient are exactly half."""
+    _cuda()
+    m = build('neuro3d_lite')
+    x, t = data_for(m)
+    l1 = float(m.loss(x, t))
+    g1 = m.gradients(x, t)
+    assert np.allclose(m.mixing, [1.0])
+    m.mixing = [0.5]
+    l2 = float(m.loss(x, t))
+    g2 = m.gradients(x, t)
+    assert np.isclose(l2, 0.5 * l1, rtol=1e-6)
+    for a, b in zip(g1, g2):
+        assert rel(b, 0.5 * a) <= 1e-6
+    loss, _, _ = m.trainingstep(x, t, optimiser='Adam')
+    assert np.isclose(float(loss), 0.5 * l1, rtol=1e-6)

@@ -491,3 +491,48 @@ def test_docs_walkthrough_prints_what_the_reference_prints(capsys):
         assert list(n_tiles) == [4, 2, 2] and int(np.prod(n_tiles)) == 16
     finally:
         nm.model_manager.reset()
+
+
+def test_model_training_state_properties():
+    """Model.lr / mom / wd / mixing / time_per_step / loss_smooth / ... (model.py:257-546): what the reference's trainer and
+    interactive shell read and set between trainingstep calls."""
+    from elektronn2_b200 import neuromancer as nm
+    from elektronn2_b200.neuromancer import optimiser
+    nm.model_manager.reset()
+    old = (optimiser.Optimiser.global_lr.get_value(), optimiser.Optimiser.global_mom.get_value(),
+           optimiser.Optimiser.global_weight_decay.get_value())
+    try:
+        inp = nm.Input((1, 1, 8, 20, 20), 'b,f,z,x,y', name='raw', print_repr=False)
+        c = nm.Conv(inp, 4, (1, 3, 3), (1, 1, 1), print_repr=False)
+        out = nm.Conv(c, 2, (1, 1, 1), (1, 1, 1), activation_func='lin', print_repr=False)
+        probs = nm.Softmax(out, print_repr=False)
+        target = nm.Input_like(probs, override_f=1, name='target', print_repr=False)
+        nll = nm.MultinoulliNLL(probs, target, target_is_sparse=True, print_repr=False)
+        loss = nm.AggregateLoss(nll, name='loss', print_repr=False)
+        model = nm.model_manager.getmodel()
+        model.designate_nodes(input_node=inp, target_node=target, loss_node=loss, prediction_node=probs)
+        model.lr, model.mom, model.wd = 1e-3, 0.8, 5e-4
+        assert np.isclose(model.lr, 1e-3) and np.isclose(model.mom, 0.8) and np.isclose(model.wd, 5e-4)
+        assert np.isclose(model.optimisers['Adam'].global_lr.get_value(), 1e-3)        # class-level, optimiser.py:19-55
+        model.set_opt_meta_params('Adam', dict(lr=2e-3))
+        assert np.isclose(model.lr, 2e-3)
+        assert np.allclose(model.mixing, [1.0])
+        model._train_plans[1] = object()
+        model.mixing = [0.5]
+        assert np.allclose(loss.mixing_weights.get_value(), [0.5]) and not model._train_plans    # re-planned with the new weight
+        assert model.dropout_rates.size == 0 and model.gradnet_rates == []
+        assert model.batch_normalisation_active is False
+        assert model.debug_output_names is None and model.prediction_feature_names is None
+        probs.feature_names = ['bg', 'fg']
+        assert model.prediction_feature_names == ('bg', 'fg')
+        with pytest.raises(ValueError):
+            probs.feature_names = ['one']
+        assert [list(s.shape) for s in model.loss_input_shapes] == [[1, 1, 8, 20, 20], [1, 1, 8, 18, 18]]
+        for i in range(120):                                                            # bounded smoothing window
+            model._last_exec_times.append(1.0 if i >= 70 else 100.0)
+            model._last_losses.append(float(i))
+        assert len(model._last_exec_times) == 50 and np.isclose(model.time_per_step, 1.0 + 1e-6)
+        assert np.isclose(model.loss_smooth, np.mean(np.arange(70, 120)))
+    finally:
+        optimiser.Optimiser.setlr(old[0]), optimiser.Optimiser.setmom(old[1]), optimiser.Optimiser.setwd(old[2])
+        nm.model_manager.reset()
