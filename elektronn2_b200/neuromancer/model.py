@@ -302,6 +302,11 @@ class Model(object):
     def test_run_prediction(self):
         return self.prediction_node.test_run()
 
+    def measure_exectimes(self, n_samples=5, n_warmup=4, print_info=True):
+        """OrderedDict node name -> execution time in ms (model.py:608-619); see ``Node.measure_exectime``."""
+        return OrderedDict((name, node.measure_exectime(n_samples=n_samples, n_warmup=n_warmup, print_info=print_info))
+                           for name, node in self.nodes.items())
+
     # -- persistence: the reference's .mdl format (model.py:229-235; graphmanager.py) -----
     def save(self, file_name):
         """Pickle ``(descriptors, desig_descr)`` exactly as the reference's ``Model.save`` does, so the file loads

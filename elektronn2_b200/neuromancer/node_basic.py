@@ -314,6 +314,57 @@ class Node(object, metaclass=_MetaNode):
             logger.warning("Shape of computed output and shape calculated by layer definition not match")
         return y
 
+    def measure_exectime(self, n_samples=5, n_warmup=4, print_info=True, local=True, nonegative=True):
+        """Time this node's computation in milliseconds (node_basic.py:1092-1176).  The reference compiles the node's
+        function under Theano's profiler, sums the op times and, for ``local=True``, subtracts its parents' totals.
+        Here every kernel launch of the node's plan is bracketed by CUDA events on the launching stream
+        (``executor.Plan.profile``): the total is the sum over the plan's launches, the local time is the sum over
+        the launches that belong to this node (a pool computed in its conv's epilogue costs its Pool node nothing)."""
+        inp = self.input_nodes
+        if not inp:
+            logger.info('Node {} has no inputs -> skipping node, giving it zero execution time.'.format(self.name))
+            return 0.0
+        vals = []
+        for i in inp:
+            sh = [1 if s_ is None else s_ for s_ in i.shape.shape]
+            vals.append(np.random.rand(*sh).astype(i.dtype))
+        plan = self._plan_for(np.shape(vals[0])[0])
+        plan.feed(dict(zip(inp, vals)))
+        for _ in range(max(1, int(n_warmup))):                      # at least once: commits the inputs to the device
+            plan.execute()
+        samples = np.zeros((max(1, int(n_samples)), 2))
+        for k in range(samples.shape[0]):
+            rows = plan.profile(repeats=1)
+            samples[k, 0] = sum(ms for (_, _, _, _, ms) in rows)
+            samples[k, 1] = sum(ms for (label, _, _, _, ms) in rows if self._owns_launch(label))
+        self._total_exec_time = float(np.median(samples[:, 0]))
+        self._local_exec_time = float(np.median(samples[:, 1]))
+        t = self._local_exec_time if local else self._total_exec_time
+        if nonegative and t < 0:
+            t = 0.0
+        if print_info:
+            logger.info('{0} samples in ms:\n{1}\n{0}: median execution time: {2} ms\n'
+                        .format(self.name, samples[:, 1 if local else 0], t))
+        return t
+
+    def _owns_launch(self, label):
+        kind, _, name = label.partition(':')
+        if name:
+            return name == self.name
+        return kind.startswith('softmax') and type(self).__name__ == 'Softmax'      # the fused loss head
+
+    @property
+    def local_exec_time(self):
+        if getattr(self, '_local_exec_time', None) is None:
+            self.measure_exectime(print_info=False, local=True)
+        return self._local_exec_time
+
+    @property
+    def total_exec_time(self):
+        if getattr(self, '_total_exec_time', None) is None:
+            self.measure_exectime(print_info=False, local=True)
+        return self._total_exec_time
+
     def predict_dense(self, raw_img, as_uint8=False, pad_raw=False):
         """Tiled dense inference (node_basic.py:860-1012); see ``dense.predict_dense``."""
         from .dense import predict_dense

@@ -476,3 +476,19 @@ def test_mixing_weight_scales_loss_and_gradients():
         assert rel(b, 0.5 * a) <= 1e-6
     loss, _, _ = m.trainingstep(x, t, optimiser='Adam')
     assert np.isclose(float(loss), 0.5 * l1, rtol=1e-6)
+
+
+def test_measure_exectime_per_node():
+    """Node.measure_exectime / Model.measure_exectimes (node_basic.py:1092-1176, model.py:608-619) on CUDA events: the
+    local time of a node is the time of its own launches, the total the time of everything its output needs."""
+    _cuda()
+    m = build('neuro3d_lite')
+    convs = [n for n in m.nodes.values() if type(n).__name__ == 'Conv']
+    deep = convs[3]
+    t_local = deep.measure_exectime(n_samples=3, n_warmup=2, print_info=False, local=True)
+    t_total = deep.measure_exectime(n_samples=3, n_warmup=2, print_info=False, local=False)
+    assert 0.0 < t_local < t_total and deep.local_exec_time > 0 and deep.total_exec_time >= deep.local_exec_time
+    assert m.input_node.measure_exectime(print_info=False) == 0.0                  # source nodes: zero, as in the reference
+    times = m.measure_exectimes(n_samples=1, n_warmup=1, print_info=False)
+    assert list(times.keys()) == list(m.nodes.keys())
+    assert all(times[c.name] > 0 for c in convs)
