@@ -329,6 +329,9 @@ class Node(object, metaclass=_MetaNode):
             sh = [1 if s_ is None else s_ for s_ in i.shape.shape]
             vals.append(np.random.rand(*sh).astype(i.dtype))
         plan = self._plan_for(np.shape(vals[0])[0])
+        if not plan.fwd_ops:                                           # nothing to launch (e.g. a pure view of an input)
+            self._total_exec_time = self._local_exec_time = 0.0
+            return 0.0
         plan.feed(dict(zip(inp, vals)))
         for _ in range(max(1, int(n_warmup))):                      # at least once: commits the inputs to the device
             plan.execute()
