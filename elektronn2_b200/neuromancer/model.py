@@ -330,6 +330,18 @@ def modelload(file_name, override_mfp_to_active=False, imposed_patch_size=None, 
     return graphmanager.load_model(file_name, override_mfp_to_active, imposed_patch_size, imposed_batch_size, name)
 
 
+def params_from_model_file(file_name):
+    """OrderedDict node name -> parameter values of a ``.mdl`` file, without building the model (model.py:897-911)."""
+    from . import graphmanager
+    logger.info("Extracting parameters from %s" % file_name)
+    node_descr, _ = graphmanager._load_all(file_name)
+    params = OrderedDict()
+    for name, descr in node_descr.items():
+        if isinstance(descr, (list, tuple)) and len(descr[1]):
+            params[name] = descr[1]
+    return params
+
+
 def kernel_lists_from_node_descr(model):
     """(filter_shapes, pool_shapes, mfp) of the Conv nodes in graph order (model.py:871-895)."""
     f, p, m = [], [], []

@@ -386,6 +386,12 @@ def test_modelload_reads_a_file_written_by_the_reference_serialiser():
     # the stream carries the reference's module paths, none of this package's
     raw = open(os.path.join(golden, 'ref_written_small.mdl'), 'rb').read()
     assert b'elektronn2.neuromancer.graphmanager' in raw and b'elektronn2_b200' not in raw
+    # params_from_model_file (model.py:897-911): the weights without building the model
+    pf = nm.params_from_model_file(os.path.join(golden, 'ref_written_small.mdl'))
+    assert list(pf.keys()) == ['conv', 'conv1', 'conv2', 'conv3', 'loss']
+    for node_name in ['conv', 'conv1', 'conv2', 'conv3']:
+        for k, v in pf[node_name].items():
+            assert np.array_equal(v, m.nodes[node_name].params[k].get_value()), (node_name, k)
 
 
 def test_f4_nodes_parameters_and_shapes():
