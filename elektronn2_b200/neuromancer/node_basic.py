@@ -210,6 +210,20 @@ class Node(object, metaclass=_MetaNode):
         return [n for n in self.model.nodes.values() if id(n) in seen]
 
     @property
+    def all_parents(self):
+        """OrderedDict name -> node of this node and everything it depends on (node_basic.py:628-648)."""
+        return OrderedDict((n.name, n) for n in self.ancestors())
+
+    @property
+    def all_children(self):
+        """OrderedDict name -> node of everything computed from this node (node_basic.py:757-765)."""
+        out = OrderedDict()
+        for child in self.children.values():
+            out[child.name] = child
+            out.update(child.all_children)
+        return out
+
+    @property
     def param_count(self):
         return int(sum(np.prod(p.shape) for p in self.params.values() if p.apply_train))
 

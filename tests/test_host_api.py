@@ -484,6 +484,8 @@ def test_docs_walkthrough_prints_what_the_reference_prints(capsys):
             assert line in out, line
         # docs/examples.rst:176-183: the dict interface
         assert repr(model) == "['image', 'conv', 'conv1', 'conv2', 'softmax', 'target', 'nll', 'loss', 'cls for errors', 'errors']"
+        assert list(conv1.all_parents.keys()) == ['image', 'conv', 'conv1']              # node_basic.py:628-648
+        assert list(conv2.all_children.keys()) == ['softmax', 'nll', 'loss', 'cls for errors', 'errors']
         assert model['nll'] == voxel_loss
         assert conv2.shape.ext_repr == ('[(10,b), (5,f), (8,z), (40,x), (40,y)]\nfov=[9, 27, 27], offsets=[4, 13, 13], '
                                         'strides=[2 4 4], spatial shape=[8, 40, 40]')
