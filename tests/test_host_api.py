@@ -231,6 +231,11 @@ def test_zstack_planner_invariants():
     assert fn(148, 768, 256, 12, 16, 16, 3, 3, 3, 1, out) == 1 and out[2] > 1
     assert fn(148, 32, 64, 112, 128, 128, 3, 3, 3, 1, out) == 1 and out[2] == 1      # 3584 tiles: never split
     assert fn(148, 256, 512, 7, 9, 9, 3, 3, 3, 1, out) == 0                          # 9x9 planes: tap kernel
+    # neuro3d's N = 100 layers (dense-prediction tile): one N tile of 112 with two output planes per tile fits since the
+    # epilogue warps share one bias tile when there is a single N tile (two N tiles of 64 used 78 % of the columns)
+    for K in (80, 100):
+        assert fn(148, K, 100, 21, 83, 83, 3, 4, 4, 0, out) == 1
+        assert (out[0], out[1], out[7]) == (112, 2, 1), list(out)
 
 
 def test_zstack_pool_fusion_plans():
